@@ -1,0 +1,309 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the osu-dreamer denoiser hot path.
+
+A functional, state-dict driven torch-CPU restatement (channels-first, fp32 or
+fp64) of the reference's `DiffusionModel` / `DiffusionTrainer.forward`
+arithmetic.  Nothing in the product package may import this file: only
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / reference
+arm do, and only as the checker / the reported CPU baseline.
+
+Pinned against golden vectors produced by importing the UNMODIFIED reference
+(`oracle/make_golden.py`, fixtures in `tests/golden/`); the reference itself
+ships no tests or golden vectors for this path, so those
+reference-generated fixtures are what pins the oracle.
+
+Each function cites the reference file:line (relative to the reference repo
+root) it restates.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+# ----------------------------------------------------------------------------
+# hyper-parameters (osu_dreamer/models/diffusion/model.yml:77-90)
+# ----------------------------------------------------------------------------
+HP = dict(emb_dim=6, a_dim=128, style_dim=32, cg_dim=512, dim=512, head_dim=64,
+          n_heads=16, depth=8, expand=4, radius=2, u_dim=64)
+
+
+def constants(emb_dim: int = 6) -> Tuple[float, float]:
+    """c0, u_scale -- osu_dreamer/models/diffusion/model.py:35-43."""
+    d0_sq = 2.0 * emb_dim
+    t99 = torch.tensor(2.3263478740408408).sigmoid().item()
+    return (1 - t99) ** 2 * d0_sq, math.sqrt(d0_sq)
+
+
+def state_dict_spec(hp=HP):
+    """(name, shape, kind) in reference state-dict order.
+    kind: 'w' weight (fan-in = prod(shape[1:])), 'b' bias, 'g' norm gain."""
+    E, A, S, Cg, D = hp['emb_dim'], hp['a_dim'], hp['style_dim'], hp['cg_dim'], hp['dim']
+    dh = hp['n_heads'] * hp['head_dim']
+    Hd = int(D * hp['expand'] * 2 / 3)  # osu_dreamer/common/swiglu.py:18
+    k = 1 + 2 * hp['radius']
+    U = hp['u_dim']
+    spec = [
+        ('proj_audio.0.weight', (A, A, 1), 'w'), ('proj_audio.0.bias', (A,), 'b'),
+        ('proj_style.0.weight', (Cg, S), 'w'), ('proj_style.0.bias', (Cg,), 'b'),
+        ('proj_in.weight', (D, E, 1), 'w'), ('proj_in.bias', (D,), 'b'),
+    ]
+    for i in range(hp['depth']):
+        p = f'net.layers.{i}.'
+        spec += [
+            (p + 'ssg1.weight', (3 * D, Cg), 'w'), (p + 'ssg1.bias', (3 * D,), 'b'),
+            (p + 'proj_cl.weight', (D, A, 1), 'w'), (p + 'proj_cl.bias', (D,), 'b'),
+            (p + 'attn.qkv_proj.weight', (3 * dh, D, 1), 'w'), (p + 'attn.qkv_proj.bias', (3 * dh,), 'b'),
+            (p + 'attn.out_proj.weight', (D, dh, 1), 'w'), (p + 'attn.out_proj.bias', (D,), 'b'),
+            (p + 'attn.q_norm.weight', (hp['head_dim'],), 'g'),
+            (p + 'attn.k_norm.weight', (hp['head_dim'],), 'g'),
+            (p + 'ssg2.weight', (3 * D, Cg), 'w'), (p + 'ssg2.bias', (3 * D,), 'b'),
+            (p + 'ffn.proj_vg.0.weight', (D, 1, k), 'w'), (p + 'ffn.proj_vg.0.bias', (D,), 'b'),
+            (p + 'ffn.proj_vg.1.weight', (2 * Hd, D, 1), 'w'), (p + 'ffn.proj_vg.1.bias', (2 * Hd,), 'b'),
+            (p + 'ffn.proj_o.weight', (D, Hd, 1), 'w'), (p + 'ffn.proj_o.bias', (D,), 'b'),
+        ]
+    spec += [
+        ('proj_out.weight', (E, D, 1), 'w'), ('proj_out.bias', (E,), 'b'),
+        ('u_head.0.weight', (E, 1, 3), 'w'), ('u_head.0.bias', (E,), 'b'),
+        ('u_head.1.weight', (U, E, 1), 'w'), ('u_head.1.bias', (U,), 'b'),
+        ('u_head.3.weight', (U, 1, 3), 'w'), ('u_head.3.bias', (U,), 'b'),
+        ('u_head.4.weight', (U, U, 1), 'w'), ('u_head.4.bias', (U,), 'b'),
+        ('u_mod.weight', (2 * U, Cg), 'w'), ('u_mod.bias', (2 * U,), 'b'),
+        ('u_out.weight', (1, U), 'w'), ('u_out.bias', (1,), 'b'),
+    ]
+    return spec
+
+
+def make_state_dict(seed: int = 1234, dtype=torch.float32, hp=HP) -> SD:
+    """Deterministic NON-DEGENERATE weights for parity tests.
+
+    The reference zero-initialises 37 tensors (backbone.py:12-16, model.py:51-53,
+    66-68) which makes default-init parity vacuous (SURVEY.md 7 hard part 1), so
+    every tensor is drawn from a seeded CPU generator instead: weights
+    N(0, 1/fan_in), biases N(0, 0.02^2) (modulation biases included), norm
+    gains 1 + N(0, 0.1^2).  Reproducible on any host with the same torch build.
+    """
+    g = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+    for name, shape, kind in state_dict_spec(hp):
+        if kind == 'w':
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            t = torch.randn(shape, generator=g) * fan_in ** -0.5
+        elif kind == 'b':
+            t = torch.randn(shape, generator=g) * 0.02
+        else:
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        if name == 'u_out.bias':
+            t = t - 0.4328  # keep the reference's operating point (model.py:71)
+        sd[name] = t.to(dtype)
+    return sd
+
+
+def make_inputs(B: int, L: int, seed: int = 7, dtype=torch.float32, a_batch: int | None = None):
+    """Seeded synthetic inputs: audio features h [B,128,L],
+    per-frame RMS-normalised latent x1 [B,6,L] (models/latent/model.py:62-65),
+    RMS-normalised style s [B,32] (:55-59), noise x0 [B,6,L], times t [B]."""
+    g = torch.Generator().manual_seed(seed)
+    Ba = B if a_batch is None else a_batch
+    h = torch.randn(Ba, 128, L, generator=g)
+    x1 = torch.randn(B, 6, L, generator=g)
+    x1 = x1 * x1.pow(2).mean(1, keepdim=True).add(1e-6).rsqrt()
+    s = torch.randn(B, 32, generator=g)
+    s = s * s.pow(2).mean(1, keepdim=True).add(1e-6).rsqrt()
+    x0 = torch.randn(B, 6, L, generator=g)
+    t = torch.rand(B, generator=g)
+    return dict(h=h.to(dtype), x1=x1.to(dtype), s=s.to(dtype), x0=x0.to(dtype), t=t.to(dtype))
+
+
+# ----------------------------------------------------------------------------
+# ops
+# ----------------------------------------------------------------------------
+def rms_norm(x: Tensor, gamma: Tensor | None = None) -> Tensor:
+    """osu_dreamer/common/rms_norm.py:7-16 -- normalise over dim=1, eps 1e-6."""
+    xf = x.float() if x.dtype != torch.float64 else x
+    inv = xf.pow(2).mean(dim=1, keepdim=True).add(1e-6).rsqrt()
+    n = (xf * inv).to(x.dtype)
+    if gamma is not None:
+        n = n * gamma[:, None]
+    return n
+
+
+def head_rms_norm(x: Tensor, weight: Tensor) -> Tensor:
+    """nn.RMSNorm(head_dim) applied to `q.float()` with eps=None -> finfo(fp32).eps, then
+    `.type_as(q)` (common/attn.py:71-72,77-78): the statistic is ALWAYS taken in fp32,
+    even when the module runs in fp64."""
+    xf = x.float()
+    eps = torch.finfo(torch.float32).eps
+    n = xf * (xf.pow(2).mean(-1, keepdim=True) + eps).rsqrt()
+    return (n * weight).to(x.dtype)
+
+
+def rope(x: Tensor) -> Tensor:
+    """osu_dreamer/common/attn.py:12-29 -- half-split rotation; the angle table
+    is built in fp32 exactly as the reference does, then cast to x.dtype."""
+    N, D = x.shape[-2], x.shape[-1]
+    inv_freq = 10000 ** (torch.arange(0, D, 2).float() / -D)
+    t = torch.arange(N, dtype=torch.float32)
+    freqs = torch.outer(t, inv_freq)
+    x1, x2 = x.chunk(2, dim=-1)
+    cos = freqs.cos().to(x.dtype)
+    sin = freqs.sin().to(x.dtype)
+    return torch.cat([x1 * cos - x2 * sin, x1 * sin + x2 * cos], dim=-1)
+
+
+def conv1x1(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
+    return torch.einsum('oc,bcl->bol', w[:, :, 0], x) + b[None, :, None]
+
+
+def sdpsa(sd: SD, p: str, x: Tensor, hp=HP) -> Tensor:
+    """osu_dreamer/common/attn.py:74-84."""
+    B, _, L = x.shape
+    H, d = hp['n_heads'], hp['head_dim']
+    qkv = conv1x1(x, sd[p + 'qkv_proj.weight'], sd[p + 'qkv_proj.bias'])
+    qkv = qkv.reshape(B, 3 * H, d, L).permute(0, 1, 3, 2)  # 'b (h d) n -> b h n d'
+    q, k, v = qkv.chunk(3, dim=1)
+    q = head_rms_norm(q, sd[p + 'q_norm.weight'])
+    k = head_rms_norm(k, sd[p + 'k_norm.weight'])
+    q, k = rope(q), rope(k)
+    att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1)
+    y = att @ v
+    y = y.permute(0, 1, 3, 2).reshape(B, H * d, L)  # 'b h n d -> b (h d) n'
+    return conv1x1(y, sd[p + 'out_proj.weight'], sd[p + 'out_proj.bias'])
+
+
+def swiglu(sd: SD, p: str, x: Tensor, hp=HP) -> Tensor:
+    """osu_dreamer/common/swiglu.py:27-32."""
+    r = hp['radius']
+    h = F.conv1d(x, sd[p + 'proj_vg.0.weight'], sd[p + 'proj_vg.0.bias'], padding=r, groups=x.shape[1])
+    vg = conv1x1(h, sd[p + 'proj_vg.1.weight'], sd[p + 'proj_vg.1.bias'])
+    v, g = vg.chunk(2, dim=1)
+    h = rms_norm(v * F.silu(g))
+    return conv1x1(h, sd[p + 'proj_o.weight'], sd[p + 'proj_o.bias'])
+
+
+def backbone_layer(sd: SD, p: str, x: Tensor, cl: Tensor, cg: Tensor, hp=HP) -> Tensor:
+    """osu_dreamer/models/diffusion/backbone.py:69-88."""
+    m = F.linear(cg, sd[p + 'ssg1.weight'], sd[p + 'ssg1.bias'])[:, :, None]
+    scale, shift, gate = m.chunk(3, dim=1)
+    h = rms_norm(x) * (1 + scale) + shift
+    h = sdpsa(sd, p + 'attn.', h + conv1x1(cl, sd[p + 'proj_cl.weight'], sd[p + 'proj_cl.bias']), hp)
+    x = x + rms_norm(h) * gate
+    m = F.linear(cg, sd[p + 'ssg2.weight'], sd[p + 'ssg2.bias'])[:, :, None]
+    scale, shift, gate = m.chunk(3, dim=1)
+    h = rms_norm(x) * (1 + scale) + shift
+    h = swiglu(sd, p + 'ffn.', h, hp)
+    x = x + rms_norm(h) * gate
+    return x
+
+
+def precompute_conditioning(sd: SD, audio: Tensor, style: Tensor):
+    """osu_dreamer/models/diffusion/model.py:73-84."""
+    a = F.silu(conv1x1(audio, sd['proj_audio.0.weight'], sd['proj_audio.0.bias']))
+    cg = F.silu(F.linear(style, sd['proj_style.0.weight'], sd['proj_style.0.bias']))
+    return a, cg
+
+
+def pred(sd: SD, a: Tensor, cg: Tensor, xt: Tensor, hp=HP, taps: dict | None = None):
+    """osu_dreamer/models/diffusion/model.py:86-103 -> (u [B], v [B,E,L])."""
+    _, u_scale = constants(hp['emb_dim'])
+    h = conv1x1(xt, sd['proj_in.weight'], sd['proj_in.bias'])
+    for i in range(hp['depth']):
+        h = backbone_layer(sd, f'net.layers.{i}.', h, a, cg, hp)
+        if taps is not None:
+            taps[f'x{i}'] = h
+    h = rms_norm(h)  # backbone.py:50
+    v = conv1x1(h, sd['proj_out.weight'], sd['proj_out.bias'])
+    E, U = hp['emb_dim'], hp['u_dim']
+    f = F.conv1d(xt, sd['u_head.0.weight'], sd['u_head.0.bias'], padding=1, groups=E)
+    f = F.silu(conv1x1(f, sd['u_head.1.weight'], sd['u_head.1.bias']))
+    f = F.conv1d(f, sd['u_head.3.weight'], sd['u_head.3.bias'], padding=1, groups=U)
+    f = F.silu(conv1x1(f, sd['u_head.4.weight'], sd['u_head.4.bias'])).mean(-1)
+    scale, shift = F.linear(cg, sd['u_mod.weight'], sd['u_mod.bias']).chunk(2, dim=-1)
+    f = f * (1 + scale) + shift
+    u = u_scale * F.softplus(F.linear(f, sd['u_out.weight'], sd['u_out.bias'])).squeeze(-1)
+    return u, v
+
+
+def forward(sd: SD, audio: Tensor, style: Tensor, xt: Tensor, hp=HP, taps=None):
+    """osu_dreamer/models/diffusion/model.py:105-114."""
+    a, cg = precompute_conditioning(sd, audio, style)
+    return pred(sd, a, cg, xt, hp, taps)
+
+
+@torch.no_grad()
+def sample(sd: SD, audio: Tensor, style: Tensor, x_init: Tensor, num_steps: int, hp=HP):
+    """osu_dreamer/models/diffusion/model.py:117-138 with the initial noise
+    passed in (the reference draws it from the global generator at :125)."""
+    c0, _ = constants(hp['emb_dim'])
+    a, cg = precompute_conditioning(sd, audio, style)
+    x = x_init
+    u0 = pred(sd, a, cg, x, hp)[0].mean().item()
+    eta = 1.0 - (math.sqrt(c0) / max(u0, math.sqrt(c0) + 1e-6)) ** (1.0 / num_steps)
+    for _ in range(num_steps):
+        u, v = pred(sd, a, cg, x, hp)
+        x = x - eta * u[:, None, None] * v
+    return x, u0, eta
+
+
+def frame_dist_sq(a: Tensor, b: Tensor) -> Tensor:
+    """osu_dreamer/models/diffusion/train.py:22-31."""
+    return (a - b).square().sum(1).mean(1)
+
+
+def trainer_loss(sd: SD, h: Tensor, x1: Tensor, s: Tensor, x0: Tensor, t: Tensor,
+                 osl_weight: float = 1.0, del_weight: float = 30.0, hp=HP):
+    """osu_dreamer/models/diffusion/train.py:78-108 with the random draws
+    (t, x0) injected instead of taken from the global generator (:79,82)."""
+    c0, _ = constants(hp['emb_dim'])
+    xt = torch.lerp(x0, x1, t[:, None, None])
+    u_pred, v_pred = forward(sd, h, s, xt, hp)
+    d_sq = frame_dist_sq(xt, x1)
+    u_target = (d_sq + c0).sqrt()
+    denoised = xt - u_pred[:, None, None] * v_pred
+    osl = (frame_dist_sq(denoised, x1) / (d_sq + c0)).mean()
+    v_target = (xt - x1) / u_target[:, None, None]
+    del_ = frame_dist_sq(v_pred, v_target).mean()
+    loss = osl_weight * osl + del_weight * del_
+    u_err = ((u_pred - u_target) / u_target).abs().mean()
+    return loss, dict(loss=loss.detach(), osl=osl.detach(), **{'del': del_.detach()}, u_mape=u_err.detach())
+
+
+def stratified_t(B: int, generator=None, device='cpu') -> Tensor:
+    """train.py:79-80 -- stratified logit-normal time draw."""
+    u = (torch.randperm(B, generator=generator, device=device)
+         + torch.rand(B, generator=generator, device=device)) / B
+    return torch.special.ndtri(u.clamp(1e-6, 1 - 1e-6)).sigmoid()
+
+
+def lr_lambda(step: int, warmup_steps: int = 1000, warmup_init: float = 0.3, decay_start: float = 30000):
+    """osu_dreamer/common/lr_schedule.py:10-22."""
+    if step < warmup_steps:
+        return warmup_init ** (1 - step / warmup_steps)
+    elif step > decay_start:
+        return (step / decay_start) ** -0.5
+    return 1.0
+
+
+def adamw_ema_step(p, g, m, v, ema, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.01,
+                   clip_coef=1.0, ema_decay=0.99, ema_first=False):
+    """One AdamW (torch.optim.AdamW defaults, train.py:111) + EMA
+    (swa_utils.get_ema_multi_avg_fn(.99), train.py:67,126) update on flat tensors.
+    `step` is 1-based.  Returns nothing; updates in place."""
+    g = g * clip_coef
+    p.mul_(1 - lr * wd)
+    m.mul_(beta1).add_(g, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-lr / bc1)
+    if ema_first:
+        ema.copy_(p)
+    else:
+        ema.lerp_(p, 1 - ema_decay)
