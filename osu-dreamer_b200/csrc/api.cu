@@ -1,0 +1,39 @@
+// extern "C" surface of libosd_b200.so (declared in include/osd_b200.h).
+#include "../../include/osd_b200.h"
+
+#include "common.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace osd;
+
+extern "C" {
+
+int osd_abi_version(void) { return OSD_ABI_VERSION; }
+const char* osd_last_error(void) { return get_error(); }
+
+int osd_gemm(const void* A, int a_major, int64_t lda, const void* B, int b_major, int64_t ldb, void* C,
+             int64_t ldc, int c_fp32, const float* bias, int M, int N, int K, int elem, int epi, int split_k,
+             void* stream) {
+  OSD_CHECK(epi >= 0 && epi <= 2, "osd_gemm: epi %d not in {0,1,2}", epi);
+  GemmArgs g;
+  g.A = A; g.B = B; g.a_major = a_major; g.b_major = b_major; g.lda = lda; g.ldb = ldb;
+  g.M = M; g.N = N; g.K = K; g.elem = elem; g.epi = epi; g.C = C; g.ldc = ldc; g.c_fp32 = c_fp32;
+  g.bias = bias; g.split_k = split_k;
+  return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+int osd_qkv_proj(const void* x, const void* w, const float* bias, const float* qnorm_w, const float* knorm_w,
+                 const float* rope, void* out, void* raw_out, int T, int L, int elem, void* stream) {
+  GemmArgs g;
+  g.A = x; g.B = w; g.lda = OSD_D; g.ldb = OSD_D; g.M = T; g.N = 3 * OSD_DH; g.K = OSD_D; g.elem = elem;
+  g.epi = EPI_QKV; g.C = out; g.ldc = 3 * OSD_DH; g.c_fp32 = 0; g.bias = bias; g.qnorm_w = qnorm_w;
+  g.knorm_w = knorm_w; g.rope = rope; g.L = L; g.dh = OSD_DH; g.raw_out = raw_out;
+  return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+int osd_rope_table(const float* inv_freq_host, int L, float* rope, void* stream) {
+  return launch_rope_table(inv_freq_host, L, rope, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,387 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : TMEM allocator + UMMA issuer (one elected lane)
+//   warps 2..5  : epilogue (TMEM -> registers -> fused epilogue -> global), lane quadrant = warp % 4
+// Pipelines: smem full/empty ring (TMA <-> UMMA) and a 2-deep TMEM accumulator ring (UMMA <-> epilogue),
+// so the epilogue of work item i overlaps the main loop of item i+1.
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace osd {
+
+static constexpr int BM = 128;
+static constexpr int GEMM_THREADS = 192;
+static constexpr int ROW_BYTES = 128;  // one swizzle row: 64 bf16 or 32 tf32
+
+struct GemmParams {
+  CUtensorMap tma_a;
+  CUtensorMap tma_b;
+  int M, N, K;
+  int a_major, b_major;
+  int num_kb;        // total k-blocks
+  int kb_per_split;  // k-blocks per split
+  int split_k;
+  int tiles_m, tiles_n;
+  int epi;
+  void* C;
+  long long ldc;
+  int c_fp32;
+  const float* bias;
+  const float* qnorm_w;
+  const float* knorm_w;
+  const float* rope;
+  int L;
+  int dh;
+  void* raw_out;
+};
+
+template <int BN, int ELEM>
+struct Cfg {
+  static constexpr int EPR = (ELEM == ELEM_BF16) ? 64 : 32;  // elements per 128-byte row
+  static constexpr int BK = EPR;                             // k-extent of one stage (elements)
+  static constexpr int UMMA_K = EPR / 4;                     // 32 bytes of K per instruction
+  static constexpr int A_BYTES = BM * ROW_BYTES;             // 16 KB
+  static constexpr int B_BYTES = BN * ROW_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulators (power of two: 256 or 512)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int ELEM, bool QKV>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<BN, ELEM>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;
+  uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a);
+    tma_prefetch_desc(&p.tma_b);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_items = p.tiles_m * p.tiles_n * p.split_k;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int split = item % p.split_k;
+        const int tile = item / p.split_k;
+        const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          const int k0 = kb * C::BK;
+          if (p.a_major == MAJOR_K) {
+            tma_load_2d(sa, &p.tma_a, &full_bar[stage], k0, tm * BM);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / C::EPR; ++c)
+              tma_load_2d(sa + c * (C::BK * ROW_BYTES), &p.tma_a, &full_bar[stage], tm * BM + c * C::EPR, k0);
+          }
+          if (p.b_major == MAJOR_K) {
+            tma_load_2d(sb, &p.tma_b, &full_bar[stage], k0, tn * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / C::EPR; ++c)
+              tma_load_2d(sb + c * (C::BK * ROW_BYTES), &p.tma_b, &full_bar[stage], tn * BN + c * C::EPR, k0);
+          }
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== UMMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(ELEM == ELEM_BF16 ? FMT_BF16 : FMT_TF32, p.a_major, p.b_major, BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        const int split = item % p.split_k;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < C::BK / C::UMMA_K; ++k) {
+            // K-major : advance 32 bytes inside the 128-byte swizzle row, 8-row groups 1024 B apart.
+            // MN-major: advance UMMA_K k-rows (128 B each); 64-element MN chunks BK*128 B apart.
+            const uint64_t adesc = (p.a_major == MAJOR_K)
+                                       ? make_smem_desc(sa + k * 32, 0, 1024)
+                                       : make_smem_desc(sa + k * C::UMMA_K * ROW_BYTES, C::BK * ROW_BYTES, 1024);
+            const uint64_t bdesc = (p.b_major == MAJOR_K)
+                                       ? make_smem_desc(sb + k * 32, 0, 1024)
+                                       : make_smem_desc(sb + k * C::UMMA_K * ROW_BYTES, C::BK * ROW_BYTES, 1024);
+            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (ELEM == ELEM_BF16)
+              umma_f16_ss(tmem_d, adesc, bdesc, idesc, accum);
+            else
+              umma_tf32_ss(tmem_d, adesc, bdesc, idesc, accum);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================================================================== epilogue (4 warps)
+    const int quad = warp & 3;
+    int it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const int tile = item / p.split_k;
+      const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int m = tm * BM + quad * 32 + lane;
+      const bool row_ok = m < p.M;
+      const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+
+      if constexpr (QKV) {
+        // 64-column chunks = one attention head of q, k or v
+        const float inv_d = 1.0f / 64.0f;
+        const float eps = 1.1920929e-07f;  // torch.finfo(float32).eps: nn.RMSNorm(eps=None)
+        const int pos = row_ok ? (m % p.L) : 0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          const int n0 = tn * BN + c * 64;
+          uint32_t r0[32], r1[32];
+          __syncwarp();
+          tmem_ld32(trow + c * 64, r0);
+          tmem_ld32(trow + c * 64 + 32, r1);
+          tmem_wait_ld();
+          if (n0 >= p.N) continue;
+          float x[64];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            x[j] = __uint_as_float(r0[j]) + __ldg(p.bias + n0 + j);
+            x[j + 32] = __uint_as_float(r1[j]) + __ldg(p.bias + n0 + 32 + j);
+          }
+          const int which = n0 / p.dh;
+          if (p.raw_out != nullptr && row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.raw_out) + (size_t)m * p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                                  pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+          }
+          if (which < 2) {
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) ss = fmaf(x[j], x[j], ss);
+            const float r = rsqrtf(ss * inv_d + eps);
+            const float* w = which == 0 ? p.qnorm_w : p.knorm_w;
+            const float4* cs = reinterpret_cast<const float4*>(p.rope + (size_t)pos * 64);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 cc = __ldg(cs + j4);
+              const float4 sn = __ldg(cs + 8 + j4);
+              const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
+              const float sv[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = j4 * 4 + e;
+                const float a = x[j] * r * __ldg(w + j);
+                const float b = x[j + 32] * r * __ldg(w + j + 32);
+                x[j] = a * cv[e] - b * sv[e];
+                x[j + 32] = a * sv[e] + b * cv[e];
+              }
+            }
+          }
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + (size_t)m * p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                                  pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = tn * BN + c * 32;
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld32(trow + c * 32, r);
+          tmem_wait_ld();
+          if (n0 >= p.N) continue;  // warp-uniform
+          if (row_ok) {
+          float x[32];
+          if (p.bias != nullptr && p.epi != EPI_ATOMIC) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) + __ldg(p.bias + n0 + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
+          }
+          if (p.epi == EPI_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
+          }
+          if (p.epi == EPI_ATOMIC) {
+            float* dst = static_cast<float*>(p.C) + (size_t)m * p.ldc + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(x[j]), "f"(x[j + 1]),
+                           "f"(x[j + 2]), "f"(x[j + 3])
+                           : "memory");
+          } else if (p.c_fp32) {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.C) + (size_t)m * p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + (size_t)m * p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                                  pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+          }
+          }  // row_ok
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int ELEM, bool QKV>
+static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
+  using C = Cfg<BN, ELEM>;
+  GemmParams p;
+  const int eb = (ELEM == ELEM_BF16) ? 2 : 4;
+  // A operand
+  if (a.a_major == MAJOR_K)
+    OSD_TRY(make_tmap_2d(&p.tma_a, a.A, eb, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * eb, C::EPR, BM));
+  else
+    OSD_TRY(make_tmap_2d(&p.tma_a, a.A, eb, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda * eb, C::EPR, C::BK));
+  if (a.b_major == MAJOR_K)
+    OSD_TRY(make_tmap_2d(&p.tma_b, a.B, eb, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb * eb, C::EPR, BN));
+  else
+    OSD_TRY(make_tmap_2d(&p.tma_b, a.B, eb, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb * eb, C::EPR, C::BK));
+  p.M = a.M;
+  p.N = a.N;
+  p.K = a.K;
+  p.a_major = a.a_major;
+  p.b_major = a.b_major;
+  p.num_kb = ceil_div(a.K, C::BK);
+  int split = a.split_k < 1 ? 1 : a.split_k;
+  if (split > p.num_kb) split = p.num_kb;
+  p.kb_per_split = ceil_div(p.num_kb, split);
+  p.split_k = ceil_div(p.num_kb, p.kb_per_split);
+  p.tiles_m = ceil_div(a.M, BM);
+  p.tiles_n = ceil_div(a.N, BN);
+  p.epi = a.epi;
+  p.C = a.C;
+  p.ldc = a.ldc;
+  p.c_fp32 = a.c_fp32;
+  p.bias = a.bias;
+  p.qnorm_w = a.qnorm_w;
+  p.knorm_w = a.knorm_w;
+  p.rope = a.rope;
+  p.L = a.L;
+  p.dh = a.dh;
+  p.raw_out = a.raw_out;
+
+  auto kern = gemm_kernel<BN, ELEM, QKV>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    OSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.split_k;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(p);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+  OSD_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem %d x %d x %d", a.M, a.N, a.K);
+  OSD_CHECK(a.A && a.B && a.C, "gemm: null operand");
+  OSD_CHECK(a.N % 32 == 0, "gemm: N=%d must be a multiple of 32", a.N);
+  OSD_CHECK(a.epi != EPI_ATOMIC || a.c_fp32, "gemm: EPI_ATOMIC needs an fp32 output");
+  OSD_CHECK(a.split_k <= 1 || a.epi == EPI_ATOMIC, "gemm: split-K needs EPI_ATOMIC");
+  const int align = a.c_fp32 ? 4 : 8;
+  OSD_CHECK(a.ldc % align == 0, "gemm: ldc=%lld must be a multiple of %d", (long long)a.ldc, align);
+  if (a.epi == EPI_QKV) {
+    OSD_CHECK(a.elem == ELEM_BF16 || a.elem == ELEM_TF32, "gemm: bad elem");
+    OSD_CHECK(a.N % 64 == 0 && a.dh % 64 == 0 && a.bias && a.qnorm_w && a.knorm_w && a.rope && a.L > 0 && !a.c_fp32,
+              "gemm: EPI_QKV arguments incomplete");
+    if (a.elem == ELEM_BF16) return launch_cfg<256, ELEM_BF16, true>(a, stream);
+    return launch_cfg<256, ELEM_TF32, true>(a, stream);
+  }
+  // narrow tiles when the wide ones cannot fill the machine or N is not a multiple of 256
+  const int wide_items = ceil_div(a.M, BM) * ceil_div(a.N, 256) * (a.split_k < 1 ? 1 : a.split_k);
+  const bool narrow = (a.N % 256 != 0) || wide_items < num_sms();
+  if (a.elem == ELEM_BF16) {
+    if (narrow) return launch_cfg<128, ELEM_BF16, false>(a, stream);
+    return launch_cfg<256, ELEM_BF16, false>(a, stream);
+  } else {
+    if (narrow) return launch_cfg<128, ELEM_TF32, false>(a, stream);
+    return launch_cfg<256, ELEM_TF32, false>(a, stream);
+  }
+}
+
+}  // namespace osd

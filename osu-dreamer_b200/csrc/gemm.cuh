@@ -1,0 +1,40 @@
+// tcgen05 GEMM: C[M,N] (+)= A[M,K] * B[N,K]^T, fp32 accumulation in TMEM, operands staged by TMA.
+#pragma once
+#include "common.h"
+
+namespace osd {
+
+enum { MAJOR_K = 0, MAJOR_MN = 1 };
+enum { ELEM_BF16 = 0, ELEM_TF32 = 1 };
+enum {
+  EPI_STORE = 0,   // C = acc + bias
+  EPI_SILU = 1,    // C = silu(acc + bias)
+  EPI_ATOMIC = 2,  // C += acc  (fp32 red.global.add; split-K / gradient accumulation)
+  EPI_QKV = 3,     // bias + per-head RMSNorm(q,k) + RoPE (common/attn.py:75-81 of the reference)
+};
+
+struct GemmArgs {
+  const void* A = nullptr;  // MAJOR_K : [M, K] row-major, leading dim lda (elements)
+  const void* B = nullptr;  // MAJOR_MN: [K, M] row-major, leading dim lda   (same for B with N)
+  int a_major = MAJOR_K, b_major = MAJOR_K;
+  int64_t lda = 0, ldb = 0;
+  int M = 0, N = 0, K = 0;
+  int elem = ELEM_BF16;
+  int epi = EPI_STORE;
+  void* C = nullptr;
+  int64_t ldc = 0;
+  int c_fp32 = 0;
+  const float* bias = nullptr;
+  int split_k = 1;
+  // EPI_QKV
+  const float* qnorm_w = nullptr;  // [64]
+  const float* knorm_w = nullptr;  // [64]
+  const float* rope = nullptr;     // [L][2][32] fp32 (cos | sin)
+  int L = 0;                       // sequence length (row m is position m % L)
+  int dh = 1024;                   // n_heads * head_dim: columns [0,dh) q, [dh,2dh) k, [2dh,3dh) v
+  void* raw_out = nullptr;         // optional bf16 [M, N] (ld = ldc): pre-norm q,k,v (saved for backward)
+};
+
+int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+
+}  // namespace osd
