@@ -79,6 +79,52 @@ OSD_API int osd_qkv_proj(const void* x, const void* w, const float* bias, const 
  * 10000 ** (arange(0,64,2)/-64). */
 OSD_API int osd_rope_table(const float* inv_freq_host, int L, float* rope, void* stream);
 
+/* Bidirectional flash attention (head_dim 64, bf16): replaces F.scaled_dot_product_attention at
+ * osu_dreamer/common/attn.py:82.  qkv bf16 [B*L, 3*H*64] token-major (q | k | v column blocks, head h at
+ * columns h*64..h*64+63 of its block); y bf16 [B*L, H*64]; lse fp32 [B, H, L] (natural log, nullable). */
+OSD_API int osd_attn_fwd(const void* qkv, void* y, float* lse, int B, int L, int H, void* stream);
+
+/* Layout changes between the reference's channels-first [B, C, L] fp32 tensors and the internal
+ * token-major [B*L, C] operands (bf16 when *_fp32 == 0). */
+OSD_API int osd_tokens_to_channels(const void* in, int in_fp32, float* out, int B, int C, int L, void* stream);
+OSD_API int osd_channels_to_tokens(const float* in, void* out, int out_fp32, int B, int C, int L, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model entry points.  `params` is a HOST array of 164 DEVICE pointers to the fp32 parameters in the
+ * reference state-dict order (proj_audio.0.weight ... u_out.bias).
+ * ---------------------------------------------------------------------------------------------- */
+#define OSD_NUM_PARAMS 164
+
+/* Sizes the caller must allocate (device memory, 1024-byte aligned). */
+OSD_API size_t osd_packed_bytes(int mode);                 /* tensor-core operand copies of the weights */
+OSD_API size_t osd_cond_floats(int B);                     /* cg + all adaLN vectors + u_mod (fp32)     */
+OSD_API size_t osd_workspace_bytes(int B, int L, int a_batch, int mode, int save);
+OSD_API size_t osd_sample_extra_bytes(int B, int L, int a_batch);
+
+/* Convert the fp32 parameters into padded tensor-core operands (call after every optimizer step /
+ * load_state_dict).  HID 1365 is padded to 1408 with zero rows/columns (swiglu.py:18). */
+OSD_API int osd_pack_weights(const float* const* params, void* packed, int mode, void* stream);
+
+/* DiffusionModel._precompute_conditioning (model.py:73-84): audio [a_batch,128,L] fp32 channels-first,
+ * style [B,32] -> a_tok [a_batch*L,128] operand dtype (token-major silu(proj_audio)), cond = cg [B,512] |
+ * ssg1 of 8 layers [8][B,1536] | ssg2 [8][B,1536] | u_mod [B,128].  scratch >= a_batch*L*128*4 bytes. */
+OSD_API int osd_precompute_conditioning(const float* const* params, const void* packed, int mode, const float* audio,
+                                        int a_batch, const float* style, int B, int L, void* scratch, void* a_tok,
+                                        float* cond, void* stream);
+
+/* DiffusionModel._pred (model.py:86-103): xt [B,6,L] fp32 -> u [B], v [B,6,L] fp32.  With save != 0 the
+ * workspace (osd_workspace_bytes(..., save=1)) keeps every activation osd_pred_backward needs. */
+OSD_API int osd_pred_forward(const float* const* params, const void* packed, int mode, const void* a_tok,
+                             const float* cond, const float* rope, const float* xt, float* u, float* v, int B, int L,
+                             int a_batch, void* workspace, int save, void* stream);
+
+/* DiffusionModel.sample (model.py:117-138): x [B,6,L] holds the initial noise on entry and the sample on
+ * exit; num_steps + 1 forwards, the u0 probe and eta stay on the device (eta_u0_out: 2 floats, nullable).
+ * workspace = osd_workspace_bytes(..., save=0), extra = osd_sample_extra_bytes(). */
+OSD_API int osd_sample(const float* const* params, const void* packed, int mode, const void* a_tok, const float* cond,
+                       const float* rope, float* x, int num_steps, float c0, int B, int L, int a_batch,
+                       void* workspace, void* extra, float* eta_u0_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,13 +1,18 @@
-// HBM-bound kernels: norms, adaLN modulation, depthwise conv, SwiGLU, layout changes, heads.
+// HBM-bound kernels of the denoiser forward path: layout changes, RMSNorm + adaLN modulation,
+// depthwise conv, SwiGLU + RMSNorm(1365), gated residual, output heads.  Token-major activations
+// [T = B*L, C] (C contiguous); one warp per token row unless noted.  All statistics in fp32.
 #include "kernels.cuh"
 #include "ptx.cuh"
 
 namespace osd {
 
+static constexpr int D = 512;
+static constexpr float RMS_EPS = 1e-6f;  // osu_dreamer/common/rms_norm.py:12
+
+// ------------------------------------------------------------------------------------------------
 struct InvFreq {
   float v[32];
 };
-
 // rope[l][0][i] = cos(l*f_i), rope[l][1][i] = sin(l*f_i); the product l*f_i is rounded to fp32 first,
 // as torch.outer(arange(N).float(), inv_freq) does in osu_dreamer/common/attn.py:16-21.
 __global__ void rope_table_kernel(InvFreq f, int L, float* __restrict__ rope) {
@@ -20,13 +25,594 @@ __global__ void rope_table_kernel(InvFreq f, int L, float* __restrict__ rope) {
   rope[(size_t)l * 64 + i] = c;
   rope[(size_t)l * 64 + 32 + i] = s;
 }
-
 int launch_rope_table(const float* inv_freq_host, int L, float* rope, cudaStream_t stream) {
   OSD_CHECK(inv_freq_host && rope && L > 0, "rope_table: bad arguments");
   InvFreq f;
   for (int i = 0; i < 32; ++i) f.v[i] = inv_freq_host[i];
   const int n = L * 32;
   rope_table_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(f, L, rope);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// [B, C, L] fp32 channels-first -> [B*L, C] token-major (bf16 or fp32).  32x32 smem transpose.
+template <typename TOut>
+__global__ void cf_to_tm_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C, int L) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, l = l0 + tx;
+    tile[i][tx] = (c < C && l < L) ? in[((size_t)b * C + c) * L + l] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int l = l0 + i, c = c0 + tx;
+    if (l < L && c < C) out[((size_t)b * L + l) * C + c] = static_cast<TOut>(tile[tx][i]);
+  }
+}
+int launch_cf_to_tm(const float* in, void* out, int out_bf16, int B, int C, int L, cudaStream_t stream) {
+  dim3 grid(ceil_div(L, 32), ceil_div(C, 32), B), block(32, 8);
+  if (out_bf16)
+    cf_to_tm_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), C, L);
+  else
+    cf_to_tm_kernel<float><<<grid, block, 0, stream>>>(in, static_cast<float*>(out), C, L);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// [B*L, C] token-major (bf16 or fp32) -> [B, C, L] fp32 channels-first.
+template <typename TIn>
+__global__ void tm_to_cf_kernel(const TIn* __restrict__ in, float* __restrict__ out, int C, int L) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int l = l0 + i, c = c0 + tx;
+    tile[i][tx] = (c < C && l < L) ? static_cast<float>(in[((size_t)b * L + l) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, l = l0 + tx;
+    if (l < L && c < C) out[((size_t)b * C + c) * L + l] = tile[tx][i];
+  }
+}
+int launch_tm_to_cf(const void* in, int in_fp32, float* out, int B, int C, int L, cudaStream_t stream) {
+  dim3 grid(ceil_div(L, 32), ceil_div(C, 32), B), block(32, 8);
+  if (in_fp32)
+    tm_to_cf_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(in), out, C, L);
+  else
+    tm_to_cf_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), out, C, L);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small dense layer on the conditioning vectors: out[b][n] = act(bias[n] + sum_k W[n][k] in[b][k]).
+// fp32 throughout (proj_style, ssg1/ssg2, u_mod: model.py:46,66, backbone.py:62,66). One warp per n.
+__global__ void linear_small_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                    const float* __restrict__ bias, float* __restrict__ out, int Bn, int N, int K,
+                                    int silu) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* w = W + (size_t)n * K;
+  for (int b = 0; b < Bn; ++b) {
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(__ldg(w + k), __ldg(in + (size_t)b * K + k), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float v = acc + (bias ? bias[n] : 0.f);
+      out[(size_t)b * N + n] = silu ? silu_f(v) : v;
+    }
+  }
+}
+int launch_linear_small(const float* in, const float* W, const float* bias, float* out, int Bn, int N, int K,
+                        int silu, cudaStream_t stream) {
+  linear_small_kernel<<<ceil_div(N, 8), 256, 0, stream>>>(in, W, bias, out, Bn, N, K, silu);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// proj_in (model.py:48,95): x[t][c] = b[c] + sum_e W[c][e] * xt[b][e][l];  xt channels-first fp32.
+__global__ void proj_in_kernel(const float* __restrict__ xt, const float* __restrict__ W,
+                               const float* __restrict__ bias, float* __restrict__ x, int L, int T) {
+  // block: 256 threads = 8 tokens x 32 lanes; each lane produces 16 channels (4 float4)
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const int b = t / L, l = t % L;
+  float in[6];
+#pragma unroll
+  for (int e = 0; e < 6; ++e) in[e] = __ldg(xt + ((size_t)b * 6 + e) * L + l);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const int c0 = v * 128 + lane * 4;
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + i;
+      float acc = __ldg(bias + c);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc = fmaf(__ldg(W + c * 6 + e), in[e], acc);
+      o[i] = acc;
+    }
+    *reinterpret_cast<float4*>(x + (size_t)t * D + c0) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+int launch_proj_in(const float* xt, const float* W, const float* bias, float* x, int B, int L, cudaStream_t stream) {
+  const int T = B * L;
+  proj_in_kernel<<<ceil_div(T, 8), 256, 0, stream>>>(xt, W, bias, x, L, T);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row helpers: a warp owns one 512-wide row; lane holds channels {v*128 + lane*4 + i}.
+__device__ __forceinline__ void load_row_f32(const float* __restrict__ p, float (&r)[16], int lane) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const float4 q = *reinterpret_cast<const float4*>(p + v * 128 + lane * 4);
+    r[4 * v] = q.x, r[4 * v + 1] = q.y, r[4 * v + 2] = q.z, r[4 * v + 3] = q.w;
+  }
+}
+__device__ __forceinline__ float row_inv_rms(const float (&r)[16]) {
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) ss = fmaf(r[i], r[i], ss);
+  ss = warp_sum(ss);
+  return rsqrtf(ss * (1.0f / D) + RMS_EPS);
+}
+
+// attn sub-block front end (backbone.py:76-78): z = rms_norm(x)*(1+scale)+shift + cl  -> bf16 / fp32.
+// mod: [B, 1536] = (scale | shift | gate); cl: token-major [Tcl, 512] bf16, broadcast over batch when
+// cl_bcast (the "#B = 1" audio of the predict path).
+template <typename TOut>
+__global__ void prenorm_mod_kernel(const float* __restrict__ x, const float* __restrict__ mod,
+                                   const __nv_bfloat16* __restrict__ cl, TOut* __restrict__ z, int L, int T,
+                                   int cl_bcast) {
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const int b = t / L;
+  float r[16];
+  load_row_f32(x + (size_t)t * D, r, lane);
+  const float inv = row_inv_rms(r);
+  const float* sc = mod + (size_t)b * 1536;
+  const float* sh = sc + 512;
+  const size_t tcl = cl_bcast ? (size_t)(t % L) : (size_t)t;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const int c0 = v * 128 + lane * 4;
+    const float4 s4 = *reinterpret_cast<const float4*>(sc + c0);
+    const float4 h4 = *reinterpret_cast<const float4*>(sh + c0);
+    float o[4] = {r[4 * v] * inv * (1.f + s4.x) + h4.x, r[4 * v + 1] * inv * (1.f + s4.y) + h4.y,
+                  r[4 * v + 2] * inv * (1.f + s4.z) + h4.z, r[4 * v + 3] * inv * (1.f + s4.w) + h4.w};
+    if (cl != nullptr) {
+      const uint2 c2 = *reinterpret_cast<const uint2*>(cl + tcl * D + c0);
+      const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&c2.x);
+      const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&c2.y);
+      o[0] += __low2float(p0), o[1] += __high2float(p0), o[2] += __low2float(p1), o[3] += __high2float(p1);
+    }
+    if constexpr (sizeof(TOut) == 2) {
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(z) + (size_t)t * D + c0) =
+          make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(z) + (size_t)t * D + c0) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+int launch_prenorm_mod(const float* x, const float* mod, const void* cl, void* z, int z_fp32, int B, int L,
+                       int cl_bcast, cudaStream_t stream) {
+  const int T = B * L;
+  if (z_fp32)
+    prenorm_mod_kernel<float><<<ceil_div(T, 8), 256, 0, stream>>>(x, mod, static_cast<const __nv_bfloat16*>(cl),
+                                                                  static_cast<float*>(z), L, T, cl_bcast);
+  else
+    prenorm_mod_kernel<__nv_bfloat16><<<ceil_div(T, 8), 256, 0, stream>>>(
+        x, mod, static_cast<const __nv_bfloat16*>(cl), static_cast<__nv_bfloat16*>(z), L, T, cl_bcast);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// gated residual (backbone.py:79-80, 85-86): x_out = x + rms_norm(h) * gate,  gate = mod[b][1024 + c].
+__global__ void postnorm_gate_add_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                         const float* __restrict__ mod, float* __restrict__ x_out, int L, int T) {
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const int b = t / L;
+  float r[16], xr[16];
+  load_row_f32(h + (size_t)t * D, r, lane);
+  load_row_f32(x + (size_t)t * D, xr, lane);
+  const float inv = row_inv_rms(r);
+  const float* gate = mod + (size_t)b * 1536 + 1024;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const int c0 = v * 128 + lane * 4;
+    const float4 g4 = *reinterpret_cast<const float4*>(gate + c0);
+    *reinterpret_cast<float4*>(x_out + (size_t)t * D + c0) =
+        make_float4(xr[4 * v] + r[4 * v] * inv * g4.x, xr[4 * v + 1] + r[4 * v + 1] * inv * g4.y,
+                    xr[4 * v + 2] + r[4 * v + 2] * inv * g4.z, xr[4 * v + 3] + r[4 * v + 3] * inv * g4.w);
+  }
+}
+int launch_postnorm_gate_add(const float* x, const float* h, const float* mod, float* x_out, int B, int L,
+                             cudaStream_t stream) {
+  const int T = B * L;
+  postnorm_gate_add_kernel<<<ceil_div(T, 8), 256, 0, stream>>>(x, h, mod, x_out, L, T);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ffn front end (backbone.py:83 + swiglu.py:20): hmod = rms_norm(x)*(1+scale)+shift, then the depthwise
+// Conv1d(k=5, pad=2, groups=512) along the sequence (zero padding at the sample's ends) + bias.
+// Block = 32 output tokens of one sample (+2 halo rows each side) x 512 channels, hmod staged in smem.
+static constexpr int DW_TOK = 32;
+template <typename TOut>
+__global__ void __launch_bounds__(256) prenorm_mod_dwconv_kernel(
+    const float* __restrict__ x, const float* __restrict__ mod, const float* __restrict__ wconv /*[512][5]*/,
+    const float* __restrict__ bconv, TOut* __restrict__ z, __nv_bfloat16* __restrict__ hmod_out, int L) {
+  extern __shared__ float sh[];  // [DW_TOK + 4][512]
+  const int b = blockIdx.y;
+  const int l0 = blockIdx.x * DW_TOK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* sc = mod + (size_t)b * 1536;
+  const float* shf = sc + 512;
+  for (int rr = warp; rr < DW_TOK + 4; rr += 8) {
+    const int l = l0 + rr - 2;
+    float* dst = sh + rr * D;
+    if (l < 0 || l >= L) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) *reinterpret_cast<float4*>(dst + v * 128 + lane * 4) = make_float4(0, 0, 0, 0);
+      continue;
+    }
+    const size_t t = (size_t)b * L + l;
+    float r[16];
+    load_row_f32(x + t * D, r, lane);
+    const float inv = row_inv_rms(r);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int c0 = v * 128 + lane * 4;
+      const float4 s4 = *reinterpret_cast<const float4*>(sc + c0);
+      const float4 h4 = *reinterpret_cast<const float4*>(shf + c0);
+      const float4 o = make_float4(r[4 * v] * inv * (1.f + s4.x) + h4.x, r[4 * v + 1] * inv * (1.f + s4.y) + h4.y,
+                                   r[4 * v + 2] * inv * (1.f + s4.z) + h4.z, r[4 * v + 3] * inv * (1.f + s4.w) + h4.w);
+      *reinterpret_cast<float4*>(dst + c0) = o;
+      if (hmod_out != nullptr && rr >= 2 && rr < DW_TOK + 2)
+        *reinterpret_cast<uint2*>(hmod_out + t * D + c0) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    }
+  }
+  __syncthreads();
+  // each thread: channels {threadIdx.x, threadIdx.x + 256}, all tokens
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c = threadIdx.x + cc * 256;
+    float w[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w[k] = __ldg(wconv + c * 5 + k);
+    const float bb = __ldg(bconv + c);
+    float win[5];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) win[k + 1] = sh[k * D + c];
+    for (int i = 0; i < DW_TOK; ++i) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) win[k] = win[k + 1];
+      win[4] = sh[(i + 4) * D + c];
+      const int l = l0 + i;
+      if (l < L) {
+        float acc = bb;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc = fmaf(w[k], win[k], acc);
+        z[((size_t)b * L + l) * D + c] = static_cast<TOut>(acc);
+      }
+    }
+  }
+}
+int launch_prenorm_mod_dwconv(const float* x, const float* mod, const float* wconv, const float* bconv, void* z,
+                              int z_fp32, void* hmod_out, int B, int L, cudaStream_t stream) {
+  dim3 grid(ceil_div(L, DW_TOK), B);
+  const int smem = (DW_TOK + 4) * D * 4;
+  if (z_fp32) {
+    auto k = prenorm_mod_dwconv_kernel<float>;
+    OSD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k<<<grid, 256, smem, stream>>>(x, mod, wconv, bconv, static_cast<float*>(z),
+                                   static_cast<__nv_bfloat16*>(hmod_out), L);
+  } else {
+    auto k = prenorm_mod_dwconv_kernel<__nv_bfloat16>;
+    OSD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k<<<grid, 256, smem, stream>>>(x, mod, wconv, bconv, static_cast<__nv_bfloat16*>(z),
+                                   static_cast<__nv_bfloat16*>(hmod_out), L);
+  }
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// SwiGLU + RMSNorm(1365, affine=False) (swiglu.py:28-30): vg = [v (1408 padded) | g (1408 padded)],
+// hn = rms_norm_1365(v * silu(g)); padded columns are exactly zero (zero weight rows / bias).
+static constexpr int HID = 1365, HIDP = 1408;
+template <typename T>
+__global__ void swiglu_norm_kernel(const T* __restrict__ vg, T* __restrict__ hn, float* __restrict__ rinv_out,
+                                   int Tn) {
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= Tn) return;
+  const T* row = vg + (size_t)t * (2 * HIDP);
+  float hs[44];  // 1408 / 32
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 11; ++i) {  // 11 chunks of 128 columns; lane owns 4 consecutive
+    const int c0 = i * 128 + lane * 4;
+    float v[4], g[4];
+    if constexpr (sizeof(T) == 2) {
+      const uint2 a = *reinterpret_cast<const uint2*>(row + c0);
+      const uint2 bq = *reinterpret_cast<const uint2*>(row + HIDP + c0);
+      const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&a);
+      const __nv_bfloat162* bp = reinterpret_cast<const __nv_bfloat162*>(&bq);
+      v[0] = __low2float(ap[0]), v[1] = __high2float(ap[0]), v[2] = __low2float(ap[1]), v[3] = __high2float(ap[1]);
+      g[0] = __low2float(bp[0]), g[1] = __high2float(bp[0]), g[2] = __low2float(bp[1]), g[3] = __high2float(bp[1]);
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(row + c0);
+      const float4 bq = *reinterpret_cast<const float4*>(row + HIDP + c0);
+      v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
+      g[0] = bq.x, g[1] = bq.y, g[2] = bq.z, g[3] = bq.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float h = v[e] * silu_f(g[e]);
+      hs[4 * i + e] = h;
+      ss = fmaf(h, h, ss);
+    }
+  }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(ss * (1.0f / HID) + RMS_EPS);
+  if (rinv_out != nullptr && lane == 0) rinv_out[t] = inv;
+#pragma unroll
+  for (int i = 0; i < 11; ++i) {
+    const int c0 = i * 128 + lane * 4;
+    if constexpr (sizeof(T) == 2) {
+      *reinterpret_cast<uint2*>(hn + (size_t)t * HIDP + c0) =
+          make_uint2(pack_bf16(hs[4 * i] * inv, hs[4 * i + 1] * inv), pack_bf16(hs[4 * i + 2] * inv, hs[4 * i + 3] * inv));
+    } else {
+      *reinterpret_cast<float4*>(hn + (size_t)t * HIDP + c0) =
+          make_float4(hs[4 * i] * inv, hs[4 * i + 1] * inv, hs[4 * i + 2] * inv, hs[4 * i + 3] * inv);
+    }
+  }
+}
+int launch_swiglu_norm(const void* vg, void* hn, float* rinv_out, int is_fp32, int T, cudaStream_t stream) {
+  if (is_fp32)
+    swiglu_norm_kernel<float><<<ceil_div(T, 8), 256, 0, stream>>>(static_cast<const float*>(vg),
+                                                                  static_cast<float*>(hn), rinv_out, T);
+  else
+    swiglu_norm_kernel<__nv_bfloat16><<<ceil_div(T, 8), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(vg), static_cast<__nv_bfloat16*>(hn), rinv_out, T);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// final rms_norm (backbone.py:50) + proj_out (model.py:97): v[b][e][l] = bo[e] + sum_c Wo[e][c] * n[t][c],
+// written channels-first fp32 [B, 6, L].
+__global__ void final_norm_proj_out_kernel(const float* __restrict__ x, const float* __restrict__ Wo /*[6][512]*/,
+                                           const float* __restrict__ bo, float* __restrict__ v, int L, int T) {
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  float r[16];
+  load_row_f32(x + (size_t)t * D, r, lane);
+  const float inv = row_inv_rms(r);
+  float acc[6];
+#pragma unroll
+  for (int e = 0; e < 6; ++e) {
+    float a = 0.f;
+#pragma unroll
+    for (int vv = 0; vv < 4; ++vv) {
+      const float4 w = *reinterpret_cast<const float4*>(Wo + e * D + vv * 128 + lane * 4);
+      a = fmaf(w.x, r[4 * vv], a);
+      a = fmaf(w.y, r[4 * vv + 1], a);
+      a = fmaf(w.z, r[4 * vv + 2], a);
+      a = fmaf(w.w, r[4 * vv + 3], a);
+    }
+    acc[e] = warp_sum(a) * inv;
+  }
+  if (lane < 6) {
+    const int b = t / L, l = t % L;
+    float o = acc[0];
+#pragma unroll
+    for (int e = 1; e < 6; ++e) o = (lane == e) ? acc[e] : o;
+    v[((size_t)b * 6 + lane) * L + l] = o + __ldg(bo + lane);
+  }
+}
+int launch_final_norm_proj_out(const float* x, const float* Wo, const float* bo, float* v, int B, int L,
+                               cudaStream_t stream) {
+  const int T = B * L;
+  final_norm_proj_out_kernel<<<ceil_div(T, 8), 256, 0, stream>>>(x, Wo, bo, v, L, T);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// u head (model.py:58-65,99): dwconv3(6) -> 1x1 6->64 -> SiLU -> dwconv3(64) -> 1x1 64->64 -> SiLU -> sum over l.
+// Block = 64 tokens of one sample (+1 halo each side); fsum[b][64] accumulated with atomics (mean = /L).
+struct UHeadW {
+  const float *w0, *b0;  // [6][3], [6]
+  const float *w1, *b1;  // [64][6], [64]
+  const float *w3, *b3;  // [64][3], [64]
+  const float *w4, *b4;  // [64][64], [64]
+};
+static constexpr int UH_TOK = 32;
+__global__ void __launch_bounds__(256) u_head_kernel(const float* __restrict__ xt, UHeadW w, float* __restrict__ fsum,
+                                                     float* __restrict__ h1_save, float* __restrict__ h2pre_save, int L) {
+  __shared__ float c1[UH_TOK + 2][6];
+  __shared__ float h1[UH_TOK + 2][65];
+  __shared__ float c2[UH_TOK][65];
+  __shared__ float w4s[64][65];
+  __shared__ float red[4][64];
+  const int b = blockIdx.y, l0 = blockIdx.x * UH_TOK;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 64 * 64; i += 256) w4s[i >> 6][i & 63] = w.w4[i];
+  // c1 = dwconv3 over l (zero padded) for positions l0-1 .. l0+UH_TOK
+  for (int i = tid; i < (UH_TOK + 2) * 6; i += 256) {
+    const int rr = i / 6, e = i % 6;
+    const int l = l0 + rr - 1;
+    float acc = 0.f;
+    if (l >= 0 && l < L) {
+      acc = w.b0[e];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int ll = l + k - 1;
+        if (ll >= 0 && ll < L) acc = fmaf(w.w0[e * 3 + k], xt[((size_t)b * 6 + e) * L + ll], acc);
+      }
+    }
+    c1[rr][e] = acc;
+  }
+  __syncthreads();
+  // h1 = silu(W1 c1 + b1); zero outside the sequence (it is the zero padding of the second dwconv)
+  for (int i = tid; i < (UH_TOK + 2) * 64; i += 256) {
+    const int rr = i >> 6, u = i & 63;
+    const int l = l0 + rr - 1;
+    float v = 0.f;
+    if (l >= 0 && l < L) {
+      float acc = w.b1[u];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc = fmaf(w.w1[u * 6 + e], c1[rr][e], acc);
+      v = silu_f(acc);
+      if (h1_save != nullptr && rr >= 1 && rr <= UH_TOK) h1_save[((size_t)b * L + l) * 64 + u] = v;
+    }
+    h1[rr][u] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < UH_TOK * 64; i += 256) {
+    const int rr = i >> 6, u = i & 63;
+    c2[rr][u] = w.b3[u] + w.w3[u * 3] * h1[rr][u] + w.w3[u * 3 + 1] * h1[rr + 1][u] + w.w3[u * 3 + 2] * h1[rr + 2][u];
+  }
+  __syncthreads();
+  // h2 = silu(W4 c2 + b4), summed over this block's valid tokens. thread -> (u = tid & 63, token group = tid >> 6)
+  {
+    const int u = tid & 63, grp = tid >> 6;
+    float part = 0.f;
+    for (int rr = grp; rr < UH_TOK; rr += 4) {
+      const int l = l0 + rr;
+      if (l >= L) break;
+      float acc = w.b4[u];
+#pragma unroll 16
+      for (int k = 0; k < 64; ++k) acc = fmaf(w4s[u][k], c2[rr][k], acc);
+      if (h2pre_save != nullptr) h2pre_save[((size_t)b * L + l) * 64 + u] = acc;
+      part += silu_f(acc);
+    }
+    red[grp][u] = part;
+  }
+  __syncthreads();
+  if (tid < 64) atomicAdd(fsum + (size_t)b * 64 + tid, red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid]);
+}
+int launch_u_head(const float* xt, const float* const* w8, float* fsum, float* h1_save, float* h2pre_save, int B,
+                  int L, cudaStream_t stream) {
+  UHeadW w{w8[0], w8[1], w8[2], w8[3], w8[4], w8[5], w8[6], w8[7]};
+  OSD_CUDA(cudaMemsetAsync(fsum, 0, (size_t)B * 64 * sizeof(float), stream));
+  dim3 grid(ceil_div(L, UH_TOK), B);
+  u_head_kernel<<<grid, 256, 0, stream>>>(xt, w, fsum, h1_save, h2pre_save, L);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// u = u_scale * softplus(u_out(f * (1 + scale) + shift)),  f = fsum / L,  (scale | shift) = u_mod(cg)  (model.py:99-102)
+__global__ void u_final_kernel(const float* __restrict__ fsum, const float* __restrict__ umod /*[B][128]*/,
+                               const float* __restrict__ wout /*[64]*/, const float* __restrict__ bout, float u_scale,
+                               float inv_L, float* __restrict__ u, int Bn) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= Bn) return;
+  float acc = 0.f;
+  for (int i = lane; i < 64; i += 32) {
+    const float f = fsum[(size_t)b * 64 + i] * inv_L;
+    const float fm = f * (1.f + umod[(size_t)b * 128 + i]) + umod[(size_t)b * 128 + 64 + i];
+    acc = fmaf(wout[i], fm, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const float zv = acc + bout[0];
+    const float sp = zv > 20.f ? zv : log1pf(expf(zv));  // F.softplus (threshold 20)
+    u[b] = u_scale * sp;
+  }
+}
+int launch_u_final(const float* fsum, const float* umod, const float* wout, const float* bout, float u_scale, int L,
+                   float* u, int B, cudaStream_t stream) {
+  u_final_kernel<<<ceil_div(B, 4), 128, 0, stream>>>(fsum, umod, wout, bout, u_scale, 1.0f / (float)L, u, B);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// sampler update (model.py:136): x <- x - eta * u[b] * v   (channels-first [B, 6, L])
+__global__ void sample_update_kernel(float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ u,
+                                     const float* __restrict__ eta, int per_sample, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = (int)(i / per_sample);
+  x[i] = x[i] - eta[0] * u[b] * v[i];
+}
+int launch_sample_update(float* x, const float* v, const float* u, const float* eta_dev, int B, int L,
+                         cudaStream_t stream) {
+  const size_t n = (size_t)B * 6 * L;
+  sample_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, v, u, eta_dev, 6 * L, n);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// eta = 1 - (sqrt(c0) / max(mean(u), sqrt(c0) + 1e-6)) ** (1/num_steps)   (model.py:131-132), on device.
+__global__ void sample_eta_kernel(const float* __restrict__ u, int Bn, float sqrt_c0, float inv_steps,
+                                  float* __restrict__ eta_out /*[2]: eta, u0*/) {
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int b = 0; b < Bn; ++b) s += (double)u[b];
+    const double u0 = s / Bn;
+    const double den = fmax(u0, (double)sqrt_c0 + 1e-6);
+    eta_out[0] = (float)(1.0 - pow((double)sqrt_c0 / den, (double)inv_steps));
+    eta_out[1] = (float)u0;
+  }
+}
+int launch_sample_eta(const float* u, int B, float sqrt_c0, int num_steps, float* eta_out, cudaStream_t stream) {
+  sample_eta_kernel<<<1, 32, 0, stream>>>(u, B, sqrt_c0, 1.0f / (float)num_steps, eta_out);
+  OSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: fp32 parameter [rows_src, cols_src] -> operand dtype [rows_dst, cols_dst] with a row
+// map (dst row r takes src row r - row_shift when inside [row_lo, row_hi)) and zero padding elsewhere.
+template <typename TOut>
+__global__ void pack_weight_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int rows_src, int cols_src,
+                                   int rows_dst, int cols_dst, int split_at, int split_pad) {
+  // dst row r: if split_at > 0 rows [0, split_at) <- src [0, split_at); rows [split_pad, split_pad + split_at) <-
+  // src [split_at, 2*split_at); everything else zero.  split_at == 0: plain copy of [rows_src, cols_src].
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = (size_t)rows_dst * cols_dst;
+  if (i >= n) return;
+  const int r = (int)(i / cols_dst), c = (int)(i % cols_dst);
+  int sr = -1;
+  if (split_at > 0) {
+    if (r < split_at)
+      sr = r;
+    else if (r >= split_pad && r < split_pad + split_at)
+      sr = r - split_pad + split_at;
+  } else if (r < rows_src) {
+    sr = r;
+  }
+  float v = 0.f;
+  if (sr >= 0 && c < cols_src) v = src[(size_t)sr * cols_src + c];
+  dst[i] = static_cast<TOut>(v);
+}
+int launch_pack_weight(const float* src, void* dst, int dst_fp32, int rows_src, int cols_src, int rows_dst,
+                       int cols_dst, int split_at, int split_pad, cudaStream_t stream) {
+  const size_t n = (size_t)rows_dst * cols_dst;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (dst_fp32)
+    pack_weight_kernel<float><<<grid, 256, 0, stream>>>(src, static_cast<float*>(dst), rows_src, cols_src, rows_dst,
+                                                        cols_dst, split_at, split_pad);
+  else
+    pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), rows_src,
+                                                                cols_src, rows_dst, cols_dst, split_at, split_pad);
   OSD_CUDA(cudaGetLastError());
   return 0;
 }

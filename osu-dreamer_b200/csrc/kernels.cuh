@@ -1,9 +1,35 @@
-// Non-GEMM kernels of the denoiser path (HBM-bound elementwise / reduction work), host launchers.
+// Non-GEMM kernels of the denoiser path (HBM-bound elementwise / reduction work) and attention: host launchers.
 #pragma once
 #include "common.h"
 
 namespace osd {
 
 int launch_rope_table(const float* inv_freq_host, int L, float* rope, cudaStream_t stream);
+int launch_cf_to_tm(const float* in, void* out, int out_bf16, int B, int C, int L, cudaStream_t stream);
+int launch_tm_to_cf(const void* in, int in_fp32, float* out, int B, int C, int L, cudaStream_t stream);
+int launch_linear_small(const float* in, const float* W, const float* bias, float* out, int Bn, int N, int K,
+                        int silu, cudaStream_t stream);
+int launch_proj_in(const float* xt, const float* W, const float* bias, float* x, int B, int L, cudaStream_t stream);
+int launch_prenorm_mod(const float* x, const float* mod, const void* cl, void* z, int z_fp32, int B, int L,
+                       int cl_bcast, cudaStream_t stream);
+int launch_postnorm_gate_add(const float* x, const float* h, const float* mod, float* x_out, int B, int L,
+                             cudaStream_t stream);
+int launch_prenorm_mod_dwconv(const float* x, const float* mod, const float* wconv, const float* bconv, void* z,
+                              int z_fp32, void* hmod_out, int B, int L, cudaStream_t stream);
+int launch_swiglu_norm(const void* vg, void* hn, float* rinv_out, int is_fp32, int T, cudaStream_t stream);
+int launch_final_norm_proj_out(const float* x, const float* Wo, const float* bo, float* v, int B, int L,
+                               cudaStream_t stream);
+int launch_u_head(const float* xt, const float* const* w8, float* fsum, float* h1_save, float* h2pre_save, int B,
+                  int L, cudaStream_t stream);
+int launch_u_final(const float* fsum, const float* umod, const float* wout, const float* bout, float u_scale, int L,
+                   float* u, int B, cudaStream_t stream);
+int launch_sample_update(float* x, const float* v, const float* u, const float* eta_dev, int B, int L,
+                         cudaStream_t stream);
+int launch_sample_eta(const float* u, int B, float sqrt_c0, int num_steps, float* eta_out, cudaStream_t stream);
+int launch_pack_weight(const float* src, void* dst, int dst_fp32, int rows_src, int cols_src, int rows_dst,
+                       int cols_dst, int split_at, int split_pad, cudaStream_t stream);
+
+// attention (attn_fwd.cu)
+int launch_attn_fwd(const void* qkv, void* y, float* lse, int B, int L, int H, cudaStream_t stream);
 
 }  // namespace osd

@@ -1,0 +1,310 @@
+// Denoiser forward orchestration (DiffusionModel._precompute_conditioning / _pred / sample of the reference,
+// osu_dreamer/models/diffusion/model.py:73-138) over the kernels in gemm.cu / attn_fwd.cu / elementwise.cu.
+#include "model.cuh"
+
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+#include <math.h>
+
+namespace osd {
+
+static inline size_t esz_of(int mode) { return mode == OSD_BF16 ? 2 : 4; }
+static inline size_t al(size_t x) { return align_up(x, 1024); }
+
+PackedLayout packed_layout(int mode) {
+  PackedLayout p;
+  p.esz = esz_of(mode);
+  size_t off = 0;
+  p.wa = off;
+  off += al((size_t)128 * 128 * p.esz);
+  size_t lo = 0;
+  p.l_cl = lo;
+  lo += al((size_t)512 * 128 * p.esz);
+  p.l_qkv = lo;
+  lo += al((size_t)3072 * 512 * p.esz);
+  p.l_out = lo;
+  lo += al((size_t)512 * 1024 * p.esz);
+  p.l_vg = lo;
+  lo += al((size_t)2 * OSD_HIDP * 512 * p.esz);
+  p.l_po = lo;
+  lo += al((size_t)512 * OSD_HIDP * p.esz);
+  p.layer0 = off;
+  p.layer_stride = lo;
+  off += 8 * lo;
+  p.bvg = off;
+  off += al((size_t)8 * 2 * OSD_HIDP * 4);
+  p.total = off;
+  return p;
+}
+
+ActPlan make_plan(int B, int L, int a_batch, int mode, int save) {
+  ActPlan a;
+  const size_t T = (size_t)B * L, Ta = (size_t)a_batch * L;
+  const size_t e = esz_of(mode);
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o += al(bytes);
+    return r;
+  };
+  a.x0 = take(T * 512 * 4);
+  a.cl = take(Ta * 512 * 2);  // proj_cl output is always bf16 (added in fp32 inside prenorm_mod)
+  a.z = take(T * 512 * e);
+  a.qkv_raw = save ? take(T * 3072 * 2) : 0;
+  a.qkv = take(T * 3072 * 2);
+  a.y = take(T * 1024 * e);
+  a.lse = take(T * 16 * 4);
+  a.o = take(T * 512 * 4);
+  a.x1 = take(T * 512 * 4);
+  a.hmod = save ? take(T * 512 * 2) : 0;
+  a.z2 = take(T * 512 * e);
+  a.vg = take(T * 2 * OSD_HIDP * e);
+  a.hn = take(T * OSD_HIDP * e);
+  a.rinv2 = take(T * 4);
+  a.f = take(T * 512 * 4);
+  a.layer_bytes = o;
+  a.layer_stride = save ? o : 0;
+  size_t tot = save ? 8 * o : o;
+  auto take2 = [&](size_t bytes) {
+    size_t r = tot;
+    tot += al(bytes);
+    return r;
+  };
+  a.x_final = save ? take2(T * 512 * 4) : a.x0;
+  a.fsum = take2((size_t)B * 64 * 4);
+  a.uh1 = save ? take2(T * 64 * 4) : 0;
+  a.uh2 = save ? take2(T * 64 * 4) : 0;
+  a.total = tot;
+  return a;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int pack_weights(const float* const* P, uint8_t* packed, int mode, cudaStream_t s) {
+  const PackedLayout lay = packed_layout(mode);
+  const int f32 = mode != OSD_BF16;
+  OSD_TRY(launch_pack_weight(P[P_AUDIO_W], packed + lay.wa, f32, 128, 128, 128, 128, 0, 0, s));
+  for (int l = 0; l < 8; ++l) {
+    uint8_t* lb = packed + lay.layer0 + l * lay.layer_stride;
+    OSD_TRY(launch_pack_weight(P[lp(l, L_CL_W)], lb + lay.l_cl, f32, 512, 128, 512, 128, 0, 0, s));
+    OSD_TRY(launch_pack_weight(P[lp(l, L_QKV_W)], lb + lay.l_qkv, f32, 3072, 512, 3072, 512, 0, 0, s));
+    OSD_TRY(launch_pack_weight(P[lp(l, L_OUT_W)], lb + lay.l_out, f32, 512, 1024, 512, 1024, 0, 0, s));
+    OSD_TRY(launch_pack_weight(P[lp(l, L_VG_W)], lb + lay.l_vg, f32, 2 * OSD_HID, 512, 2 * OSD_HIDP, 512, OSD_HID,
+                               OSD_HIDP, s));
+    OSD_TRY(launch_pack_weight(P[lp(l, L_PO_W)], lb + lay.l_po, f32, 512, OSD_HID, 512, OSD_HIDP, 0, 0, s));
+    OSD_TRY(launch_pack_weight(P[lp(l, L_VG_B)], packed + lay.bvg + (size_t)l * 2 * OSD_HIDP * 4, 1, 2 * OSD_HID, 1,
+                               2 * OSD_HIDP, 1, OSD_HID, OSD_HIDP, s));
+  }
+  return 0;
+}
+
+static int precompute_conditioning(const float* const* P, const PackedW& W, int mode, const float* audio, int a_batch,
+                                   const float* style, int B, int L, void* a_tok, float* cond, void* scratch,
+                                   cudaStream_t s) {
+  const int Ta = a_batch * L;
+  const int f32 = mode != OSD_BF16;
+  // audio [Ba,128,L] fp32 -> token-major operand dtype -> a = silu(proj_audio(audio))  (model.py:45,82)
+  OSD_TRY(launch_cf_to_tm(audio, scratch, !f32, a_batch, 128, L, s));
+  GemmArgs g;
+  g.A = scratch; g.B = W.wa(); g.lda = 128; g.ldb = 128; g.M = Ta; g.N = 128; g.K = 128;
+  g.elem = f32 ? ELEM_TF32 : ELEM_BF16; g.epi = EPI_SILU; g.C = a_tok; g.ldc = 128; g.c_fp32 = f32;
+  g.bias = P[P_AUDIO_B];
+  OSD_TRY(launch_gemm(g, s));
+  // cg = silu(proj_style(style)) (model.py:46,83); modulation vectors for every layer (backbone.py:76,82) and u_mod
+  CondPack c{cond, B};
+  float* cw = cond;
+  OSD_TRY(launch_linear_small(style, P[P_STYLE_W], P[P_STYLE_B], cw, B, 512, 32, 1, s));
+  for (int l = 0; l < 8; ++l) {
+    OSD_TRY(launch_linear_small(c.cg(), P[lp(l, L_SSG1_W)], P[lp(l, L_SSG1_B)], const_cast<float*>(c.mod1(l)), B, 1536,
+                                512, 0, s));
+    OSD_TRY(launch_linear_small(c.cg(), P[lp(l, L_SSG2_W)], P[lp(l, L_SSG2_B)], const_cast<float*>(c.mod2(l)), B, 1536,
+                                512, 0, s));
+  }
+  OSD_TRY(launch_linear_small(c.cg(), P[P_UMOD_W], P[P_UMOD_B], const_cast<float*>(c.umod()), B, 128, 512, 0, s));
+  return 0;
+}
+
+// proj_cl for one layer: cl = a_tok * Wcl^T + b  -> bf16 [Ta, 512]   (backbone.py:63,78)
+static int proj_cl(const float* const* P, const PackedW& W, int mode, int l, const void* a_tok, int Ta, void* cl,
+                   cudaStream_t s) {
+  GemmArgs g;
+  g.A = a_tok; g.B = W.cl(l); g.lda = 128; g.ldb = 128; g.M = Ta; g.N = 512; g.K = 128;
+  g.elem = mode == OSD_BF16 ? ELEM_BF16 : ELEM_TF32; g.epi = EPI_STORE; g.C = cl; g.ldc = 512; g.c_fp32 = 0;
+  g.bias = P[lp(l, L_CL_B)];
+  return launch_gemm(g, s);
+}
+
+struct FwdCtx {
+  const float* const* P;
+  PackedW W;
+  int mode, B, L, a_batch;
+  CondPack cond;
+  const void* a_tok;  // [Ta,128] operand dtype
+  const float* rope;
+  uint8_t* ws;
+  ActPlan plan;
+  int save;
+  const uint8_t* cl_hoisted;  // [8][Ta,512] bf16 or null
+};
+
+static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cudaStream_t s) {
+  const int B = c.B, L = c.L, T = B * L, Ta = c.a_batch * L;
+  const int mode = c.mode;
+  const int f32 = mode != OSD_BF16;
+  const int elem = f32 ? ELEM_TF32 : ELEM_BF16;
+  OSD_CHECK(!f32, "pred_forward: the fp32/tf32 path is not enabled in this build");
+  const ActPlan& pl = c.plan;
+  auto LB = [&](int l) { return c.ws + (size_t)l * pl.layer_stride; };
+  const void* a_tok = c.a_tok;
+
+  OSD_TRY(launch_proj_in(xt, c.P[P_IN_W], c.P[P_IN_B], reinterpret_cast<float*>(LB(0) + pl.x0), B, L, s));
+  for (int l = 0; l < 8; ++l) {
+    uint8_t* lb = LB(l);
+    float* x0 = reinterpret_cast<float*>(lb + pl.x0);
+    float* x1 = reinterpret_cast<float*>(lb + pl.x1);
+    float* xo = (l == 7) ? reinterpret_cast<float*>(c.ws + pl.x_final)
+                         : reinterpret_cast<float*>(LB(l + 1) + pl.x0);
+    const void* cl;
+    if (c.cl_hoisted != nullptr) {
+      cl = c.cl_hoisted + (size_t)l * al((size_t)Ta * 512 * 2);
+    } else {
+      OSD_TRY(proj_cl(c.P, c.W, mode, l, a_tok, Ta, lb + pl.cl, s));
+      cl = lb + pl.cl;
+    }
+    // ---- attention sub-block (backbone.py:76-80)
+    OSD_TRY(launch_prenorm_mod(x0, c.cond.mod1(l), cl, lb + pl.z, f32, B, L, c.a_batch == 1, s));
+    GemmArgs q;
+    q.A = lb + pl.z; q.B = c.W.qkv(l); q.lda = 512; q.ldb = 512; q.M = T; q.N = 3072; q.K = 512; q.elem = elem;
+    q.epi = EPI_QKV; q.C = lb + pl.qkv; q.ldc = 3072; q.c_fp32 = 0; q.bias = c.P[lp(l, L_QKV_B)];
+    q.qnorm_w = c.P[lp(l, L_QN_W)]; q.knorm_w = c.P[lp(l, L_KN_W)]; q.rope = c.rope; q.L = L; q.dh = 1024;
+    q.raw_out = c.save ? lb + pl.qkv_raw : nullptr;
+    OSD_TRY(launch_gemm(q, s));
+    OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), B, L, 16, s));
+    GemmArgs o;
+    o.A = lb + pl.y; o.B = c.W.out(l); o.lda = 1024; o.ldb = 1024; o.M = T; o.N = 512; o.K = 1024; o.elem = elem;
+    o.epi = EPI_STORE; o.C = lb + pl.o; o.ldc = 512; o.c_fp32 = 1; o.bias = c.P[lp(l, L_OUT_B)];
+    OSD_TRY(launch_gemm(o, s));
+    OSD_TRY(launch_postnorm_gate_add(x0, reinterpret_cast<float*>(lb + pl.o), c.cond.mod1(l), x1, B, L, s));
+    // ---- ffn sub-block (backbone.py:82-86, swiglu.py:27-32)
+    OSD_TRY(launch_prenorm_mod_dwconv(x1, c.cond.mod2(l), c.P[lp(l, L_DW_W)], c.P[lp(l, L_DW_B)], lb + pl.z2, f32,
+                                      c.save ? lb + pl.hmod : nullptr, B, L, s));
+    GemmArgs g;
+    g.A = lb + pl.z2; g.B = c.W.vg(l); g.lda = 512; g.ldb = 512; g.M = T; g.N = 2 * OSD_HIDP; g.K = 512; g.elem = elem;
+    g.epi = EPI_STORE; g.C = lb + pl.vg; g.ldc = 2 * OSD_HIDP; g.c_fp32 = f32; g.bias = c.W.bvg(l);
+    OSD_TRY(launch_gemm(g, s));
+    OSD_TRY(launch_swiglu_norm(lb + pl.vg, lb + pl.hn, reinterpret_cast<float*>(lb + pl.rinv2), f32, T, s));
+    GemmArgs po;
+    po.A = lb + pl.hn; po.B = c.W.po(l); po.lda = OSD_HIDP; po.ldb = OSD_HIDP; po.M = T; po.N = 512; po.K = OSD_HIDP;
+    po.elem = elem; po.epi = EPI_STORE; po.C = lb + pl.f; po.ldc = 512; po.c_fp32 = 1; po.bias = c.P[lp(l, L_PO_B)];
+    OSD_TRY(launch_gemm(po, s));
+    OSD_TRY(launch_postnorm_gate_add(x1, reinterpret_cast<float*>(lb + pl.f), c.cond.mod2(l), xo, B, L, s));
+  }
+  OSD_TRY(launch_final_norm_proj_out(reinterpret_cast<float*>(c.ws + pl.x_final), c.P[P_OUT_W], c.P[P_OUT_B], v, B, L,
+                                     s));
+  // ---- distance head (model.py:99-102)
+  const float* uw[8] = {c.P[P_UH0_W], c.P[P_UH0_B], c.P[P_UH1_W], c.P[P_UH1_B],
+                        c.P[P_UH3_W], c.P[P_UH3_B], c.P[P_UH4_W], c.P[P_UH4_B]};
+  float* fsum = reinterpret_cast<float*>(c.ws + pl.fsum);
+  OSD_TRY(launch_u_head(xt, uw, fsum, c.save ? reinterpret_cast<float*>(c.ws + pl.uh1) : nullptr,
+                        c.save ? reinterpret_cast<float*>(c.ws + pl.uh2) : nullptr, B, L, s));
+  OSD_TRY(launch_u_final(fsum, c.cond.umod(), c.P[P_UOUT_W], c.P[P_UOUT_B], sqrtf(2.0f * OSD_E), L, u, B, s));
+  return 0;
+}
+
+}  // namespace osd
+
+// ================================================================================================
+using namespace osd;
+
+extern "C" {
+
+size_t osd_packed_bytes(int mode) { return packed_layout(mode).total; }
+size_t osd_cond_floats(int B) { return CondPack::floats(B); }
+size_t osd_workspace_bytes(int B, int L, int a_batch, int mode, int save) {
+  return make_plan(B, L, a_batch, mode, save).total;
+}
+size_t osd_sample_extra_bytes(int B, int L, int a_batch) {
+  // hoisted proj_cl outputs [8][Ta,512] bf16 + v [B,6,L] + u [B] + eta [2]
+  return 8 * al((size_t)a_batch * L * 512 * 2) + al((size_t)B * 6 * L * 4) + al((size_t)B * 4) + 1024;
+}
+
+int osd_pack_weights(const float* const* params, void* packed, int mode, void* stream) {
+  OSD_CHECK(params && packed, "osd_pack_weights: null argument");
+  OSD_CHECK(mode == OSD_BF16 || mode == OSD_TF32, "osd_pack_weights: bad mode %d", mode);
+  return pack_weights(params, static_cast<uint8_t*>(packed), mode, static_cast<cudaStream_t>(stream));
+}
+
+int osd_precompute_conditioning(const float* const* params, const void* packed, int mode, const float* audio,
+                                int a_batch, const float* style, int B, int L, void* scratch, void* a_tok,
+                                float* cond, void* stream) {
+  OSD_CHECK(params && packed && audio && style && scratch && a_tok && cond,
+            "osd_precompute_conditioning: null argument");
+  OSD_CHECK(a_batch == B || a_batch == 1, "osd_precompute_conditioning: audio batch %d must be 1 or B=%d", a_batch, B);
+  PackedW W{static_cast<const uint8_t*>(packed), packed_layout(mode)};
+  return precompute_conditioning(params, W, mode, audio, a_batch, style, B, L, a_tok, cond, scratch,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int osd_tokens_to_channels(const void* in, int in_fp32, float* out, int B, int C, int L, void* stream) {
+  return launch_tm_to_cf(in, in_fp32, out, B, C, L, static_cast<cudaStream_t>(stream));
+}
+int osd_channels_to_tokens(const float* in, void* out, int out_fp32, int B, int C, int L, void* stream) {
+  return launch_cf_to_tm(in, out, !out_fp32, B, C, L, static_cast<cudaStream_t>(stream));
+}
+
+int osd_pred_forward(const float* const* params, const void* packed, int mode, const void* a_tok, const float* cond,
+                     const float* rope, const float* xt, float* u, float* v, int B, int L, int a_batch,
+                     void* workspace, int save, void* stream) {
+  OSD_CHECK(params && packed && a_tok && cond && rope && xt && u && v && workspace, "osd_pred_forward: null argument");
+  FwdCtx c;
+  c.P = params;
+  c.W = PackedW{static_cast<const uint8_t*>(packed), packed_layout(mode)};
+  c.mode = mode; c.B = B; c.L = L; c.a_batch = a_batch;
+  c.cond = CondPack{cond, B};
+  c.a_tok = a_tok;
+  c.rope = rope;
+  c.ws = static_cast<uint8_t*>(workspace);
+  c.plan = make_plan(B, L, a_batch, mode, save);
+  c.save = save;
+  c.cl_hoisted = nullptr;
+  return pred_forward(c, xt, u, v, static_cast<cudaStream_t>(stream));
+}
+
+// DiffusionModel.sample (model.py:117-138): x is the initial noise on entry and the sample on exit.
+// The step-invariant proj_cl(a) of all 8 layers is computed once; the u0 probe stays on the device.
+int osd_sample(const float* const* params, const void* packed, int mode, const void* a_tok, const float* cond,
+               const float* rope, float* x, int num_steps, float c0, int B, int L, int a_batch, void* workspace,
+               void* extra, float* eta_u0_out, void* stream) {
+  OSD_CHECK(params && packed && a_tok && cond && rope && x && workspace && extra, "osd_sample: null argument");
+  OSD_CHECK(num_steps >= 1, "osd_sample: num_steps must be >= 1");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FwdCtx c;
+  c.P = params;
+  c.W = PackedW{static_cast<const uint8_t*>(packed), packed_layout(mode)};
+  c.mode = mode; c.B = B; c.L = L; c.a_batch = a_batch;
+  c.cond = CondPack{cond, B};
+  c.a_tok = a_tok;
+  c.rope = rope;
+  c.ws = static_cast<uint8_t*>(workspace);
+  c.plan = make_plan(B, L, a_batch, mode, 0);
+  c.save = 0;
+  uint8_t* ex = static_cast<uint8_t*>(extra);
+  const int Ta = a_batch * L;
+  const size_t cl_bytes = al((size_t)Ta * 512 * 2);
+  for (int l = 0; l < 8; ++l) OSD_TRY(proj_cl(params, c.W, mode, l, a_tok, Ta, ex + l * cl_bytes, s));
+  c.cl_hoisted = ex;
+  float* v = reinterpret_cast<float*>(ex + 8 * cl_bytes);
+  float* u = reinterpret_cast<float*>(ex + 8 * cl_bytes + al((size_t)B * 6 * L * 4));
+  float* eta = reinterpret_cast<float*>(ex + 8 * cl_bytes + al((size_t)B * 6 * L * 4) + al((size_t)B * 4));
+  OSD_TRY(pred_forward(c, x, u, v, s));
+  OSD_TRY(launch_sample_eta(u, B, sqrtf(c0), num_steps, eta, s));
+  for (int i = 0; i < num_steps; ++i) {
+    OSD_TRY(pred_forward(c, x, u, v, s));
+    OSD_TRY(launch_sample_update(x, v, u, eta, B, L, s));
+  }
+  if (eta_u0_out != nullptr)
+    OSD_CUDA(cudaMemcpyAsync(eta_u0_out, eta, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+}  // extern "C"

@@ -96,3 +96,88 @@ def qkv_proj(x, w, bias, qnorm_w, knorm_w, rope, L, raw_out=None):
     _check(load().osd_qkv_proj(ptr(x), ptr(w), ptr(bias), ptr(qnorm_w), ptr(knorm_w), ptr(rope), ptr(out),
                                ptr(raw_out), c_int(T), c_int(L), c_int(_elem_of(x)), stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# model-level entry points
+# ---------------------------------------------------------------------------------------------
+NUM_PARAMS = 164
+
+
+def _sz(fn, *args):
+    lib = load()
+    f = getattr(lib, fn)
+    f.restype = c_size_t
+    return int(f(*[c_int(a) for a in args]))
+
+
+def packed_bytes(mode):
+    return _sz('osd_packed_bytes', mode)
+
+
+def cond_floats(B):
+    return _sz('osd_cond_floats', B)
+
+
+def workspace_bytes(B, L, a_batch, mode, save):
+    return _sz('osd_workspace_bytes', B, L, a_batch, mode, save)
+
+
+def sample_extra_bytes(B, L, a_batch):
+    return _sz('osd_sample_extra_bytes', B, L, a_batch)
+
+
+def param_array(tensors):
+    """HOST array of device pointers, reference state-dict order."""
+    assert len(tensors) == NUM_PARAMS, len(tensors)
+    for t in tensors:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise OsdError('parameters must be contiguous fp32 CUDA tensors (no CPU path)')
+    return (c_void_p * NUM_PARAMS)(*[t.data_ptr() for t in tensors])
+
+
+def attn_fwd(qkv, B, L, H=16, want_lse=True):
+    T = B * L
+    y = torch.empty(T, H * 64, dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device) if want_lse else None
+    _check(load().osd_attn_fwd(ptr(qkv), ptr(y), ptr(lse), c_int(B), c_int(L), c_int(H), stream()))
+    return y, lse
+
+
+def pack_weights(parr, packed, mode):
+    _check(load().osd_pack_weights(parr, ptr(packed), c_int(mode), stream()))
+
+
+def precompute_conditioning(parr, packed, mode, audio, style, scratch, a_tok, cond):
+    a_batch, _, L = audio.shape
+    B = style.shape[0]
+    _check(load().osd_precompute_conditioning(parr, ptr(packed), c_int(mode), ptr(audio), c_int(a_batch), ptr(style),
+                                              c_int(B), c_int(L), ptr(scratch), ptr(a_tok), ptr(cond), stream()))
+
+
+def pred_forward(parr, packed, mode, a_tok, cond, rope, xt, u, v, a_batch, workspace, save):
+    B, _, L = xt.shape
+    _check(load().osd_pred_forward(parr, ptr(packed), c_int(mode), ptr(a_tok), ptr(cond), ptr(rope), ptr(xt), ptr(u),
+                                   ptr(v), c_int(B), c_int(L), c_int(a_batch), ptr(workspace), c_int(save), stream()))
+
+
+def sample(parr, packed, mode, a_tok, cond, rope, x, num_steps, c0, a_batch, workspace, extra, eta_u0):
+    B, _, L = x.shape
+    _check(load().osd_sample(parr, ptr(packed), c_int(mode), ptr(a_tok), ptr(cond), ptr(rope), ptr(x),
+                             c_int(num_steps), c_float(c0), c_int(B), c_int(L), c_int(a_batch), ptr(workspace),
+                             ptr(extra), ptr(eta_u0), stream()))
+
+
+def tokens_to_channels(tok, B, C, L):
+    out = torch.empty(B, C, L, dtype=torch.float32, device=tok.device)
+    _check(load().osd_tokens_to_channels(ptr(tok), c_int(1 if tok.dtype == torch.float32 else 0), ptr(out), c_int(B),
+                                         c_int(C), c_int(L), stream()))
+    return out
+
+
+def channels_to_tokens(x, out_dtype=torch.bfloat16):
+    B, C, L = x.shape
+    out = torch.empty(B * L, C, dtype=out_dtype, device=x.device)
+    _check(load().osd_channels_to_tokens(ptr(x), ptr(out), c_int(1 if out_dtype == torch.float32 else 0), c_int(B),
+                                         c_int(C), c_int(L), stream()))
+    return out

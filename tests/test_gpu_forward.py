@@ -1,0 +1,135 @@
+"""GPU parity tests (run with -m gpu on a B200): CUDA path through the C ABI vs the CPU oracle / goldens.
+
+Tolerances (stated by BASELINE.json north_star): bf16 mode 2e-2, taken max-normalised against the fp32
+reference (golden `v32`/`u32` produced by the unmodified reference on CPU)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import denoiser_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 2e-2
+
+
+def _model(sd):
+    from osu_dreamer_b200.denoiser import DiffusionModel, default_args
+    m = DiffusionModel(6, 128, 32, default_args())
+    m.load_state_dict(sd)
+    return m.cuda().eval()
+
+
+def _maxnorm(a, b):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+@pytest.mark.parametrize('B,L', [(1, 128), (2, 256), (1, 200), (2, 1000), (1, 2048)])
+def test_attention_matches_sdpa(B, L):
+    from osu_dreamer_b200 import lib
+    g = torch.Generator().manual_seed(L)
+    qkv = torch.randn(B * L, 3072, generator=g).cuda().to(torch.bfloat16)
+    y, lse = lib.attn_fwd(qkv, B, L)
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(B, L, 3, 16, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) / 8
+    ref = torch.softmax(s, -1) @ v
+    ref = ref.permute(0, 2, 1, 3).reshape(B * L, 1024)
+    assert _maxnorm(y, ref) < 1e-2
+    assert torch.allclose(lse.cpu(), torch.logsumexp(s, -1).cpu(), atol=2e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize('B,L,seed', [(2, 128, 7), (2, 320, 8), (1, 1000, 9)])
+def test_forward_matches_reference_golden(golden_dir, oracle_sd, B, L, seed):
+    g = np.load(os.path.join(golden_dir, f'fwd_B{B}_L{L}.npz'))
+    inp = O.make_inputs(B, L, seed=seed)
+    xt = torch.lerp(inp['x0'], inp['x1'], inp['t'][:, None, None])
+    m = _model(oracle_sd)
+    with torch.no_grad():
+        u, v = m(inp['h'].cuda(), inp['s'].cuda(), xt.cuda())
+    torch.cuda.synchronize()
+    eu, ev = _maxnorm(u, g['u32']), _maxnorm(v, g['v32'])
+    print(f'B={B} L={L} u err {eu:.3e} v err {ev:.3e} (reference bf16-autocast itself: '
+          f"{_maxnorm(g['v_bf16'], g['v32']):.3e})")
+    assert eu < BF16_TOL and ev < BF16_TOL
+
+
+def test_forward_broadcast_audio(golden_dir, oracle_sd):
+    g = np.load(os.path.join(golden_dir, 'fwd_bcast_B3_L96.npz'))
+    inp = O.make_inputs(3, 96, seed=10, a_batch=1)
+    m = _model(oracle_sd)
+    with torch.no_grad():
+        a, cg = m._precompute_conditioning(inp['h'].cuda(), inp['s'].cuda())
+        assert a.shape == (1, 128, 96) and cg.shape == (3, 512)
+        u, v = m._pred(a, cg, inp['x0'].cuda())
+    assert _maxnorm(u, g['u32']) < BF16_TOL and _maxnorm(v, g['v32']) < BF16_TOL
+
+
+def test_default_init_known_answer():
+    from osu_dreamer_b200.denoiser import DiffusionModel, default_args
+    m = DiffusionModel(6, 128, 32, default_args()).cuda().eval()
+    inp = O.make_inputs(2, 64, seed=3)
+    with torch.no_grad():
+        u, v = m(inp['h'].cuda(), inp['s'].cuda(), inp['x0'].cuda())
+    assert torch.allclose(u.cpu(), torch.full((2,), 1.73205), atol=2e-4) and float(v.abs().max()) == 0.0
+
+
+def test_forward_live_oracle_medium(oracle_sd):
+    """a size the CPU oracle finishes in seconds but with several kv tiles: B=2, L=640."""
+    inp = O.make_inputs(2, 640, seed=123)
+    with torch.no_grad():
+        ur, vr = O.forward(oracle_sd, inp['h'], inp['s'], inp['x0'])
+    m = _model(oracle_sd)
+    with torch.no_grad():
+        u, v = m(inp['h'].cuda(), inp['s'].cuda(), inp['x0'].cuda())
+    assert _maxnorm(u, ur) < BF16_TOL and _maxnorm(v, vr) < BF16_TOL
+
+
+def test_sampler_matches_reference_golden(golden_dir, oracle_sd):
+    g = np.load(os.path.join(golden_dir, 'sample_B2_L128_N8.npz'))
+    inp = O.make_inputs(2, 128, seed=31)
+    m = _model(oracle_sd)
+    x = m.sample_from(inp['h'].cuda(), inp['s'].cuda(), torch.from_numpy(g['x_init']).cuda(), 8)
+    torch.cuda.synchronize()
+    err = _maxnorm(x, g['x_final'])
+    # oracle facts for the same run
+    xo, u0, eta = O.sample(oracle_sd, inp['h'], inp['s'], torch.from_numpy(g['x_init']), 8)
+    eta_u0 = m.last_eta_u0.cpu()
+    print(f'sampler err {err:.3e}; eta {float(eta_u0[0]):.6f} vs {eta:.6f}; u0 {float(eta_u0[1]):.5f} vs {u0:.5f}')
+    assert abs(float(eta_u0[1]) - u0) < BF16_TOL * u0
+    assert err < 5e-2  # 9 chained bf16 forwards
+
+
+def test_sample_draws_like_reference(oracle_sd):
+    """`sample` consumes the global generator exactly like model.py:125 (randn(B,E,l) on audio.device)."""
+    inp = O.make_inputs(2, 128, seed=31)
+    m = _model(oracle_sd)
+    torch.manual_seed(5)
+    x1 = m.sample(inp['h'].cuda(), inp['s'].cuda(), 2)
+    torch.manual_seed(5)
+    x_init = torch.randn(2, 6, 128, device='cuda')
+    x2 = m.sample_from(inp['h'].cuda(), inp['s'].cuda(), x_init, 2)
+    assert torch.equal(x1, x2)
+
+
+def test_large_shape_properties(oracle_sd):
+    """BASELINE config sizes the oracle cannot run: L=8192.  Size-independent properties:
+    (i) batch independence: sample b of a B=2 batch equals the B=1 run of that sample;
+    (ii) softmax rows: attention of constant V returns that constant."""
+    from osu_dreamer_b200 import lib
+    L = 8192
+    inp = O.make_inputs(2, L, seed=55)
+    m = _model(oracle_sd)
+    with torch.no_grad():
+        u2, v2 = m(inp['h'].cuda(), inp['s'].cuda(), inp['x0'].cuda())
+        u1, v1 = m(inp['h'][1:].cuda(), inp['s'][1:].cuda(), inp['x0'][1:].cuda())
+    assert torch.isfinite(v2).all() and torch.isfinite(u2).all()
+    assert _maxnorm(v2[1:], v1) < 1e-6 and _maxnorm(u2[1:], u1) < 1e-6
+    qkv = torch.randn(L, 3072, generator=torch.Generator().manual_seed(1)).cuda().to(torch.bfloat16)
+    qkv[:, 2048:] = 0.5
+    y, _ = lib.attn_fwd(qkv, 1, L)
+    assert float((y.float() - 0.5).abs().max()) < 4e-3

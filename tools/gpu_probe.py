@@ -89,6 +89,56 @@ def cases():
         refo = torch.stack([nr(q, qw), nr(k, kw), v], 1).reshape(T, 3072)
         return max(e_raw, rel(out, refo))
     cs.append(('qkv_epilogue', qkv_case))
+
+    def attn_case(B, L):
+        def f():
+            qkv = rnd(B * L, 3072)
+            y, lse = lib.attn_fwd(qkv, B, L)
+            torch.cuda.synchronize()
+            q, k, v = qkv.float().view(B, L, 3, 16, 64).permute(2, 0, 3, 1, 4)
+            sc = (q @ k.transpose(-1, -2)) / 8
+            ref = (torch.softmax(sc, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, 1024)
+            e2 = float((lse - torch.logsumexp(sc, -1)).abs().max())
+            return max(rel(y, ref), e2)
+        return f
+    cs.append(('attn_B1_L128', attn_case(1, 128)))
+    cs.append(('attn_B2_L512', attn_case(2, 512)))
+    cs.append(('attn_B1_L200', attn_case(1, 200)))
+    cs.append(('attn_B1_L4096', attn_case(1, 4096)))
+
+    def attn_speed():
+        B, L = 8, 8192
+        qkv = rnd(B * L, 3072)
+        for _ in range(2):
+            lib.attn_fwd(qkv, B, L)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            lib.attn_fwd(qkv, B, L)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        tf = 4 * B * 16 * L * L * 64 / ms / 1e9
+        return {'ms': ms, 'tflops': tf}
+    cs.append(('attn_speed_B8_L8192', attn_speed))
+
+    def gemm_speed():
+        M, N, K = 131072, 3072, 512
+        A, Bm = rnd(M, K), rnd(N, K)
+        C = torch.empty(M, N, dtype=bf, device=dev)
+        for _ in range(2):
+            lib.gemm(A, Bm, C)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            lib.gemm(A, Bm, C)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        return {'ms': ms, 'tflops': 2 * M * N * K / ms / 1e9}
+    cs.append(('gemm_speed_qkv_shape', gemm_speed))
     return cs
 
 
