@@ -113,7 +113,8 @@ def test_sample_draws_like_reference(oracle_sd):
     torch.manual_seed(5)
     x_init = torch.randn(2, 6, 128, device='cuda')
     x2 = m.sample_from(inp['h'].cuda(), inp['s'].cuda(), x_init, 2)
-    assert torch.equal(x1, x2)
+    # not bit-identical: the u-head mean accumulates with fp32 atomics (order varies run to run)
+    assert torch.allclose(x1, x2, rtol=1e-4, atol=1e-4)
 
 
 def test_large_shape_properties(oracle_sd):
