@@ -125,6 +125,22 @@ OSD_API int osd_sample(const float* const* params, const void* packed, int mode,
                        const float* rope, float* x, int num_steps, float c0, int B, int L, int a_batch,
                        void* workspace, void* extra, float* eta_u0_out, void* stream);
 
+/* Backward of the attention kernel (gradient of attn.py:82): dqkv bf16 [B*L, 3*H*64] receives (dq | dk | dv)
+ * w.r.t. the roped q, k and v; dsum fp32 [B,H,L] is scratch (rowsum(dO o O)). */
+OSD_API int osd_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, void* dqkv,
+                         int B, int L, int H, void* stream);
+
+/* Gradient of DiffusionModel.forward (what autograd computes for the reference at train.py:84 + Lightning's
+ * backward): given du [B] and dv [B,6,L], ACCUMULATES the parameter gradients into grads[164] (HOST array of
+ * DEVICE fp32 pointers, parameter shapes).  `workspace` is the save=1 workspace the forward filled;
+ * bwd_workspace = osd_backward_workspace_bytes().  audio / style / xt are the forward's inputs (data: no
+ * gradient is produced for them).  Training shape only: a_batch == B. */
+OSD_API size_t osd_backward_workspace_bytes(int B, int L, int a_batch);
+OSD_API int osd_pred_backward(const float* const* params, const void* packed, int mode, const void* a_tok,
+                              const float* cond, const float* rope, const float* audio, const float* style,
+                              const float* xt, const float* du, const float* dv, float* const* grads, int B, int L,
+                              int a_batch, void* workspace, void* bwd_workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

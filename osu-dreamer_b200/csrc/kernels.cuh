@@ -29,7 +29,36 @@ int launch_sample_eta(const float* u, int B, float sqrt_c0, int num_steps, float
 int launch_pack_weight(const float* src, void* dst, int dst_fp32, int rows_src, int cols_src, int rows_dst,
                        int cols_dst, int split_at, int split_pad, cudaStream_t stream);
 
-// attention (attn_fwd.cu)
+// backward (elementwise_bwd.cu, uhead_bwd.cu)
+int launch_final_bwd(const float* x, const float* dv, const float* Wo, float* dx, float* dWo, float* dbo, int B, int L,
+                     cudaStream_t s);
+int launch_postnorm_gate_bwd(const float* dx, const float* h, const float* mod, void* dh, float* dmod, float* dbias,
+                             int B, int L, cudaStream_t s);
+int launch_prenorm_mod_bwd(const void* dz, const float* x, const float* mod, float* dx, float* dmod, float* dbcl, int B,
+                           int L, cudaStream_t s);
+int launch_dwconv_prenorm_bwd(const void* dz2, const void* hmod, const float* x1, const float* mod, const float* wconv,
+                              float* dx, float* dmod, float* dw, float* db, int B, int L, cudaStream_t s);
+int launch_swiglu_norm_bwd(const void* vg, const void* dhn, const float* rinv, void* dvg, float* dbvg, int T,
+                           cudaStream_t s);
+int launch_colsum_bf16(const void* m, float* out, int T, int N, cudaStream_t s);
+int launch_qknorm_rope_bwd(void* dqkv, const void* raw, const float* rope, const float* qw, const float* kw,
+                           float* dqw, float* dkw, float* dbias, int B, int L, cudaStream_t s);
+int launch_proj_in_bwd(const float* dx, const float* xt, float* dW, float* db, int B, int L, cudaStream_t s);
+int launch_silu_bwd(const float* da, const float* pre, void* dpre, float* db, int T, cudaStream_t s);
+int launch_linear_small_bwd(const float* dout, const float* pre_or_null, const float* in, const float* W, float* dW,
+                            float* db, float* din, float* dpre_scratch, int Bn, int N, int K, int silu,
+                            cudaStream_t s);
+int launch_unpack_grad(const float* src, float* dst, int rows_src, int cols_src, int rows_dst, int cols_dst,
+                       int split_at, int split_pad, cudaStream_t s);
+int launch_u_final_bwd(const float* du, const float* fsum, const float* umod, const float* wout, const float* bout,
+                       float u_scale, int L, float* dfsum, float* dumod, float* dwout, float* dbout, int B,
+                       cudaStream_t s);
+int launch_u_head_bwd(const float* xt, const float* const* w8, const float* dfsum, float* const* g8, int B, int L,
+                      cudaStream_t s);
+
+// attention (attn_fwd.cu, attn_bwd.cu)
+int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, void* dqkv, int B,
+                    int L, int H, cudaStream_t stream);
 int launch_attn_fwd(const void* qkv, void* y, float* lse, int B, int L, int H, cudaStream_t stream);
 
 }  // namespace osd

@@ -211,6 +211,175 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
   return 0;
 }
 
+// ================================================================================================ backward
+struct BwdPlan {
+  size_t dx, dh, dhn, dvg, dz2, dy, dqkv, dz, dsum, da_tok, a_pre, da_pre, audio_tm, dcond, dfsum, dpre_s;
+  size_t gWvg, gWpo, gbvg;  // padded fp32 gradient scratch
+  size_t total;
+};
+static BwdPlan make_bwd_plan(int B, int L, int a_batch) {
+  BwdPlan p;
+  const size_t T = (size_t)B * L, Ta = (size_t)a_batch * L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o += al(bytes);
+    return r;
+  };
+  p.dx = take(T * 512 * 4);
+  p.dh = take(T * 512 * 2);
+  p.dhn = take(T * OSD_HIDP * 2);
+  p.dvg = take(T * 2 * OSD_HIDP * 2);
+  p.dz2 = take(T * 512 * 2);
+  p.dy = take(T * 1024 * 2);
+  p.dqkv = take(T * 3072 * 2);
+  p.dz = take(T * 512 * 2);
+  p.dsum = take(T * 16 * 4);
+  p.da_tok = take(Ta * 128 * 4);
+  p.a_pre = take(Ta * 128 * 4);
+  p.da_pre = take(Ta * 128 * 2);
+  p.audio_tm = take(Ta * 128 * 2);
+  p.dcond = take(CondPack::floats(B) * 4);
+  p.dfsum = take((size_t)B * 64 * 4);
+  p.dpre_s = take((size_t)B * 512 * 4 * 2);
+  p.gWvg = take((size_t)2 * OSD_HIDP * 512 * 4);
+  p.gWpo = take((size_t)512 * OSD_HIDP * 4);
+  p.gbvg = take((size_t)2 * OSD_HIDP * 4);
+  p.total = o;
+  return p;
+}
+
+static int split_for(int M, int N, int K, int bn) {
+  const int tiles = ceil_div(M, 128) * ceil_div(N, bn);
+  const int kb = ceil_div(K, 64);
+  int s = ceil_div(4 * num_sms(), tiles);
+  if (s > kb) s = kb;
+  if (s < 1) s = 1;
+  return s;
+}
+// dX[M,N] = dY[M,K] * W[K,N]   (W stored [K rows][N] row-major = MN-major B operand)
+static int gemm_dgrad(const void* dY, int64_t ldy, const void* W, int64_t ldw, void* dX, int64_t ldx, int x_fp32,
+                      int atomic, int M, int N, int K, cudaStream_t s) {
+  GemmArgs g;
+  g.A = dY; g.a_major = MAJOR_K; g.lda = ldy; g.B = W; g.b_major = MAJOR_MN; g.ldb = ldw;
+  g.M = M; g.N = N; g.K = K; g.elem = ELEM_BF16; g.epi = atomic ? EPI_ATOMIC : EPI_STORE; g.C = dX; g.ldc = ldx;
+  g.c_fp32 = x_fp32; g.split_k = 1;
+  return launch_gemm(g, s);
+}
+// dW[M,N] += dY[T,M]^T * X[T,N]   (both operands MN-major, contraction over tokens, split-K + fp32 atomics)
+static int gemm_wgrad(const void* dY, int64_t ldy, const void* X, int64_t ldx, float* dW, int64_t ldw, int M, int N,
+                      int T, cudaStream_t s) {
+  GemmArgs g;
+  g.A = dY; g.a_major = MAJOR_MN; g.lda = ldy; g.B = X; g.b_major = MAJOR_MN; g.ldb = ldx;
+  g.M = M; g.N = N; g.K = T; g.elem = ELEM_BF16; g.epi = EPI_ATOMIC; g.C = dW; g.ldc = ldw; g.c_fp32 = 1;
+  g.split_k = split_for(M, N, T, (N % 256 == 0) ? 256 : 128);
+  return launch_gemm(g, s);
+}
+
+static int pred_backward(const FwdCtx& c, const float* audio, const float* style, const float* xt, const float* du,
+                         const float* dv, float* const* G, uint8_t* bw, cudaStream_t s) {
+  const int B = c.B, L = c.L, T = B * L;
+  OSD_CHECK(c.mode == OSD_BF16, "pred_backward: bf16 mode only");
+  OSD_CHECK(c.a_batch == B, "pred_backward: broadcast audio (a_batch=1) is an inference-only shape");
+  OSD_CHECK(c.save, "pred_backward: forward must have been run with save=1");
+  const ActPlan& pl = c.plan;
+  const BwdPlan bp = make_bwd_plan(B, L, c.a_batch);
+  auto LB = [&](int l) { return c.ws + (size_t)l * pl.layer_stride; };
+  float* dx = reinterpret_cast<float*>(bw + bp.dx);
+  void* dh = bw + bp.dh;
+  float* dcond = reinterpret_cast<float*>(bw + bp.dcond);
+  CondPack dc{dcond, B};
+  float* da_tok = reinterpret_cast<float*>(bw + bp.da_tok);
+  float* gWvg = reinterpret_cast<float*>(bw + bp.gWvg);
+  float* gWpo = reinterpret_cast<float*>(bw + bp.gWpo);
+  float* gbvg = reinterpret_cast<float*>(bw + bp.gbvg);
+  OSD_CUDA(cudaMemsetAsync(dcond, 0, CondPack::floats(B) * 4, s));
+  OSD_CUDA(cudaMemsetAsync(da_tok, 0, (size_t)T * 128 * 4, s));
+
+  // ---- heads
+  OSD_TRY(launch_final_bwd(reinterpret_cast<float*>(c.ws + pl.x_final), dv, c.P[P_OUT_W], dx, G[P_OUT_W], G[P_OUT_B], B,
+                           L, s));
+  {
+    float* dfsum = reinterpret_cast<float*>(bw + bp.dfsum);
+    OSD_TRY(launch_u_final_bwd(du, reinterpret_cast<float*>(c.ws + pl.fsum), c.cond.umod(), c.P[P_UOUT_W],
+                               c.P[P_UOUT_B], sqrtf(2.0f * OSD_E), L, dfsum, const_cast<float*>(dc.umod()),
+                               G[P_UOUT_W], G[P_UOUT_B], B, s));
+    const float* uw[8] = {c.P[P_UH0_W], c.P[P_UH0_B], c.P[P_UH1_W], c.P[P_UH1_B],
+                          c.P[P_UH3_W], c.P[P_UH3_B], c.P[P_UH4_W], c.P[P_UH4_B]};
+    float* ug[8] = {G[P_UH0_W], G[P_UH0_B], G[P_UH1_W], G[P_UH1_B], G[P_UH3_W], G[P_UH3_B], G[P_UH4_W], G[P_UH4_B]};
+    OSD_TRY(launch_u_head_bwd(xt, uw, dfsum, ug, B, L, s));
+  }
+
+  for (int l = 7; l >= 0; --l) {
+    uint8_t* lb = LB(l);
+    const float* x0 = reinterpret_cast<float*>(lb + pl.x0);
+    const float* x1 = reinterpret_cast<float*>(lb + pl.x1);
+    float* dm1 = const_cast<float*>(dc.mod1(l));
+    float* dm2 = const_cast<float*>(dc.mod2(l));
+    // ---------------- ffn sub-block
+    OSD_TRY(launch_postnorm_gate_bwd(dx, reinterpret_cast<float*>(lb + pl.f), c.cond.mod2(l), dh, dm2,
+                                     G[lp(l, L_PO_B)], B, L, s));
+    OSD_TRY(gemm_dgrad(dh, 512, c.W.po(l), OSD_HIDP, bw + bp.dhn, OSD_HIDP, 0, 0, T, OSD_HIDP, 512, s));
+    OSD_CUDA(cudaMemsetAsync(gWpo, 0, (size_t)512 * OSD_HIDP * 4, s));
+    OSD_TRY(gemm_wgrad(dh, 512, lb + pl.hn, OSD_HIDP, gWpo, OSD_HIDP, 512, OSD_HIDP, T, s));
+    OSD_TRY(launch_unpack_grad(gWpo, G[lp(l, L_PO_W)], 512, OSD_HIDP, 512, OSD_HID, 0, 0, s));
+    OSD_CUDA(cudaMemsetAsync(gbvg, 0, (size_t)2 * OSD_HIDP * 4, s));
+    OSD_TRY(launch_swiglu_norm_bwd(lb + pl.vg, bw + bp.dhn, reinterpret_cast<float*>(lb + pl.rinv2), bw + bp.dvg, gbvg,
+                                   T, s));
+    OSD_TRY(launch_unpack_grad(gbvg, G[lp(l, L_VG_B)], 2 * OSD_HIDP, 1, 2 * OSD_HID, 1, OSD_HID, OSD_HIDP, s));
+    OSD_TRY(gemm_dgrad(bw + bp.dvg, 2 * OSD_HIDP, c.W.vg(l), 512, bw + bp.dz2, 512, 0, 0, T, 512, 2 * OSD_HIDP, s));
+    OSD_CUDA(cudaMemsetAsync(gWvg, 0, (size_t)2 * OSD_HIDP * 512 * 4, s));
+    OSD_TRY(gemm_wgrad(bw + bp.dvg, 2 * OSD_HIDP, lb + pl.z2, 512, gWvg, 512, 2 * OSD_HIDP, 512, T, s));
+    OSD_TRY(launch_unpack_grad(gWvg, G[lp(l, L_VG_W)], 2 * OSD_HIDP, 512, 2 * OSD_HID, 512, OSD_HID, OSD_HIDP, s));
+    OSD_TRY(launch_dwconv_prenorm_bwd(bw + bp.dz2, lb + pl.hmod, x1, c.cond.mod2(l), c.P[lp(l, L_DW_W)], dx, dm2,
+                                      G[lp(l, L_DW_W)], G[lp(l, L_DW_B)], B, L, s));
+    // ---------------- attention sub-block
+    OSD_TRY(launch_postnorm_gate_bwd(dx, reinterpret_cast<float*>(lb + pl.o), c.cond.mod1(l), dh, dm1,
+                                     G[lp(l, L_OUT_B)], B, L, s));
+    OSD_TRY(gemm_dgrad(dh, 512, c.W.out(l), 1024, bw + bp.dy, 1024, 0, 0, T, 1024, 512, s));
+    OSD_TRY(gemm_wgrad(dh, 512, lb + pl.y, 1024, G[lp(l, L_OUT_W)], 1024, 512, 1024, T, s));
+    OSD_TRY(launch_attn_bwd(lb + pl.qkv, lb + pl.y, bw + bp.dy, reinterpret_cast<float*>(lb + pl.lse),
+                            reinterpret_cast<float*>(bw + bp.dsum), bw + bp.dqkv, B, L, 16, s));
+    OSD_TRY(launch_qknorm_rope_bwd(bw + bp.dqkv, lb + pl.qkv_raw, c.rope, c.P[lp(l, L_QN_W)], c.P[lp(l, L_KN_W)],
+                                   G[lp(l, L_QN_W)], G[lp(l, L_KN_W)], G[lp(l, L_QKV_B)], B, L, s));
+    OSD_TRY(gemm_dgrad(bw + bp.dqkv, 3072, c.W.qkv(l), 512, bw + bp.dz, 512, 0, 0, T, 512, 3072, s));
+    OSD_TRY(gemm_wgrad(bw + bp.dqkv, 3072, lb + pl.z, 512, G[lp(l, L_QKV_W)], 512, 3072, 512, T, s));
+    OSD_TRY(launch_prenorm_mod_bwd(bw + bp.dz, x0, c.cond.mod1(l), dx, dm1, G[lp(l, L_CL_B)], B, L, s));
+    OSD_TRY(gemm_wgrad(bw + bp.dz, 512, c.a_tok, 128, G[lp(l, L_CL_W)], 128, 512, 128, T, s));
+    OSD_TRY(gemm_dgrad(bw + bp.dz, 512, c.W.cl(l), 128, da_tok, 128, 1, 1, T, 128, 512, s));
+  }
+  OSD_TRY(launch_proj_in_bwd(dx, xt, G[P_IN_W], G[P_IN_B], B, L, s));
+
+  // ---- audio branch: a = silu(pre), pre = audio_tm Wa^T + ba
+  {
+    OSD_TRY(launch_cf_to_tm(audio, bw + bp.audio_tm, 1, B, 128, L, s));
+    GemmArgs g;
+    g.A = bw + bp.audio_tm; g.B = c.W.wa(); g.lda = 128; g.ldb = 128; g.M = T; g.N = 128; g.K = 128;
+    g.elem = ELEM_BF16; g.epi = EPI_STORE; g.C = bw + bp.a_pre; g.ldc = 128; g.c_fp32 = 1; g.bias = c.P[P_AUDIO_B];
+    OSD_TRY(launch_gemm(g, s));
+    OSD_TRY(launch_silu_bwd(da_tok, reinterpret_cast<float*>(bw + bp.a_pre), bw + bp.da_pre, G[P_AUDIO_B], T, s));
+    OSD_TRY(gemm_wgrad(bw + bp.da_pre, 128, bw + bp.audio_tm, 128, G[P_AUDIO_W], 128, 128, 128, T, s));
+  }
+  // ---- conditioning vectors (fp32, tiny)
+  float* dcg = dcond;  // [B,512]
+  float* scratch = reinterpret_cast<float*>(bw + bp.dpre_s);
+  for (int l = 0; l < 8; ++l) {
+    OSD_TRY(launch_linear_small_bwd(dc.mod1(l), nullptr, c.cond.cg(), c.P[lp(l, L_SSG1_W)], G[lp(l, L_SSG1_W)],
+                                    G[lp(l, L_SSG1_B)], dcg, nullptr, B, 1536, 512, 0, s));
+    OSD_TRY(launch_linear_small_bwd(dc.mod2(l), nullptr, c.cond.cg(), c.P[lp(l, L_SSG2_W)], G[lp(l, L_SSG2_W)],
+                                    G[lp(l, L_SSG2_B)], dcg, nullptr, B, 1536, 512, 0, s));
+  }
+  OSD_TRY(launch_linear_small_bwd(dc.umod(), nullptr, c.cond.cg(), c.P[P_UMOD_W], G[P_UMOD_W], G[P_UMOD_B], dcg, nullptr,
+                                  B, 128, 512, 0, s));
+  // cg = silu(pre_s): recompute the pre-activation, then the layer's own gradients
+  float* pre_s = scratch;
+  float* dpre_s = scratch + (size_t)B * 512;
+  OSD_TRY(launch_linear_small(style, c.P[P_STYLE_W], c.P[P_STYLE_B], pre_s, B, 512, 32, 0, s));
+  OSD_TRY(launch_linear_small_bwd(dcg, pre_s, style, c.P[P_STYLE_W], G[P_STYLE_W], G[P_STYLE_B], nullptr, dpre_s, B, 512,
+                                  32, 1, s));
+  return 0;
+}
+
 }  // namespace osd
 
 // ================================================================================================
@@ -305,6 +474,39 @@ int osd_sample(const float* const* params, const void* packed, int mode, const v
   if (eta_u0_out != nullptr)
     OSD_CUDA(cudaMemcpyAsync(eta_u0_out, eta, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return 0;
+}
+
+
+size_t osd_backward_workspace_bytes(int B, int L, int a_batch) { return make_bwd_plan(B, L, a_batch).total; }
+
+// Gradient of osd_pred_forward(save=1) composed with osd_precompute_conditioning: given du [B], dv [B,6,L]
+// ACCUMULATES d(loss)/d(parameter) into grads[164] (fp32, parameter shapes, caller zero-initialised or
+// carrying earlier accumulation).
+int osd_pred_backward(const float* const* params, const void* packed, int mode, const void* a_tok, const float* cond,
+                      const float* rope, const float* audio, const float* style, const float* xt, const float* du,
+                      const float* dv, float* const* grads, int B, int L, int a_batch, void* workspace,
+                      void* bwd_workspace, void* stream) {
+  OSD_CHECK(params && packed && a_tok && cond && rope && audio && style && xt && du && dv && grads && workspace &&
+                bwd_workspace,
+            "osd_pred_backward: null argument");
+  FwdCtx c;
+  c.P = params;
+  c.W = PackedW{static_cast<const uint8_t*>(packed), packed_layout(mode)};
+  c.mode = mode; c.B = B; c.L = L; c.a_batch = a_batch;
+  c.cond = CondPack{cond, B};
+  c.a_tok = a_tok;
+  c.rope = rope;
+  c.ws = static_cast<uint8_t*>(workspace);
+  c.plan = make_plan(B, L, a_batch, mode, 1);
+  c.save = 1;
+  c.cl_hoisted = nullptr;
+  return pred_backward(c, audio, style, xt, du, dv, grads, static_cast<uint8_t*>(bwd_workspace),
+                       static_cast<cudaStream_t>(stream));
+}
+
+int osd_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, void* dqkv, int B, int L,
+                 int H, void* stream) {
+  return launch_attn_bwd(qkv, y, dy, lse, dsum, dqkv, B, L, H, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -170,7 +170,7 @@ class DiffusionModel(nn.Module):
         rt = self._rt
         k = (B, L, a_batch, save, tag)
         if k not in rt.ws:
-            if len(rt.ws) > 4:
+            if len(rt.ws) > 6:
                 rt.ws.clear()
             dev = self._params()[0].device
             n = lib.workspace_bytes(B, L, a_batch, self._mode(), save) if tag == '' else lib.sample_extra_bytes(B, L, a_batch)

@@ -181,3 +181,27 @@ def channels_to_tokens(x, out_dtype=torch.bfloat16):
     _check(load().osd_channels_to_tokens(ptr(x), ptr(out), c_int(1 if out_dtype == torch.float32 else 0), c_int(B),
                                          c_int(C), c_int(L), stream()))
     return out
+
+
+def backward_workspace_bytes(B, L, a_batch):
+    return _sz('osd_backward_workspace_bytes', B, L, a_batch)
+
+
+def grad_array(tensors):
+    assert len(tensors) == NUM_PARAMS
+    return (c_void_p * NUM_PARAMS)(*[t.data_ptr() for t in tensors])
+
+
+def pred_backward(parr, packed, mode, a_tok, cond, rope, audio, style, xt, du, dv, garr, a_batch, workspace, bwd_ws):
+    B, _, L = xt.shape
+    _check(load().osd_pred_backward(parr, ptr(packed), c_int(mode), ptr(a_tok), ptr(cond), ptr(rope), ptr(audio),
+                                    ptr(style), ptr(xt), ptr(du), ptr(dv), garr, c_int(B), c_int(L), c_int(a_batch),
+                                    ptr(workspace), ptr(bwd_ws), stream()))
+
+
+def attn_bwd(qkv, y, dy, lse, B, L, H=16):
+    dqkv = torch.empty_like(qkv)
+    dsum = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device)
+    _check(load().osd_attn_bwd(ptr(qkv), ptr(y), ptr(dy), ptr(lse), ptr(dsum), ptr(dqkv), c_int(B), c_int(L), c_int(H),
+                               stream()))
+    return dqkv
