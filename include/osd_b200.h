@@ -53,6 +53,8 @@ extern "C" {
 
 OSD_API int osd_abi_version(void);
 OSD_API const char* osd_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+OSD_API unsigned long long osd_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Building blocks (exported for unit tests and micro-benchmarks; the model entry points below are
@@ -140,6 +142,17 @@ OSD_API int osd_pred_backward(const float* const* params, const void* packed, in
                               const float* cond, const float* rope, const float* audio, const float* style,
                               const float* xt, const float* du, const float* dv, float* const* grads, int B, int L,
                               int a_batch, void* workspace, void* bwd_workspace, void* stream);
+
+/* Fused optimizer tail of fit-denoiser on FLAT fp32 buffers of n elements: global-norm clip
+ * (gradient_clip_val, model.yml:39; coefficient min(1, max/(norm+1e-6)) as torch.nn.utils.clip_grad_norm_),
+ * torch.optim.AdamW update (train.py:111; step is 1-based) and the EMA of the parameters
+ * (get_ema_multi_avg_fn(.99), train.py:67,126; ema_copy != 0 on the first update; ema may be NULL).
+ * grad_scale multiplies the raw gradients first (1/world_size after a summing allreduce).
+ * acc_scratch: 1 double, scal_out: 2 floats {grad norm, applied multiplier}; no host synchronisation. */
+OSD_API int osd_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, size_t n, int step, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                               float grad_scale, float ema_decay, int ema_copy, double* acc_scratch, float* scal_out,
+                               void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,12 +37,20 @@ class _DenoiserFn(torch.autograd.Function):
         B, _, L = xt.shape
         a_batch = audio.shape[0]
         dev = xt.device
-        sizes = [int(torch.Size(s).numel()) for s in ctx.shapes]
-        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-        grads, off = [], 0
-        for s, n in zip(ctx.shapes, sizes):
-            grads.append(flat[off:off + n].view(s))
-            off += n
+        targets = getattr(model, '_grad_targets', None)
+        direct = targets is not None and len(targets) == len(ctx.shapes) and targets[0].device == dev
+        if direct:
+            # the trainer owns one flat gradient buffer: accumulate straight into it, autograd sees no param grads
+            grads = targets
+        else:
+            # one zeroed buffer, every tensor 256-byte aligned (the kernels use 16-byte vector atomics)
+            sizes = [int(torch.Size(s).numel()) for s in ctx.shapes]
+            padded = [(n + 63) // 64 * 64 for n in sizes]
+            flat = torch.zeros(sum(padded), dtype=torch.float32, device=dev)
+            grads, off = [], 0
+            for s, n, pn in zip(ctx.shapes, sizes, padded):
+                grads.append(flat[off:off + n].view(s))
+                off += pn
         du = torch.zeros(B, device=dev) if du is None else du.float().contiguous()
         dv = torch.zeros(B, 6, L, device=dev) if dv is None else dv.float().contiguous()
         ws = model._workspace(B, L, a_batch, 1)
@@ -51,6 +59,8 @@ class _DenoiserFn(torch.autograd.Function):
             rt.ws[key] = torch.empty(lib.backward_workspace_bytes(B, L, a_batch), dtype=torch.uint8, device=dev)
         lib.pred_backward(rt.parr, rt.packed, model._mode(), a_tok, cond, model._rope(L, dev), audio, style, xt, du, dv,
                           lib.grad_array(grads), a_batch, ws, rt.ws[key])
+        if direct:
+            return (None, None, None, None, *([None] * len(grads)))
         return (None, None, None, None, *grads)
 
 

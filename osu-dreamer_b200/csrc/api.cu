@@ -11,6 +11,7 @@ extern "C" {
 
 int osd_abi_version(void) { return OSD_ABI_VERSION; }
 const char* osd_last_error(void) { return get_error(); }
+unsigned long long osd_launch_count(void) { return launch_count(); }
 
 int osd_gemm(const void* A, int a_major, int64_t lda, const void* B, int b_major, int64_t ldb, void* C,
              int64_t ldc, int c_fp32, const float* bias, int M, int N, int K, int elem, int epi, int split_k,

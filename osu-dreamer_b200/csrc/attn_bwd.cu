@@ -461,7 +461,7 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
   const int dh = H * 64;
   attn_bwd_prep_kernel<<<ceil_div(B * L, 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(y),
                                                                static_cast<const __nv_bfloat16*>(dy), dsum, B, H, L);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   AttnBwdParams p;
   {
     uint64_t dims[3] = {(uint64_t)3 * dh, (uint64_t)L, (uint64_t)B};
@@ -492,9 +492,9 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
   const long long grid = (long long)ceil_div(L, 128) * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_bwd: grid too large");
   attn_bwd_dkdv_kernel<<<(unsigned)grid, BW_THREADS, DKV_SMEM_BYTES, stream>>>(p);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   attn_bwd_dq_kernel<<<(unsigned)grid, BW_THREADS, DQ_SMEM_BYTES, stream>>>(p);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 

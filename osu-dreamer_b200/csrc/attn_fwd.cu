@@ -320,7 +320,7 @@ int launch_attn_fwd(const void* qkv, void* y, float* lse, int B, int L, int H, c
   const long long grid = (long long)n_qt * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_fwd: grid too large");
   attn_fwd_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(p);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 

@@ -15,6 +15,10 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+static unsigned long long g_launches = 0;
+void count_launch() { ++g_launches; }
+unsigned long long launch_count() { return g_launches; }
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;

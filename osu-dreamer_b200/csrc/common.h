@@ -29,6 +29,13 @@ const char* get_error();
     }                                                                                        \
   } while (0)
 
+// after every kernel launch: count it (osd_launch_count) and surface launch-configuration errors
+#define OSD_LAUNCHED()                   \
+  do {                                   \
+    osd::count_launch();                 \
+    OSD_CUDA(cudaGetLastError());        \
+  } while (0)
+
 #define OSD_TRY(expr)      \
   do {                     \
     int _s = (expr);       \
@@ -36,6 +43,8 @@ const char* get_error();
   } while (0)
 
 int num_sms();
+void count_launch();
+unsigned long long launch_count();
 
 // 2D/3D tiled tensor map, SWIZZLE_128B, element size 2 (bf16) or 4 (fp32/tf32).
 // dims[0] is the contiguous dimension; strides_bytes[i] is the byte stride of dims[i+1].

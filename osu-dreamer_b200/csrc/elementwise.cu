@@ -31,7 +31,7 @@ int launch_rope_table(const float* inv_freq_host, int L, float* rope, cudaStream
   for (int i = 0; i < 32; ++i) f.v[i] = inv_freq_host[i];
   const int n = L * 32;
   rope_table_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(f, L, rope);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -59,7 +59,7 @@ int launch_cf_to_tm(const float* in, void* out, int out_bf16, int B, int C, int 
     cf_to_tm_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), C, L);
   else
     cf_to_tm_kernel<float><<<grid, block, 0, stream>>>(in, static_cast<float*>(out), C, L);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -86,7 +86,7 @@ int launch_tm_to_cf(const void* in, int in_fp32, float* out, int B, int C, int L
     tm_to_cf_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(in), out, C, L);
   else
     tm_to_cf_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), out, C, L);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -113,7 +113,7 @@ __global__ void linear_small_kernel(const float* __restrict__ in, const float* _
 int launch_linear_small(const float* in, const float* W, const float* bias, float* out, int Bn, int N, int K,
                         int silu, cudaStream_t stream) {
   linear_small_kernel<<<ceil_div(N, 8), 256, 0, stream>>>(in, W, bias, out, Bn, N, K, silu);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -147,7 +147,7 @@ __global__ void proj_in_kernel(const float* __restrict__ xt, const float* __rest
 int launch_proj_in(const float* xt, const float* W, const float* bias, float* x, int B, int L, cudaStream_t stream) {
   const int T = B * L;
   proj_in_kernel<<<ceil_div(T, 8), 256, 0, stream>>>(xt, W, bias, x, L, T);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -215,7 +215,7 @@ int launch_prenorm_mod(const float* x, const float* mod, const void* cl, void* z
   else
     prenorm_mod_kernel<__nv_bfloat16><<<ceil_div(T, 8), 256, 0, stream>>>(
         x, mod, static_cast<const __nv_bfloat16*>(cl), static_cast<__nv_bfloat16*>(z), L, T, cl_bcast);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -244,7 +244,7 @@ int launch_postnorm_gate_add(const float* x, const float* h, const float* mod, f
                              cudaStream_t stream) {
   const int T = B * L;
   postnorm_gate_add_kernel<<<ceil_div(T, 8), 256, 0, stream>>>(x, h, mod, x_out, L, T);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -327,7 +327,7 @@ int launch_prenorm_mod_dwconv(const float* x, const float* mod, const float* wco
     k<<<grid, 256, smem, stream>>>(x, mod, wconv, bconv, static_cast<__nv_bfloat16*>(z),
                                    static_cast<__nv_bfloat16*>(hmod_out), L);
   }
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -389,7 +389,7 @@ int launch_swiglu_norm(const void* vg, void* hn, float* rinv_out, int is_fp32, i
   else
     swiglu_norm_kernel<__nv_bfloat16><<<ceil_div(T, 8), 256, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(vg), static_cast<__nv_bfloat16*>(hn), rinv_out, T);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -429,7 +429,7 @@ int launch_final_norm_proj_out(const float* x, const float* Wo, const float* bo,
                                cudaStream_t stream) {
   const int T = B * L;
   final_norm_proj_out_kernel<<<ceil_div(T, 8), 256, 0, stream>>>(x, Wo, bo, v, L, T);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -513,7 +513,7 @@ int launch_u_head(const float* xt, const float* const* w8, float* fsum, float* h
   OSD_CUDA(cudaMemsetAsync(fsum, 0, (size_t)B * 64 * sizeof(float), stream));
   dim3 grid(ceil_div(L, UH_TOK), B);
   u_head_kernel<<<grid, 256, 0, stream>>>(xt, w, fsum, h1_save, h2pre_save, L);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -540,7 +540,7 @@ __global__ void u_final_kernel(const float* __restrict__ fsum, const float* __re
 int launch_u_final(const float* fsum, const float* umod, const float* wout, const float* bout, float u_scale, int L,
                    float* u, int B, cudaStream_t stream) {
   u_final_kernel<<<ceil_div(B, 4), 128, 0, stream>>>(fsum, umod, wout, bout, u_scale, 1.0f / (float)L, u, B);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -556,7 +556,7 @@ int launch_sample_update(float* x, const float* v, const float* u, const float* 
                          cudaStream_t stream) {
   const size_t n = (size_t)B * 6 * L;
   sample_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, v, u, eta_dev, 6 * L, n);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -574,7 +574,7 @@ __global__ void sample_eta_kernel(const float* __restrict__ u, int Bn, float sqr
 }
 int launch_sample_eta(const float* u, int B, float sqrt_c0, int num_steps, float* eta_out, cudaStream_t stream) {
   sample_eta_kernel<<<1, 32, 0, stream>>>(u, B, sqrt_c0, 1.0f / (float)num_steps, eta_out);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -613,7 +613,7 @@ int launch_pack_weight(const float* src, void* dst, int dst_fp32, int rows_src, 
   else
     pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), rows_src,
                                                                 cols_src, rows_dst, cols_dst, split_at, split_pad);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 

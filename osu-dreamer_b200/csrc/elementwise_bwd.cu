@@ -116,7 +116,7 @@ int launch_final_bwd(const float* x, const float* dv, const float* Wo, float* dx
                      cudaStream_t s) {
   dim3 grid(ceil_div(L, TOKB), B);
   final_bwd_kernel<<<grid, 256, 0, s>>>(x, dv, Wo, dx, dWo, dbo, L);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -174,7 +174,7 @@ int launch_postnorm_gate_bwd(const float* dx, const float* h, const float* mod, 
                              int B, int L, cudaStream_t s) {
   dim3 grid(ceil_div(L, TOKB), B);
   postnorm_gate_bwd_kernel<<<grid, 256, 0, s>>>(dx, h, mod, static_cast<__nv_bfloat16*>(dh), dmod, dbias, L);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -232,7 +232,7 @@ int launch_prenorm_mod_bwd(const void* dz, const float* x, const float* mod, flo
                            int L, cudaStream_t s) {
   dim3 grid(ceil_div(L, TOKB), B);
   prenorm_mod_bwd_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dz), x, mod, dx, dmod, dbcl, L);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -372,7 +372,7 @@ int launch_dwconv_prenorm_bwd(const void* dz2, const void* hmod, const float* x1
   dwconv_prenorm_bwd_kernel<<<grid, 256, smem, s>>>(static_cast<const __nv_bfloat16*>(dz2),
                                                     static_cast<const __nv_bfloat16*>(hmod), x1, mod, wconv, dx, dmod,
                                                     dw, db, L);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 int launch_colsum_bf16(const void* m, float* out, int T, int N, cudaStream_t s) {
   OSD_CHECK(N % 8 == 0, "colsum: N must be a multiple of 8");
   colsum_bf16_kernel<<<ceil_div(T, 128), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(m), out, T, N);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 int launch_swiglu_norm_bwd(const void* vg, const void* dhn, const float* rinv, void* dvg, float* dbvg, int T,
@@ -464,7 +464,7 @@ int launch_swiglu_norm_bwd(const void* vg, const void* dhn, const float* rinv, v
   swiglu_norm_bwd_kernel<<<ceil_div(T, TOKB), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(vg),
                                                            static_cast<const __nv_bfloat16*>(dhn), rinv,
                                                            static_cast<__nv_bfloat16*>(dvg), dbvg, T);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return launch_colsum_bf16(dvg, dbvg, T, 2 * HIDP, s);
 }
 
@@ -597,7 +597,7 @@ int launch_qknorm_rope_bwd(void* dqkv, const void* raw, const float* rope, const
   dim3 grid(ceil_div(L, TOKB), B);
   qknorm_rope_bwd_kernel<<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(raw),
                                               rope, qw, kw, dqw, dkw, dbias, L);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(256) proj_in_bwd_kernel(const float* __restric
 int launch_proj_in_bwd(const float* dx, const float* xt, float* dW, float* db, int B, int L, cudaStream_t s) {
   dim3 grid(ceil_div(L, TOKB), B);
   proj_in_bwd_kernel<<<grid, 256, 0, s>>>(dx, xt, dW, db, L);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -669,7 +669,7 @@ __global__ void silu_bwd_kernel(const float* __restrict__ da, const float* __res
 }
 int launch_silu_bwd(const float* da, const float* pre, void* dpre, float* db, int T, cudaStream_t s) {
   silu_bwd_kernel<<<ceil_div(T, 64), 256, 0, s>>>(da, pre, static_cast<__nv_bfloat16*>(dpre), db, T);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -711,11 +711,11 @@ int launch_linear_small_bwd(const float* dout, const float* pre_or_null, const f
                             cudaStream_t s) {
   linear_small_bwd_w_kernel<<<ceil_div(N, 8), 256, 0, s>>>(dout, pre_or_null, in, dW, db, silu ? dpre_scratch : nullptr,
                                                            Bn, N, K, silu);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   if (din != nullptr) {
     dim3 grid(ceil_div(K, 128), Bn);
     linear_small_bwd_in_kernel<<<grid, 128, 0, s>>>(silu ? dpre_scratch : dout, W, din, Bn, N, K);
-    OSD_CUDA(cudaGetLastError());
+    OSD_LAUNCHED();
   }
   return 0;
 }
@@ -738,7 +738,7 @@ int launch_unpack_grad(const float* src, float* dst, int rows_src, int cols_src,
   const size_t n = (size_t)rows_dst * cols_dst;
   unpack_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, rows_src, cols_src, rows_dst, cols_dst,
                                                                  split_at, split_pad);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 

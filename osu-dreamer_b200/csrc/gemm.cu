@@ -353,7 +353,7 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   const int total = p.tiles_m * p.tiles_n * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
   kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(p);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 

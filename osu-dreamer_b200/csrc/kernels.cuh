@@ -56,6 +56,11 @@ int launch_u_final_bwd(const float* du, const float* fsum, const float* umod, co
 int launch_u_head_bwd(const float* xt, const float* const* w8, const float* dfsum, float* const* g8, int B, int L,
                       cudaStream_t s);
 
+// optimizer (optim.cu)
+int launch_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, size_t n, int step, float lr,
+                     float beta1, float beta2, float eps, float wd, float max_norm, float grad_scale, float ema_decay,
+                     int ema_copy, double* acc_scratch, float* scal_out, cudaStream_t s);
+
 // attention (attn_fwd.cu, attn_bwd.cu)
 int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, void* dqkv, int B,
                     int L, int H, cudaStream_t stream);

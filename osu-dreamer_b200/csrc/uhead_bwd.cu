@@ -58,7 +58,7 @@ int launch_u_final_bwd(const float* du, const float* fsum, const float* umod, co
                        cudaStream_t s) {
   u_final_bwd_kernel<<<1, 64, 0, s>>>(du, fsum, umod, wout, bout, u_scale, 1.0f / (float)L, dfsum, dumod, dwout, dbout,
                                       B);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 
@@ -260,7 +260,7 @@ int launch_u_head_bwd(const float* xt, const float* const* w8, const float* dfsu
   }
   dim3 grid(ceil_div(L, UB_TOK * UB_SUB), B);
   u_head_bwd_kernel<<<grid, 256, smem, s>>>(xt, w, dfsum, g, L);
-  OSD_CUDA(cudaGetLastError());
+  OSD_LAUNCHED();
   return 0;
 }
 

@@ -133,6 +133,8 @@ def param_array(tensors):
     for t in tensors:
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise OsdError('parameters must be contiguous fp32 CUDA tensors (no CPU path)')
+        if t.data_ptr() % 16:
+            raise OsdError('parameter storage must be 16-byte aligned (vector loads)')
     return (c_void_p * NUM_PARAMS)(*[t.data_ptr() for t in tensors])
 
 
@@ -189,6 +191,9 @@ def backward_workspace_bytes(B, L, a_batch):
 
 def grad_array(tensors):
     assert len(tensors) == NUM_PARAMS
+    for t in tensors:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()) or t.data_ptr() % 16:
+            raise OsdError('gradient buffers must be contiguous, 16-byte aligned fp32 CUDA tensors')
     return (c_void_p * NUM_PARAMS)(*[t.data_ptr() for t in tensors])
 
 
@@ -205,3 +210,17 @@ def attn_bwd(qkv, y, dy, lse, B, L, H=16):
     _check(load().osd_attn_bwd(ptr(qkv), ptr(y), ptr(dy), ptr(lse), ptr(dsum), ptr(dqkv), c_int(B), c_int(L), c_int(H),
                                stream()))
     return dqkv
+
+
+def adamw_ema_step(p, g, m, v, ema, step, lr, beta1, beta2, eps, wd, max_norm, grad_scale, ema_decay, ema_copy, acc,
+                   scal):
+    _check(load().osd_adamw_ema_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), c_size_t(p.numel()), c_int(step),
+                                     c_float(lr), c_float(beta1), c_float(beta2), c_float(eps), c_float(wd),
+                                     c_float(max_norm), c_float(grad_scale), c_float(ema_decay),
+                                     c_int(1 if ema_copy else 0), ptr(acc), ptr(scal), stream()))
+
+
+def launch_count() -> int:
+    f = load().osd_launch_count
+    f.restype = ctypes.c_ulonglong
+    return int(f())
