@@ -1,0 +1,146 @@
+"""`fit-denoiser` / `predict` entry points (reference: osu_dreamer/scripts/fit_denoiser.py:17-32,
+osu_dreamer/scripts/predict.py:21-100, wired in osu_dreamer/__main__.py:19-29).
+
+`fit-denoiser` reads the reference's own YAML schema (osu_dreamer/models/diffusion/model.yml: seed_everything /
+trainer / data / model) and runs the training loop on the CUDA path; under torchrun it is data-parallel over
+the GPUs of the box (one process per GPU, NCCL all-reduce of the gradients).  pytorch_lightning is not
+required.  `predict` needs the reference's latent / style models and audio front end, which are outside this
+package: `install()` swaps this package's DiffusionModel into an importable reference checkout so that
+`python -m osu_dreamer predict ...` runs its `diffusion.sample` call (models/inference/model.py:50) on the
+CUDA path while everything else stays the reference's.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+from pathlib import Path
+
+import click
+import torch
+import yaml
+
+from .data import LatentWindows, batches, split_mapsets, synthetic_batches
+from .trainer import DiffusionTrainer
+
+
+def install() -> None:
+    """Make the reference (if importable) use this package's DiffusionModel / args classes."""
+    from . import denoiser
+    import importlib
+    ref = importlib.import_module('osu_dreamer.models.diffusion.model')
+    ref.DiffusionModel = denoiser.DiffusionModel
+    ref.DiffusionModelArgs = denoiser.DiffusionModelArgs
+    bb = importlib.import_module('osu_dreamer.models.diffusion.backbone')
+    bb.BackboneArgs = denoiser.BackboneArgs
+    for name in ('osu_dreamer.models.inference.model', 'osu_dreamer.models.diffusion.train'):
+        if name in sys.modules:
+            sys.modules[name].DiffusionModel = denoiser.DiffusionModel
+
+
+def build_trainer(cfg: dict) -> DiffusionTrainer:
+    m = dict(cfg['model'])
+    clip = (cfg.get('trainer') or {}).get('gradient_clip_val', 0.0) or 0.0
+    return DiffusionTrainer(**m, gradient_clip_val=float(clip))
+
+
+def save_checkpoint(path: str, tr: DiffusionTrainer, epoch: int):
+    """Lightning-shaped checkpoint: what export-inference reads (models/inference/artifact.py:18-42)."""
+    hp = dict(tr.hparams)
+    torch.save({'state_dict': {k: v.detach().cpu() for k, v in tr.state_dict().items()}, 'hyper_parameters': hp,
+                'global_step': tr.global_step, 'epoch': epoch,
+                'optimizer_state': {k: tr._opt[k].cpu() for k in ('m', 'v')} if tr._opt else None}, path)
+
+
+def load_checkpoint(path: str, tr: DiffusionTrainer):
+    ck = torch.load(path, map_location='cpu', weights_only=False)
+    tr.load_state_dict(ck['state_dict'])
+    tr.global_step = int(ck.get('global_step', 0))
+    return ck
+
+
+@click.command('fit-denoiser')
+@click.option('-c', '--config', type=click.Path(exists=True, dir_okay=False), required=True, help='config file')
+@click.option('--ckpt-path', type=click.Path(exists=True, dir_okay=False), help='checkpoint from which to resume training')
+@click.option('--synthetic', is_flag=True, help='train on synthetic latents instead of the cached dataset')
+@click.option('--max-steps', type=int, default=None, help='stop after this many optimizer steps')
+@click.option('--out', type=click.Path(dir_okay=False), default='denoiser.ckpt', help='checkpoint to write')
+def fit_denoiser(config: str, ckpt_path: str | None, synthetic: bool, max_steps: int | None, out: str):
+    """begin a training run for the diffusion model."""
+    cfg = yaml.safe_load(open(config))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise click.ClickException('fit-denoiser needs a CUDA device: the B200 path has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    seed = cfg.get('seed_everything', True)
+    torch.manual_seed((0 if seed is True else int(seed)) + rank)
+    tr = build_trainer(cfg)
+    if ckpt_path:
+        load_checkpoint(ckpt_path, tr)
+    else:  # every rank starts from rank 0's initialisation
+        tr.diffusion_ema.module.load_state_dict(tr.diffusion.state_dict())
+    tr = tr.cuda()
+    if world > 1 and not ckpt_path:
+        import torch.distributed as dist
+        for p in list(tr.diffusion.parameters()) + list(tr.diffusion_ema.module.parameters()):
+            dist.broadcast(p.data, 0)
+    d = cfg['data']
+    tcfg = cfg.get('trainer') or {}
+    log_every = int(tcfg.get('log_every_n_steps', 50))
+    max_epochs = int(tcfg.get('max_epochs', -1))
+    if synthetic:
+        def epochs():
+            yield synthetic_batches(d['batch_size'], d['seq_len'], seed=rank)
+        val_sets = None
+    else:
+        train_sets, val_sets = split_mapsets(Path(d.get('data_path', './data')), '*.latent.npz',
+                                             d.get('max_val_count', 512), d.get('max_val_frac', .3))
+        def epochs():
+            e = 0
+            while max_epochs < 0 or e < max_epochs:
+                yield batches(LatentWindows(train_sets, d['seq_len'], d.get('shuffle_buffer_size', 1),
+                                            d.get('max_per_map', -1), seed=e), d['batch_size'], rank, world)
+                e += 1
+    t0, best = time.time(), float('inf')
+    for epoch, it in enumerate(epochs()):
+        for batch in it:
+            batch = tuple(t.cuda(non_blocking=True) for t in batch)
+            loss, log = tr.training_step(batch, world_size=world)
+            if rank == 0 and tr.global_step % log_every == 0:
+                print(f'step {tr.global_step} lr {tr.current_lr():.2e} ' +
+                      ' '.join(f'train/{k} {float(v):.4f}' for k, v in log.items()) + f' [{time.time() - t0:.0f}s]', flush=True)
+            if max_steps is not None and tr.global_step >= max_steps:
+                break
+        if rank == 0 and val_sets:
+            vals = []
+            for vb in LatentWindows(val_sets, None):
+                vals.append(tr.validation_step(tuple(t[None].cuda() for t in vb)))
+            vl = sum(float(v['val/loss']) for v in vals) / max(1, len(vals))
+            print(f'epoch {epoch} val/loss {vl:.4f}', flush=True)
+            if vl < best:  # ModelCheckpoint(monitor=val/loss, mode=min, save_top_k=1), model.yml:15-21
+                best = vl
+                save_checkpoint(out, tr, epoch)
+        if max_steps is not None and tr.global_step >= max_steps:
+            break
+    if rank == 0 and (not val_sets or not os.path.exists(out)):
+        save_checkpoint(out, tr, epoch)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+@click.group()
+def main():
+    pass
+
+
+main.add_command(fit_denoiser)
+
+if __name__ == '__main__':
+    main()

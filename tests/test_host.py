@@ -1,0 +1,117 @@
+"""CPU: host-side mirror of the reference interface (no kernels run)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from oracle import denoiser_oracle as O
+from oracle import refimport
+
+
+def _new():
+    from osu_dreamer_b200.denoiser import DiffusionModel, default_args
+    return DiffusionModel(6, 128, 32, default_args())
+
+
+def test_state_dict_contract(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'constants.npz'))
+    m = _new()
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g['names'])
+    assert [str(tuple(v.shape)) for v in sd.values()] == list(g['shapes'])
+    assert sum(p.numel() for p in m.parameters()) == int(g['n_params'])
+    assert abs(m.c0 - float(g['c0'])) < 1e-12 and abs(m.u_scale - float(g['u_scale'])) < 1e-12
+    assert len(list(m.buffers())) == 0
+
+
+def test_reference_init_facts():
+    """zero-initialised tensors (backbone.py:12-16, model.py:51-53,66-68) and u_out.bias (model.py:71)."""
+    m = _new()
+    sd = m.state_dict()
+    zero = [k for k, v in sd.items() if float(v.abs().max()) == 0.0]
+    assert len(zero) == 37
+    assert all(any(t in k for t in ('ssg1', 'ssg2', 'proj_out', 'u_mod', 'u_out.weight')) for k in zero)
+    assert abs(float(sd['u_out.bias']) + 0.4328) < 1e-6
+    assert float(sd['net.layers.0.attn.q_norm.weight'].min()) == 1.0
+    w = sd['net.layers.2.attn.qkv_proj.weight']
+    assert float(w.abs().max()) <= 512 ** -0.5 + 1e-6 and float(w.std()) > 0.02
+
+
+def test_deepcopy_and_pickle_free_runtime():
+    m = _new()
+    m2 = copy.deepcopy(m)
+    assert m2._rt is not m._rt and m2._rt.parr is None
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
+def test_args_validation():
+    from osu_dreamer_b200.denoiser import DiffusionModel, DiffusionModelArgs, BackboneArgs
+    with pytest.raises(ValueError):
+        DiffusionModel(6, 128, 32, DiffusionModelArgs(512, 512, BackboneArgs(depth=4, expand=4, head_dim=64, n_heads=16, radius=2)))
+    # dict-shaped args as produced by models/inference/artifact.py:52-71 dataclass_from_dict on older ckpts
+    DiffusionModel(6, 128, 32, DiffusionModelArgs(512, 512, dict(depth=8, expand=4, head_dim=64, n_heads=16, radius=2)))
+
+
+def test_lr_schedule_matches_golden(golden_dir):
+    from osu_dreamer_b200.trainer import LRScheduleArgs, make_lr_schedule
+    g = np.load(os.path.join(golden_dir, 'constants.npz'))
+    f = make_lr_schedule(LRScheduleArgs(warmup_steps=1000, warmup_init=0.3, decay_start=30000))
+    for s, v in zip(g['lr_steps'], g['lr_vals']):
+        assert abs(f(int(s)) - float(v)) < 1e-12
+
+
+def test_trainer_from_reference_yaml_schema():
+    from osu_dreamer_b200.cli import build_trainer
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = yaml.safe_load(open(os.path.join(root, 'osu-dreamer_b200', 'denoiser.yml')))
+    tr = build_trainer(cfg)
+    keys = list(tr.state_dict().keys())
+    assert len(keys) == 329 and 'diffusion_ema.n_averaged' in keys
+    assert sum(k.startswith('diffusion_ema.module.') for k in keys) == 164 and keys[0] == 'diffusion.proj_audio.0.weight'
+    assert tr.gradient_clip_val == 1.0 and abs(tr.current_lr() - 3e-4 * 0.3) < 1e-12
+
+
+@pytest.mark.skipif(not refimport.available(), reason='reference checkout not present on this host')
+def test_reference_checkpoint_interchange():
+    """a reference state dict loads into the mirror and back (strict), and the reference YAML parses."""
+    ns = refimport.import_reference()
+    ref = refimport.build_reference_model(ns, O.make_state_dict(1234))
+    m = _new()
+    m.load_state_dict(ref.state_dict(), strict=True)
+    ref.load_state_dict(m.state_dict(), strict=True)
+    from osu_dreamer_b200.cli import build_trainer
+    cfg = yaml.safe_load(open(os.path.join(refimport.REFERENCE_ROOT, 'osu_dreamer/models/diffusion/model.yml')))
+    assert build_trainer(cfg).val_batches == 8
+
+
+def test_flat_buffers_are_aligned():
+    from osu_dreamer_b200.trainer import _flatten, _is_flat
+    m = _new()
+    ps = list(m.parameters())
+    before = [p.detach().clone() for p in ps]
+    flat = _flatten(ps)
+    assert _is_flat(ps, flat) and all(p.data_ptr() % 256 == flat.data_ptr() % 256 for p in ps)
+    assert all(torch.equal(a, b) for a, b in zip(before, ps))
+    assert flat.numel() >= sum(p.numel() for p in ps)
+
+
+def test_latent_cache_reader(tmp_path):
+    from osu_dreamer_b200.data import LatentWindows, batches, split_mapsets
+    rng = np.random.default_rng(0)
+    for ms in range(4):
+        d = tmp_path / f'set{ms}'
+        d.mkdir()
+        l = 400 + 37 * ms
+        np.save(d / 'h.npy', rng.standard_normal((128, l)).astype(np.float32))
+        for k in range(2):
+            np.savez(d / f'm{k}.latent.npz', z=rng.standard_normal((6, l)).astype(np.float32),
+                     s=rng.standard_normal(32).astype(np.float32), labels=rng.random(5).astype(np.float32))
+    train, val = split_mapsets(tmp_path, '*.latent.npz', 2, 0.3)
+    assert len(train) == 3 and len(val) == 1
+    bs = list(batches(LatentWindows(train, 152, shuffle_buffer_size=4, max_per_map=2, seed=1), 4, pin=False))
+    assert len(bs) >= 2 and bs[0][0].shape == (4, 128, 152) and bs[0][1].shape == (4, 6, 152) and bs[0][2].shape == (4, 32)
+    full = list(LatentWindows(val, None))
+    assert full[0].z.shape[0] == 6 and full[0].h.shape[1] == full[0].z.shape[1]
