@@ -83,8 +83,12 @@ OSD_API int osd_rope_table(const float* inv_freq_host, int L, float* rope, void*
 
 /* Bidirectional flash attention (head_dim 64, bf16): replaces F.scaled_dot_product_attention at
  * osu_dreamer/common/attn.py:82.  qkv bf16 [B*L, 3*H*64] token-major (q | k | v column blocks, head h at
- * columns h*64..h*64+63 of its block); y bf16 [B*L, H*64]; lse fp32 [B, H, L] (natural log, nullable). */
-OSD_API int osd_attn_fwd(const void* qkv, void* y, float* lse, int B, int L, int H, void* stream);
+ * columns h*64..h*64+63 of its block); y bf16 [B*L, H*64]; lse fp32 [B, H, L] (natural log, nullable).
+ * bound_log2: optional DEVICE scalar, an upper bound of the scaled scores in log2 units (q,k are RMS-normalised
+ * in this model, so such a bound exists per layer): selects the fixed-max softmax; NULL -> online softmax.
+ * variant: 0 = 64-row kv tiles / 3 CTAs per SM, 1 = 128-row kv tiles / 2 CTAs per SM. */
+OSD_API int osd_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                         int variant, void* stream);
 
 /* Layout changes between the reference's channels-first [B, C, L] fp32 tensors and the internal
  * token-major [B*L, C] operands (bf16 when *_fp32 == 0). */

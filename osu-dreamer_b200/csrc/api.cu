@@ -37,8 +37,9 @@ int osd_rope_table(const float* inv_freq_host, int L, float* rope, void* stream)
   return launch_rope_table(inv_freq_host, L, rope, static_cast<cudaStream_t>(stream));
 }
 
-int osd_attn_fwd(const void* qkv, void* y, float* lse, int B, int L, int H, void* stream) {
-  return launch_attn_fwd(qkv, y, lse, B, L, H, static_cast<cudaStream_t>(stream));
+int osd_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int variant,
+                 void* stream) {
+  return launch_attn_fwd(qkv, y, lse, bound_log2, B, L, H, variant, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -376,13 +376,20 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
         tmem_ld32(tDP + cch * 32, rp);
         tmem_wait_ld();
         float pt[32], ds[32];
+        const float4* l4 = reinterpret_cast<const float4*>(st + cch * 32);       // broadcast LDS.128
+        const float4* d4 = reinterpret_cast<const float4*>(st + 64 + cch * 32);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float l2 = st[cch * 32 + k];
-          const float dd = st[64 + cch * 32 + k];
-          const float pr = ex2f(fmaf(__uint_as_float(rs[k]), c, -l2));
-          pt[k] = pr;
-          ds[k] = pr * (__uint_as_float(rp[k]) - dd) * p.scale;
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 lv = l4[k4], dv = d4[k4];
+          const float l2[4] = {lv.x, lv.y, lv.z, lv.w};
+          const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = k4 * 4 + e;
+            const float pr = ex2f(fmaf(__uint_as_float(rs[k]), c, -l2[e]));
+            pt[k] = pr;
+            ds[k] = pr * (__uint_as_float(rp[k]) - dd[e]) * p.scale;
+          }
         }
         st_row32_sw128(aPT, row, cch * 32, pt);
         st_row32_sw128(aDST, row, cch * 32, ds);

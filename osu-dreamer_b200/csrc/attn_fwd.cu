@@ -16,18 +16,27 @@
 namespace osd {
 
 static constexpr int AT_BQ = 128;
-static constexpr int AT_BKV = 128;
 static constexpr int AT_D = 64;
 static constexpr int AT_THREADS = 192;
 static constexpr int AT_TILE = 128 * 128;  // bytes of a [128 x 64] bf16 tile
-static constexpr int AT_SMEM_TILES = AT_TILE /*Q*/ + 2 * AT_TILE /*K*/ + 2 * AT_TILE /*V*/ + 2 * AT_TILE /*P*/;
-static constexpr int AT_SMEM_BYTES = AT_SMEM_TILES + 256;  // + barriers; base must be 1024-aligned (checked)
-static constexpr uint32_t AT_TMEM_COLS = 256;
-static constexpr uint32_t AT_S_COL = 0;
-static constexpr uint32_t AT_O_COL = 128;
+// BKV = kv rows per tile: 128 -> 2 CTAs/SM (112 KB smem, 256 TMEM columns), 64 -> 3 CTAs/SM (64 KB, 128 columns)
+template <int BKV>
+struct AtCfg {
+  static constexpr int KV_TILE = BKV * 128;               // bytes of a [BKV x 64] bf16 tile
+  static constexpr int P_BYTES = (BKV / 64) * AT_TILE;    // [128 q x BKV] bf16 as 64-column sub-tiles
+  static constexpr int SMEM_TILES = AT_TILE + 4 * KV_TILE + P_BYTES;
+  static constexpr int SMEM_BYTES = SMEM_TILES + 256;     // + barriers; base must be 1024-aligned (checked)
+  static constexpr uint32_t TMEM_COLS = (BKV == 128) ? 256 : 128;
+  static constexpr uint32_t S_COL = 0;
+  static constexpr uint32_t O_COL = BKV;
+  static constexpr int CTAS = (BKV == 128) ? 2 : 3;
+};
 
 struct AttnFwdParams {
-  CUtensorMap tma_qkv;  // dims (3*dh, L, B), box (64, 128, 1), bf16, SW128
+  CUtensorMap tma_qkv;  // dims (3*dh, L, B), box (64, 128, 1), bf16, SW128  (Q tiles)
+  CUtensorMap tma_kv;   // same tensor, box (64, BKV, 1)                       (K / V tiles)
+  const float* bound_log2;  // optional device scalar: upper bound of the scaled scores in log2 units (fixed-max
+                            // softmax, no running max / O rescale); NULL or a non-finite value -> online softmax
   __nv_bfloat16* y;     // [B*L, dh]
   float* lse;           // [B, H, L]
   int B, H, L;
@@ -42,7 +51,9 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+template <int BKV>
+__global__ void __launch_bounds__(AT_THREADS, AtCfg<BKV>::CTAS) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+  using C = AtCfg<BKV>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -50,16 +61,16 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
   {
     uint32_t dyn;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    if (pad + AT_SMEM_TILES + 128 > dyn) {
+    if (pad + C::SMEM_TILES + 128 > dyn) {
       if (threadIdx.x == 0) printf("osd attn_fwd: dynamic smem base misaligned (pad %u)\n", pad);
       __trap();
     }
   }
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AT_TILE;
-  uint8_t* sV = sK + 2 * AT_TILE;
-  uint8_t* sP = sV + 2 * AT_TILE;  // [2 sub-tiles of 128 rows x 64 kv] bf16, K-major SW128
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_TILE);
+  uint8_t* sV = sK + 2 * C::KV_TILE;
+  uint8_t* sP = sV + 2 * C::KV_TILE;  // [BKV/64 sub-tiles of 128 rows x 64 kv] bf16, K-major SW128
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + C::P_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;   // [2]
   uint64_t* k_empty = bars + 3;  // [2]
@@ -80,10 +91,11 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
   const int h = bh % p.H;
   const int b = bh / p.H;
   const int q0 = qt * AT_BQ;
-  const int n_kv = (p.L + AT_BKV - 1) / AT_BKV;
+  const int n_kv = (p.L + BKV - 1) / BKV;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tma_qkv);
+    tma_prefetch_desc(&p.tma_kv);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
@@ -98,7 +110,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, AT_TMEM_COLS);
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -115,27 +127,27 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], AT_TILE);
-        tma_load_3d(sK + st * AT_TILE, &p.tma_qkv, &k_full[st], p.dh + h * AT_D, j * AT_BKV, b);
+        mbar_expect_tx(&k_full[st], C::KV_TILE);
+        tma_load_3d(sK + st * C::KV_TILE, &p.tma_kv, &k_full[st], p.dh + h * AT_D, j * BKV, b);
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], AT_TILE);
-        tma_load_3d(sV + st * AT_TILE, &p.tma_qkv, &v_full[st], 2 * p.dh + h * AT_D, j * AT_BKV, b);
+        mbar_expect_tx(&v_full[st], C::KV_TILE);
+        tma_load_3d(sV + st * C::KV_TILE, &p.tma_kv, &v_full[st], 2 * p.dh + h * AT_D, j * BKV, b);
       }
     }
   } else if (warp == 1) {
     // ============================================================ UMMA issuer
     if (elect_one()) {
-      const uint32_t idesc_s = make_idesc(FMT_BF16, 0, 0, 128, 128);
+      const uint32_t idesc_s = make_idesc(FMT_BF16, 0, 0, 128, BKV);
       const uint32_t idesc_o = make_idesc(FMT_BF16, 0, 1, 128, 64);
       const uint32_t aQ = smem_u32(sQ);
       const uint32_t aP = smem_u32(sP);
-      const uint32_t tS = tmem_base + AT_S_COL;
-      const uint32_t tO = tmem_base + AT_O_COL;
+      const uint32_t tS = tmem_base + C::S_COL;
+      const uint32_t tO = tmem_base + C::O_COL;
       auto issue_s = [&](int j) {
         const int st = j & 1;
         mbar_wait(&k_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t aK = smem_u32(sK + st * AT_TILE);
+        const uint32_t aK = smem_u32(sK + st * C::KV_TILE);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ss(tS, make_smem_desc(aQ + k * 32, 0, 1024), make_smem_desc(aK + k * 32, 0, 1024), idesc_s,
@@ -155,9 +167,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
         mbar_wait(p_full, j & 1);
         mbar_wait(&v_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t aV = smem_u32(sV + st * AT_TILE);
+        const uint32_t aV = smem_u32(sV + st * C::KV_TILE);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < BKV / 16; ++k) {
           // P: K-major, two 64-column sub-tiles of 16 KB; V: MN-major, 16 kv rows (2 KB) per step
           const uint64_t pd = make_smem_desc(aP + (k >> 2) * AT_TILE + (k & 3) * 32, 0, 1024);
           const uint64_t vd = make_smem_desc(aV + k * 16 * 128, 0, 1024);
@@ -172,42 +184,51 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tS = tmem_base + AT_S_COL + lane_off;
-    const uint32_t tO = tmem_base + AT_O_COL + lane_off;
+    const uint32_t tS = tmem_base + C::S_COL + lane_off;
+    const uint32_t tO = tmem_base + C::O_COL + lane_off;
     const float c = p.scale_log2;
-    float m = -INFINITY, l = 0.f;
+    // fixed-max mode: q and k are RMS-normalised (attn.py:77-78), so the scaled scores are bounded by a
+    // per-layer constant; softmax is shift-invariant, so exp2(s*c - bound) needs no running max and O is
+    // never rescaled.  Falls back to the online softmax when no finite bound is supplied.
+    float bound = INFINITY;
+    if (p.bound_log2 != nullptr) bound = __ldg(p.bound_log2);
+    const bool fixed = bound < 3.0e38f;
+    float m = fixed ? bound / c : -INFINITY, l = 0.f;
     const uint32_t sP_row = smem_u32(sP) + row * 128;
     const int sw = row & 7;
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int valid = p.L - j * AT_BKV;  // kv columns >= valid are padding (only the last tile)
-      // ---- pass 1: row max
-      float mx = -INFINITY;
+      const int valid = p.L - j * BKV;  // kv columns >= valid are padding (only the last tile)
+      float m_new = m, alpha = 1.0f;
+      if (!fixed) {
+        // ---- pass 1: row max
+        float mx = -INFINITY;
 #pragma unroll 1
-      for (int cch = 0; cch < 4; ++cch) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld32(tS + cch * 32, r);
-        tmem_wait_ld();
-        if (valid >= AT_BKV) {
+        for (int cch = 0; cch < BKV / 32; ++cch) {
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld32(tS + cch * 32, r);
+          tmem_wait_ld();
+          if (valid >= BKV) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (cch * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+            for (int i = 0; i < 32; ++i)
+              if (cch * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          }
         }
+        m_new = fmaxf(m, mx);
+        alpha = ex2((m - m_new) * c);
       }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = ex2((m - m_new) * c);
       const float neg_mc = -m_new * c;
       // ---- O correction (needs P V_{j-1} complete; also guarantees the P buffer is free)
       if (j > 0) {
         mbar_wait(o_ready, (j - 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+        if (!fixed && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
           for (int cch = 0; cch < 2; ++cch) {
             uint32_t r[32];
@@ -224,13 +245,13 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
       // ---- pass 2: P = exp2(S*c - m*c) -> bf16 smem (SW128 K-major), row sum
       float sum = 0.f;
 #pragma unroll 1
-      for (int cch = 0; cch < 4; ++cch) {
+      for (int cch = 0; cch < BKV / 32; ++cch) {
         uint32_t r[32];
         __syncwarp();
         tmem_ld32(tS + cch * 32, r);
         tmem_wait_ld();
         float pv[32];
-        if (valid >= AT_BKV) {
+        if (valid >= BKV) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) pv[i] = ex2(fmaf(__uint_as_float(r[i]), c, neg_mc));
         } else {
@@ -238,8 +259,12 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
           for (int i = 0; i < 32; ++i)
             pv[i] = (cch * 32 + i < valid) ? ex2(fmaf(__uint_as_float(r[i]), c, neg_mc)) : 0.f;
         }
+        {  // four independent partial sums: the serial FADD chain was a visible stall
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sum += pv[i];
+          for (int i = 0; i < 32; i += 4) s0 += pv[i], s1 += pv[i + 1], s2 += pv[i + 2], s3 += pv[i + 3];
+          sum += (s0 + s1) + (s2 + s3);
+        }
         const uint32_t sub = sP_row + (cch >> 1) * AT_TILE;
 #pragma unroll
         for (int u4 = 0; u4 < 4; ++u4) {
@@ -291,18 +316,23 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
   tc_fence_after();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, AT_TMEM_COLS);
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
-int launch_attn_fwd(const void* qkv, void* y, float* lse, int B, int L, int H, cudaStream_t stream) {
-  OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd: bad arguments");
+template <int BKV>
+static int launch_attn_fwd_t(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                             cudaStream_t stream) {
+  using C = AtCfg<BKV>;
   AttnFwdParams p;
   const int dh = H * AT_D;
   uint64_t dims[3] = {(uint64_t)3 * dh, (uint64_t)L, (uint64_t)B};
   uint64_t strides[2] = {(uint64_t)3 * dh * 2, (uint64_t)L * 3 * dh * 2};
   uint32_t box[3] = {64, 128, 1};
+  uint32_t box_kv[3] = {64, (uint32_t)BKV, 1};
   OSD_TRY(make_tmap(&p.tma_qkv, qkv, 2, 3, dims, strides, box));
+  OSD_TRY(make_tmap(&p.tma_kv, qkv, 2, 3, dims, strides, box_kv));
+  p.bound_log2 = bound_log2;
   p.y = static_cast<__nv_bfloat16*>(y);
   p.lse = lse;
   p.B = B;
@@ -313,15 +343,23 @@ int launch_attn_fwd(const void* qkv, void* y, float* lse, int B, int L, int H, c
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int n_qt = ceil_div(L, AT_BQ);
   const long long grid = (long long)n_qt * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_fwd: grid too large");
-  attn_fwd_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(p);
+  attn_fwd_kernel<BKV><<<(unsigned)grid, AT_THREADS, C::SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
   return 0;
+}
+
+// variant: 0 = default (BKV 64, 3 CTAs/SM), 1 = BKV 128 (2 CTAs/SM)
+int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int variant,
+                    cudaStream_t stream) {
+  OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd: bad arguments");
+  if (variant == 1) return launch_attn_fwd_t<128>(qkv, y, lse, bound_log2, B, L, H, stream);
+  return launch_attn_fwd_t<64>(qkv, y, lse, bound_log2, B, L, H, stream);
 }
 
 }  // namespace osd

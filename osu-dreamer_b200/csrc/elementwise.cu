@@ -579,6 +579,26 @@ int launch_sample_eta(const float* u, int B, float sqrt_c0, int num_steps, float
 }
 
 // ------------------------------------------------------------------------------------------------
+// Upper bound of the scaled attention scores in log2 units for one layer: q and k leave nn.RMSNorm(64) with
+// ||.||_2 <= 8 before the elementwise gain (attn.py:71-72,77-78) and RoPE is a rotation, so
+// |q.k| / sqrt(64) <= 8 max|w_q| max|w_k|.  Written as +inf when too large for a fixed-max softmax.
+__global__ void qk_bound_kernel(const float* __restrict__ qw, const float* __restrict__ kw, float* __restrict__ out) {
+  float a = fmaxf(fabsf(qw[threadIdx.x]), fabsf(qw[threadIdx.x + 32]));
+  float b = fmaxf(fabsf(kw[threadIdx.x]), fabsf(kw[threadIdx.x + 32]));
+  a = warp_max(a);
+  b = warp_max(b);
+  if (threadIdx.x == 0) {
+    const float bound = 8.0f * a * b * 1.4426950408889634f;
+    out[0] = (bound < 48.0f) ? bound : INFINITY;
+  }
+}
+int launch_qk_bound(const float* qw, const float* kw, float* out, cudaStream_t stream) {
+  qk_bound_kernel<<<1, 32, 0, stream>>>(qw, kw, out);
+  OSD_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight packing: fp32 parameter [rows_src, cols_src] -> operand dtype [rows_dst, cols_dst] with a row
 // map (dst row r takes src row r - row_shift when inside [row_lo, row_hi)) and zero padding elsewhere.
 template <typename TOut>

@@ -64,6 +64,8 @@ int launch_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, s
 // attention (attn_fwd.cu, attn_bwd.cu)
 int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, void* dqkv, int B,
                     int L, int H, cudaStream_t stream);
-int launch_attn_fwd(const void* qkv, void* y, float* lse, int B, int L, int H, cudaStream_t stream);
+int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int variant,
+                    cudaStream_t stream);
+int launch_qk_bound(const float* qw, const float* kw, float* out, cudaStream_t stream);
 
 }  // namespace osd

@@ -34,6 +34,8 @@ PackedLayout packed_layout(int mode) {
   off += 8 * lo;
   p.bvg = off;
   off += al((size_t)8 * 2 * OSD_HIDP * 4);
+  p.bounds = off;
+  off += al(8 * 4);
   p.total = off;
   return p;
 }
@@ -94,6 +96,7 @@ static int pack_weights(const float* const* P, uint8_t* packed, int mode, cudaSt
     OSD_TRY(launch_pack_weight(P[lp(l, L_PO_W)], lb + lay.l_po, f32, 512, OSD_HID, 512, OSD_HIDP, 0, 0, s));
     OSD_TRY(launch_pack_weight(P[lp(l, L_VG_B)], packed + lay.bvg + (size_t)l * 2 * OSD_HIDP * 4, 1, 2 * OSD_HID, 1,
                                2 * OSD_HIDP, 1, OSD_HID, OSD_HIDP, s));
+    OSD_TRY(launch_qk_bound(P[lp(l, L_QN_W)], P[lp(l, L_KN_W)], reinterpret_cast<float*>(packed + lay.bounds) + l, s));
   }
   return 0;
 }
@@ -179,7 +182,7 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
     q.qnorm_w = c.P[lp(l, L_QN_W)]; q.knorm_w = c.P[lp(l, L_KN_W)]; q.rope = c.rope; q.L = L; q.dh = 1024;
     q.raw_out = c.save ? lb + pl.qkv_raw : nullptr;
     OSD_TRY(launch_gemm(q, s));
-    OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), B, L, 16, s));
+    OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), c.W.bound(l), B, L, 16, 0, s));
     GemmArgs o;
     o.A = lb + pl.y; o.B = c.W.out(l); o.lda = 1024; o.ldb = 1024; o.M = T; o.N = 512; o.K = 1024; o.elem = elem;
     o.epi = EPI_STORE; o.C = lb + pl.o; o.ldc = 512; o.c_fp32 = 1; o.bias = c.P[lp(l, L_OUT_B)];

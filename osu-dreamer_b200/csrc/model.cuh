@@ -24,6 +24,7 @@ struct PackedLayout {
   size_t layer0, layer_stride;
   size_t l_cl, l_qkv, l_out, l_vg, l_po;  // offsets inside a layer block (bytes)
   size_t bvg;                             // fp32 [8][2816]
+  size_t bounds;                          // fp32 [8] attention score bounds (log2 units) per layer
   size_t total;
 };
 PackedLayout packed_layout(int mode);
@@ -37,6 +38,7 @@ struct PackedW {
   const void* out(int l) const { return base + lay.layer0 + l * lay.layer_stride + lay.l_out; }
   const void* vg(int l) const { return base + lay.layer0 + l * lay.layer_stride + lay.l_vg; }
   const void* po(int l) const { return base + lay.layer0 + l * lay.layer_stride + lay.l_po; }
+  const float* bound(int l) const { return reinterpret_cast<const float*>(base + lay.bounds) + l; }
   const float* bvg(int l) const { return reinterpret_cast<const float*>(base + lay.bvg) + (size_t)l * 2 * OSD_HIDP; }
 };
 

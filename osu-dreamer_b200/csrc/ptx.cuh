@@ -59,10 +59,23 @@ static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity)
          (int)threadIdx.x, smem_u32(bar), parity);
   __trap();
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint
+// elapses) instead of burning issue slots that the softmax / epilogue warps of the same SM sub-partition need.
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_suspend(bar, parity, 1000000u)) {
     if (clock64() - t0 > OSD_WATCHDOG_CYCLES) mbar_timeout(bar, parity);
   }
 }

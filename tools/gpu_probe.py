@@ -106,22 +106,69 @@ def cases():
     cs.append(('attn_B1_L200', attn_case(1, 200)))
     cs.append(('attn_B1_L4096', attn_case(1, 4096)))
 
-    def attn_speed():
+    def attn_bound_case(B, L, variant):
+        def f():
+            qkv = rnd(B * L, 3072)
+            bound = torch.tensor([14.0], device=dev)
+            y, lse = lib.attn_fwd(qkv, B, L, bound_log2=bound, variant=variant)
+            torch.cuda.synchronize()
+            q, k, v = qkv.float().view(B, L, 3, 16, 64).permute(2, 0, 3, 1, 4)
+            sc = (q @ k.transpose(-1, -2)) / 8
+            ref = (torch.softmax(sc, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, 1024)
+            e2 = float((lse - torch.logsumexp(sc, -1)).abs().max())
+            return max(rel(y, ref), e2)
+        return f
+    for v in (0, 1):
+        cs.append((f'attn_fixed_v{v}_L200', attn_bound_case(1, 200, v)))
+        cs.append((f'attn_fixed_v{v}_L1024', attn_bound_case(2, 1024, v)))
+        cs.append((f'attn_online_v{v}_L1000', (lambda vv: (lambda: attn_case_v(1, 1000, vv)))(v)))
+
+    def attn_case_v(B, L, variant):
+        qkv = rnd(B * L, 3072)
+        y, lse = lib.attn_fwd(qkv, B, L, variant=variant)
+        torch.cuda.synchronize()
+        q, k, v = qkv.float().view(B, L, 3, 16, 64).permute(2, 0, 3, 1, 4)
+        sc = (q @ k.transpose(-1, -2)) / 8
+        ref = (torch.softmax(sc, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, 1024)
+        return max(rel(y, ref), float((lse - torch.logsumexp(sc, -1)).abs().max()))
+
+    def attn_speed(variant, fixed):
+        def f():
+            B, L = 8, 8192
+            qkv = rnd(B * L, 3072)
+            bound = torch.tensor([14.0], device=dev) if fixed else None
+            for _ in range(2):
+                lib.attn_fwd(qkv, B, L, bound_log2=bound, variant=variant)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                lib.attn_fwd(qkv, B, L, bound_log2=bound, variant=variant)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            return {'ms': ms, 'tflops': 4 * B * 16 * L * L * 64 / ms / 1e9}
+        return f
+    for v in (0, 1):
+        for fx in (0, 1):
+            cs.append((f'attn_speed_B8_L8192_v{v}_fixed{fx}', attn_speed(v, fx)))
+
+    def attn_bwd_speed():
         B, L = 8, 8192
         qkv = rnd(B * L, 3072)
-        for _ in range(2):
-            lib.attn_fwd(qkv, B, L)
+        dy = rnd(B * L, 1024)
+        y, lse = lib.attn_fwd(qkv, B, L)
+        lib.attn_bwd(qkv, y, dy, lse, B, L)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(5):
-            lib.attn_fwd(qkv, B, L)
+        for _ in range(3):
+            lib.attn_bwd(qkv, y, dy, lse, B, L)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
-        tf = 4 * B * 16 * L * L * 64 / ms / 1e9
-        return {'ms': ms, 'tflops': tf}
-    cs.append(('attn_speed_B8_L8192', attn_speed))
+        ms = e0.elapsed_time(e1) / 3
+        return {'ms': ms, 'tflops_algorithmic': 8 * B * 16 * L * L * 64 / ms / 1e9}
+    cs.append(('attn_bwd_speed_B8_L8192', attn_bwd_speed))
 
     def gemm_speed():
         M, N, K = 131072, 3072, 512
