@@ -53,9 +53,9 @@ struct AttnBwdParams {
 };
 
 // ================================================================================================= dQ
-//   smem : Q [128x64] | dO [128x64] | K_j x2 [64x64] | V_j x2 [64x64] | dS [128x64] | barriers
-//   TMEM : S cols [0,64) | dP [64,128) | dQ [128,192)
-static constexpr int DQ_SMEM_TILES = 2 * T128 + 4 * T64 + T128;
+//   smem : Q [128x64] | dO [128x64] | K_j x2 [64x64] | V_j x2 [64x64] | barriers
+//   TMEM : S cols [0,64) | dP [64,128) | dQ [128,192) | dS bf16 [192,224) (A operand of dQ += dS K_j, never in smem)
+static constexpr int DQ_SMEM_TILES = 2 * T128 + 4 * T64;
 static constexpr int DQ_SMEM_BYTES = DQ_SMEM_TILES + 256;
 
 __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid_constant__ AttnBwdParams p) {
@@ -72,8 +72,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
   uint8_t* sDO = sQ + T128;
   uint8_t* sK = sDO + T128;     // 2 stages
   uint8_t* sV = sK + 2 * T64;   // 2 stages
-  uint8_t* sDS = sV + 2 * T64;  // [128 q x 64 kv] K-major
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + T128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * T64);
   uint64_t* qdo_full = bars + 0;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
@@ -127,8 +126,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
     if (elect_one()) {
       const uint32_t id_s = make_idesc(FMT_BF16, 0, 0, 128, 64);   // S, dP : K-major x K-major
       const uint32_t id_o = make_idesc(FMT_BF16, 0, 1, 128, 64);   // dQ    : dS K-major x K_j MN-major
-      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aDS = smem_u32(sDS);
-      const uint32_t tS = tmem_base, tDP = tmem_base + 64, tDQ = tmem_base + 128;
+      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO);
+      const uint32_t tS = tmem_base, tDP = tmem_base + 64, tDQ = tmem_base + 128, tDS = tmem_base + 192;
       auto issue_s = [&](int j) {
         const int st = j & 1;
         mbar_wait(&kv_full[st], (j >> 1) & 1);
@@ -152,8 +151,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
         const uint32_t aK = smem_u32(sK + st * T64);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tDQ, make_smem_desc(aDS + k * 32, 0, 1024), make_smem_desc(aK + k * 16 * 128, 0, 1024), id_o,
-                      (j > 0 || k > 0) ? 1u : 0u);
+          umma_f16_ts(tDQ, tDS + k * 8, make_smem_desc(aK + k * 16 * 128, 0, 1024), id_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
         umma_commit(dq_done);
       }
@@ -163,13 +161,13 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS = tmem_base + lane_off, tDP = tmem_base + 64 + lane_off, tDQ = tmem_base + 128 + lane_off;
+    const uint32_t tDS = tmem_base + 192 + lane_off;
     const int q = q0 + row;
     const bool ok = q < p.L;
     const size_t sidx = ((size_t)b * p.H + h) * p.L + (ok ? q : 0);
     const float lse2 = ok ? p.lse[sidx] * 1.4426950408889634f : INFINITY;
     const float dsum = ok ? p.dsum[sidx] : 0.f;
     const float c = p.scale_log2;
-    const uint32_t aDS = smem_u32(sDS);
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
@@ -192,10 +190,13 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
           const float d = pr * (__uint_as_float(rp[i]) - dsum) * p.scale;
           ds[i] = (cch * 32 + i < valid) ? d : 0.f;
         }
-        st_row32_sw128(aDS, row, cch * 32, ds);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(ds[2 * i], ds[2 * i + 1]);
+        tmem_st16(tDS + cch * 16, pk);
       }
+      tmem_wait_st();
       tc_fence_before();
-      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
     }
@@ -228,10 +229,12 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
 }
 
 // ================================================================================================= dK, dV
-//   smem : K [128x64] | V [128x64] | Q_i x2 [64x64] | dO_i x2 [64x64] | P^T [128x64] | dS^T [128x64] |
-//          lse2/D staging [2][2][64] f32 | barriers
-//   TMEM : S^T cols [0,64) | dP^T [64,128) | dV [128,192) | dK [192,256)
-static constexpr int DKV_SMEM_TILES = 2 * T128 + 4 * T64 + 2 * T128;
+//   smem : K [128x64] | V [128x64] | Q_i x2 [64x64] | dO_i x2 [64x64] | lse2/D staging [2][2][64] f32 | barriers
+//   TMEM : S^T cols [0,64) | dP^T [64,128) | dV [128,192) | dK [192,256); the bf16 P^T / dS^T tiles are written
+//          back over the first 32 columns of S^T / dP^T and consumed from there as the A operands of
+//          dV += P^T dO_i and dK += dS^T Q_i (no shared-memory staging; the tensor pipe is in order, so the next
+//          S^T / dP^T MMAs are simply issued after them).
+static constexpr int DKV_SMEM_TILES = 2 * T128 + 4 * T64;
 static constexpr int DKV_SMEM_BYTES = DKV_SMEM_TILES + 1024 + 256;
 
 __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdParams p) {
@@ -248,10 +251,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
   uint8_t* sV = sK + T128;
   uint8_t* sQ = sV + T128;       // 2 stages [64 x 64]
   uint8_t* sDO = sQ + 2 * T64;   // 2 stages
-  uint8_t* sPT = sDO + 2 * T64;  // [128 kv x 64 q] K-major
-  uint8_t* sDST = sPT + T128;
-  float* sStat = reinterpret_cast<float*>(sDST + T128);  // [2 buf][lse2 64 | D 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDST + T128 + 1024);
+  float* sStat = reinterpret_cast<float*>(sDO + 2 * T64);  // [2 buf][lse2 64 | D 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDO + 2 * T64 + 1024);
   uint64_t* kv_full = bars + 0;
   uint64_t* q_full = bars + 1;   // [2]
   uint64_t* q_empty = bars + 3;  // [2]
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
     if (elect_one()) {
       const uint32_t id_s = make_idesc(FMT_BF16, 0, 0, 128, 64);  // S^T = K Q_i^T, dP^T = V dO_i^T
       const uint32_t id_o = make_idesc(FMT_BF16, 0, 1, 128, 64);  // dV = P^T dO_i, dK = dS^T Q_i (B MN-major)
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aPT = smem_u32(sPT), aDST = smem_u32(sDST);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
       const uint32_t tS = tmem_base, tDP = tmem_base + 64, tDV = tmem_base + 128, tDK = tmem_base + 192;
       auto issue_s = [&](int i) {
         const int st = i & 1;
@@ -326,18 +327,16 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
         const int st = i & 1;
         mbar_wait(ds_full, i & 1);
         tc_fence_after();
-        if (i + 1 < n_q) issue_s(i + 1);
         const uint32_t aQ = smem_u32(sQ + st * T64), aDO = smem_u32(sDO + st * T64);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tDV, make_smem_desc(aPT + k * 32, 0, 1024), make_smem_desc(aDO + k * 16 * 128, 0, 1024), id_o,
-                      (i > 0 || k > 0) ? 1u : 0u);
+          umma_f16_ts(tDV, tS + k * 8, make_smem_desc(aDO + k * 16 * 128, 0, 1024), id_o, (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tDK, make_smem_desc(aDST + k * 32, 0, 1024), make_smem_desc(aQ + k * 16 * 128, 0, 1024), id_o,
-                      (i > 0 || k > 0) ? 1u : 0u);
+          umma_f16_ts(tDK, tDP + k * 8, make_smem_desc(aQ + k * 16 * 128, 0, 1024), id_o, (i > 0 || k > 0) ? 1u : 0u);
         umma_commit(&q_empty[st]);
         umma_commit(acc_done);
+        if (i + 1 < n_q) issue_s(i + 1);  // overwrites P^T / dS^T only after the two MMAs above have read them
       }
     }
   } else {
@@ -348,7 +347,6 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
     const uint32_t tS = tmem_base + lane_off, tDP = tmem_base + 64 + lane_off;
     const uint32_t tDV = tmem_base + 128 + lane_off, tDK = tmem_base + 192 + lane_off;
     const float c = p.scale_log2;
-    const uint32_t aPT = smem_u32(sPT), aDST = smem_u32(sDST);
     const size_t sbase = ((size_t)b * p.H + h) * p.L;
     for (int i = 0; i < n_q; ++i) {
       // stage lse2 / D of this q tile (double-buffered); q rows past L get lse2 = +inf -> P = 0
@@ -362,12 +360,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
           st[tid] = okq ? p.dsum[sbase + qi] : 0.f;
       }
       named_bar_sync(1, 128);
-      mbar_wait(s_full, i & 1);
+      mbar_wait(s_full, i & 1);  // also implies dV_{i-1} / dK_{i-1} have consumed the previous P^T / dS^T
       tc_fence_after();
-      if (i > 0) {
-        mbar_wait(acc_done, (i - 1) & 1);  // P^T / dS^T buffers free
-        tc_fence_after();
-      }
 #pragma unroll 1
       for (int cch = 0; cch < 2; ++cch) {
         uint32_t rs[32], rp[32];
@@ -391,11 +385,16 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
             ds[k] = pr * (__uint_as_float(rp[k]) - dd[e]) * p.scale;
           }
         }
-        st_row32_sw128(aPT, row, cch * 32, pt);
-        st_row32_sw128(aDST, row, cch * 32, ds);
+        uint32_t pk[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(pt[2 * k], pt[2 * k + 1]);
+        tmem_st16(tS + cch * 16, pk);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(ds[2 * k], ds[2 * k + 1]);
+        tmem_st16(tDP + cch * 16, pk);
       }
+      tmem_wait_st();
       tc_fence_before();
-      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
     }

@@ -20,16 +20,23 @@ static constexpr int AT_D = 64;
 static constexpr int AT_THREADS = 192;
 static constexpr int AT_TILE = 128 * 128;  // bytes of a [128 x 64] bf16 tile
 // BKV = kv rows per tile: 128 -> 2 CTAs/SM (112 KB smem, 256 TMEM columns), 64 -> 3 CTAs/SM (64 KB, 128 columns)
-template <int BKV>
+// PT = keep P in tensor memory (bf16, two per 32-bit column, row = lane) and feed it to the P*V MMA as the
+// A operand straight from TMEM: no P staging in shared memory (which otherwise costs a 32 KB store + 32 KB
+// operand read per 128x128 tile against a 128 B/clk shared-memory port).
+//   BKV=128, PT: S cols [0,128) | P [128,192) | O [192,256)      (S_{j+1} may be issued before P_j V_j)
+//   BKV=64,  PT: S cols [0,64), P aliases S cols [0,32) | O [64,128)   (P_j V_j is issued before S_{j+1})
+template <int BKV, bool PT>
 struct AtCfg {
   static constexpr int KV_TILE = BKV * 128;               // bytes of a [BKV x 64] bf16 tile
-  static constexpr int P_BYTES = (BKV / 64) * AT_TILE;    // [128 q x BKV] bf16 as 64-column sub-tiles
+  static constexpr int P_BYTES = PT ? 0 : (BKV / 64) * AT_TILE;  // [128 q x BKV] bf16 as 64-column sub-tiles
   static constexpr int SMEM_TILES = AT_TILE + 4 * KV_TILE + P_BYTES;
   static constexpr int SMEM_BYTES = SMEM_TILES + 256;     // + barriers; base must be 1024-aligned (checked)
   static constexpr uint32_t TMEM_COLS = (BKV == 128) ? 256 : 128;
   static constexpr uint32_t S_COL = 0;
-  static constexpr uint32_t O_COL = BKV;
-  static constexpr int CTAS = (BKV == 128) ? 2 : 3;
+  static constexpr uint32_t P_COL = (BKV == 128) ? 128 : 0;
+  static constexpr uint32_t O_COL = (BKV == 128 && PT) ? 192 : BKV;
+  static constexpr bool P_ALIASES_S = PT && BKV == 64;
+  static constexpr int CTAS = (BKV == 128) ? 2 : (PT ? 4 : 3);
 };
 
 struct AttnFwdParams {
@@ -51,9 +58,9 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int BKV>
-__global__ void __launch_bounds__(AT_THREADS, AtCfg<BKV>::CTAS) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
-  using C = AtCfg<BKV>;
+template <int BKV, bool PT>
+__global__ void __launch_bounds__(AT_THREADS, AtCfg<BKV, PT>::CTAS) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+  using C = AtCfg<BKV, PT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -157,8 +164,9 @@ __global__ void __launch_bounds__(AT_THREADS, AtCfg<BKV>::CTAS) attn_fwd_kernel(
       };
       mbar_wait(q_full, 0);
       issue_s(0);
+      const uint32_t tP = tmem_base + C::P_COL;
       for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) {
+        if (!C::P_ALIASES_S && j + 1 < n_kv) {
           mbar_wait(s_empty, j & 1);  // softmax has consumed S_j
           tc_fence_after();
           issue_s(j + 1);
@@ -170,13 +178,19 @@ __global__ void __launch_bounds__(AT_THREADS, AtCfg<BKV>::CTAS) attn_fwd_kernel(
         const uint32_t aV = smem_u32(sV + st * C::KV_TILE);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
-          // P: K-major, two 64-column sub-tiles of 16 KB; V: MN-major, 16 kv rows (2 KB) per step
-          const uint64_t pd = make_smem_desc(aP + (k >> 2) * AT_TILE + (k & 3) * 32, 0, 1024);
+          // V: MN-major B operand, 16 kv rows (2 KB) per K step
           const uint64_t vd = make_smem_desc(aV + k * 16 * 128, 0, 1024);
-          umma_f16_ss(tO, pd, vd, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          if (PT) {
+            umma_f16_ts(tO, tP + k * 8, vd, idesc_o, (j > 0 || k > 0) ? 1u : 0u);  // 16 bf16 = 8 columns per step
+          } else {
+            // P: K-major smem, 64-column sub-tiles of 16 KB
+            const uint64_t pd = make_smem_desc(aP + (k >> 2) * AT_TILE + (k & 3) * 32, 0, 1024);
+            umma_f16_ss(tO, pd, vd, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&v_empty[st]);
         umma_commit(o_ready);
+        if (C::P_ALIASES_S && j + 1 < n_kv) issue_s(j + 1);  // tensor pipe is in order: S_{j+1} overwrites P_j after use
       }
     }
   } else {
@@ -186,6 +200,7 @@ __global__ void __launch_bounds__(AT_THREADS, AtCfg<BKV>::CTAS) attn_fwd_kernel(
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS = tmem_base + C::S_COL + lane_off;
     const uint32_t tO = tmem_base + C::O_COL + lane_off;
+    const uint32_t tP = tmem_base + C::P_COL + lane_off;
     const float c = p.scale_log2;
     // fixed-max mode: q and k are RMS-normalised (attn.py:77-78), so the scaled scores are bounded by a
     // per-layer constant; softmax is shift-invariant, so exp2(s*c - bound) needs no running max and O is
@@ -265,24 +280,32 @@ __global__ void __launch_bounds__(AT_THREADS, AtCfg<BKV>::CTAS) attn_fwd_kernel(
           for (int i = 0; i < 32; i += 4) s0 += pv[i], s1 += pv[i + 1], s2 += pv[i + 2], s3 += pv[i + 3];
           sum += (s0 + s1) + (s2 + s3);
         }
-        const uint32_t sub = sP_row + (cch >> 1) * AT_TILE;
+        if (PT) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) {
-          const int u = (cch & 1) * 4 + u4;  // 16-byte unit inside the 128-byte row
-          const uint32_t addr = sub + ((u ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                       "r"(pack_bf16(pv[u4 * 8 + 0], pv[u4 * 8 + 1])), "r"(pack_bf16(pv[u4 * 8 + 2], pv[u4 * 8 + 3])),
-                       "r"(pack_bf16(pv[u4 * 8 + 4], pv[u4 * 8 + 5])), "r"(pack_bf16(pv[u4 * 8 + 6], pv[u4 * 8 + 7]))
-                       : "memory");
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+          tmem_st16(tP + cch * 16, pk);
+        } else {
+          const uint32_t sub = sP_row + (cch >> 1) * AT_TILE;
+#pragma unroll
+          for (int u4 = 0; u4 < 4; ++u4) {
+            const int u = (cch & 1) * 4 + u4;  // 16-byte unit inside the 128-byte row
+            const uint32_t addr = sub + ((u ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                         "r"(pack_bf16(pv[u4 * 8 + 0], pv[u4 * 8 + 1])), "r"(pack_bf16(pv[u4 * 8 + 2], pv[u4 * 8 + 3])),
+                         "r"(pack_bf16(pv[u4 * 8 + 4], pv[u4 * 8 + 5])), "r"(pack_bf16(pv[u4 * 8 + 6], pv[u4 * 8 + 7]))
+                         : "memory");
+          }
         }
       }
+      if (PT) tmem_wait_st();
       l = l * alpha + sum;
       m = m_new;
       tc_fence_before();
-      fence_proxy_async_smem();
+      if (!PT) fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(s_empty);
+        if (!C::P_ALIASES_S) mbar_arrive(s_empty);
         mbar_arrive(p_full);
       }
     }
@@ -320,10 +343,10 @@ __global__ void __launch_bounds__(AT_THREADS, AtCfg<BKV>::CTAS) attn_fwd_kernel(
   }
 }
 
-template <int BKV>
+template <int BKV, bool PT>
 static int launch_attn_fwd_t(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                              cudaStream_t stream) {
-  using C = AtCfg<BKV>;
+  using C = AtCfg<BKV, PT>;
   AttnFwdParams p;
   const int dh = H * AT_D;
   uint64_t dims[3] = {(uint64_t)3 * dh, (uint64_t)L, (uint64_t)B};
@@ -343,23 +366,26 @@ static int launch_attn_fwd_t(const void* qkv, void* y, float* lse, const float* 
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<BKV, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int n_qt = ceil_div(L, AT_BQ);
   const long long grid = (long long)n_qt * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_fwd: grid too large");
-  attn_fwd_kernel<BKV><<<(unsigned)grid, AT_THREADS, C::SMEM_BYTES, stream>>>(p);
+  attn_fwd_kernel<BKV, PT><<<(unsigned)grid, AT_THREADS, C::SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
   return 0;
 }
 
-// variant: 0 = default (BKV 64, 3 CTAs/SM), 1 = BKV 128 (2 CTAs/SM)
+// variant: 0 = BKV 64 / P in smem (3 CTAs/SM), 1 = BKV 128 / P in smem (2 CTAs/SM),
+//          2 = BKV 64 / P in TMEM aliasing S, 3 = BKV 128 / P in TMEM
 int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int variant,
                     cudaStream_t stream) {
   OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd: bad arguments");
-  if (variant == 1) return launch_attn_fwd_t<128>(qkv, y, lse, bound_log2, B, L, H, stream);
-  return launch_attn_fwd_t<64>(qkv, y, lse, bound_log2, B, L, H, stream);
+  if (variant == 1) return launch_attn_fwd_t<128, false>(qkv, y, lse, bound_log2, B, L, H, stream);
+  if (variant == 2) return launch_attn_fwd_t<64, true>(qkv, y, lse, bound_log2, B, L, H, stream);
+  if (variant == 3) return launch_attn_fwd_t<128, true>(qkv, y, lse, bound_log2, B, L, H, stream);
+  return launch_attn_fwd_t<64, false>(qkv, y, lse, bound_log2, B, L, H, stream);
 }
 
 }  // namespace osd

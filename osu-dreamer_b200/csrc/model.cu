@@ -182,7 +182,7 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
     q.qnorm_w = c.P[lp(l, L_QN_W)]; q.knorm_w = c.P[lp(l, L_KN_W)]; q.rope = c.rope; q.L = L; q.dh = 1024;
     q.raw_out = c.save ? lb + pl.qkv_raw : nullptr;
     OSD_TRY(launch_gemm(q, s));
-    OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), c.W.bound(l), B, L, 16, 0, s));
+    OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), c.W.bound(l), B, L, 16, 2, s));
     GemmArgs o;
     o.A = lb + pl.y; o.B = c.W.out(l); o.lda = 1024; o.ldb = 1024; o.M = T; o.N = 512; o.K = 1024; o.elem = elem;
     o.epi = EPI_STORE; o.C = lb + pl.o; o.ldc = 512; o.c_fp32 = 1; o.bias = c.P[lp(l, L_OUT_B)];
