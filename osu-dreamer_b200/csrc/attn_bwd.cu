@@ -53,8 +53,12 @@ struct AttnBwdParams {
 };
 
 // ================================================================================================= dQ
-//   smem : Q [128x64] | dO [128x64] | K_j x2 [64x64] | V_j x2 [64x64] | barriers
-//   TMEM : S cols [0,64) | dP [64,128) | dQ [128,192) | dS bf16 [192,224) (A operand of dQ += dS K_j, never in smem)
+//   smem : Q [128x64] | dO [128x64] (staging only) | K_j x2 [64x64] | V_j x2 [64x64] | barriers
+//   TMEM : S cols [0,64) | dP [64,128) | dQ [128,192) | Q bf16 [192,224) | dO bf16 [224,256)
+//          Q and dO are copied once into TMEM and used from there as the A operands of S = Q K_j^T and
+//          dP = dO V_j^T (a 128x64 smem A tile would otherwise be re-read for every kv tile and make those MMAs
+//          shared-memory-bound); dS (bf16) is written over dP's first 32 columns and consumed from there by
+//          dQ += dS K_j, which is therefore issued before the next S / dP MMAs (in-order tensor pipe).
 static constexpr int DQ_SMEM_TILES = 2 * T128 + 4 * T64;
 static constexpr int DQ_SMEM_BYTES = DQ_SMEM_TILES + 256;
 
@@ -79,7 +83,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
   uint64_t* s_full = bars + 5;
   uint64_t* ds_full = bars + 6;
   uint64_t* dq_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* qt_ready = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = (p.L + 127) / 128;
@@ -98,6 +103,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
     mbar_init(s_full, 1);
     mbar_init(ds_full, 4);
     mbar_init(dq_done, 1);
+    mbar_init(qt_ready, 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -126,34 +132,33 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
     if (elect_one()) {
       const uint32_t id_s = make_idesc(FMT_BF16, 0, 0, 128, 64);   // S, dP : K-major x K-major
       const uint32_t id_o = make_idesc(FMT_BF16, 0, 1, 128, 64);   // dQ    : dS K-major x K_j MN-major
-      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO);
-      const uint32_t tS = tmem_base, tDP = tmem_base + 64, tDQ = tmem_base + 128, tDS = tmem_base + 192;
+      const uint32_t tS = tmem_base, tDP = tmem_base + 64, tDQ = tmem_base + 128;
+      const uint32_t tQ = tmem_base + 192, tDO = tmem_base + 224, tDS = tDP;
       auto issue_s = [&](int j) {
         const int st = j & 1;
         mbar_wait(&kv_full[st], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t aK = smem_u32(sK + st * T64), aV = smem_u32(sV + st * T64);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tS, make_smem_desc(aQ + k * 32, 0, 1024), make_smem_desc(aK + k * 32, 0, 1024), id_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_f16_ts(tS, tQ + k * 8, make_smem_desc(aK + k * 32, 0, 1024), id_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tDP, make_smem_desc(aDO + k * 32, 0, 1024), make_smem_desc(aV + k * 32, 0, 1024), id_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_f16_ts(tDP, tDO + k * 8, make_smem_desc(aV + k * 32, 0, 1024), id_s, k > 0);
         umma_commit(s_full);
       };
-      mbar_wait(qdo_full, 0);
+      mbar_wait(qt_ready, 0);  // Q / dO copied into TMEM by the softmax warps
+      tc_fence_after();
       issue_s(0);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
-        mbar_wait(ds_full, j & 1);  // dS_j written; S_j / dP_j consumed
+        mbar_wait(ds_full, j & 1);  // dS_j written (over dP_j); S_j / dP_j consumed
         tc_fence_after();
-        if (j + 1 < n_kv) issue_s(j + 1);
         const uint32_t aK = smem_u32(sK + st * T64);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ts(tDQ, tDS + k * 8, make_smem_desc(aK + k * 16 * 128, 0, 1024), id_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
         umma_commit(dq_done);
+        if (j + 1 < n_kv) issue_s(j + 1);
       }
     }
   } else {
@@ -161,7 +166,26 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS = tmem_base + lane_off, tDP = tmem_base + 64 + lane_off, tDQ = tmem_base + 128 + lane_off;
-    const uint32_t tDS = tmem_base + 192 + lane_off;
+    const uint32_t tDS = tDP;
+    {  // one-time copy of this thread's Q and dO rows (128 B each, SW128 smem) into TMEM columns [192,256)
+      mbar_wait(qdo_full, 0);
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t base = smem_u32(which == 0 ? sQ : sDO) + row * 128;
+        uint32_t r[32];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(r[4 * u]), "=r"(r[4 * u + 1]), "=r"(r[4 * u + 2]), "=r"(r[4 * u + 3])
+                       : "r"(base + ((u ^ (row & 7)) << 4)));
+        __syncwarp();
+        tmem_st32(tmem_base + 192 + which * 32 + lane_off, r);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qt_ready);
+    }
     const int q = q0 + row;
     const bool ok = q < p.L;
     const size_t sidx = ((size_t)b * p.H + h) * p.L + (ok ? q : 0);
@@ -171,10 +195,6 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      if (j > 0) {
-        mbar_wait(dq_done, (j - 1) & 1);  // dS buffer free (dQ_{j-1} retired)
-        tc_fence_after();
-      }
       const int valid = p.L - j * 64;
 #pragma unroll 1
       for (int cch = 0; cch < 2; ++cch) {
@@ -193,7 +213,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(ds[2 * i], ds[2 * i + 1]);
-        tmem_st16(tDS + cch * 16, pk);
+        __syncwarp();
+        tmem_st16(tDS + cch * 16, pk);  // over dP columns [16*cch, 16*cch+16): already consumed above
       }
       tmem_wait_st();
       tc_fence_before();
@@ -348,18 +369,20 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
     const uint32_t tDV = tmem_base + 128 + lane_off, tDK = tmem_base + 192 + lane_off;
     const float c = p.scale_log2;
     const size_t sbase = ((size_t)b * p.H + h) * p.L;
+    // lse2 / D of a q tile are staged in smem (double-buffered); the global loads for tile i+1 are issued before
+    // tile i is processed so that their latency is off the critical path.  q rows past L: lse2 = +inf -> P = 0
+    auto load_stat = [&](int i) -> float {
+      const int qi = i * 64 + (tid & 63);
+      const bool okq = qi < p.L;
+      if (tid < 64) return okq ? p.lse[sbase + qi] * 1.4426950408889634f : INFINITY;
+      return okq ? p.dsum[sbase + qi] : 0.f;
+    };
+    sStat[tid] = load_stat(0);
+    named_bar_sync(1, 128);
     for (int i = 0; i < n_q; ++i) {
-      // stage lse2 / D of this q tile (double-buffered); q rows past L get lse2 = +inf -> P = 0
       float* st = sStat + (i & 1) * 128;
-      {
-        const int qi = i * 64 + (tid & 63);
-        const bool okq = qi < p.L;
-        if (tid < 64)
-          st[tid] = okq ? p.lse[sbase + qi] * 1.4426950408889634f : INFINITY;
-        else
-          st[tid] = okq ? p.dsum[sbase + qi] : 0.f;
-      }
-      named_bar_sync(1, 128);
+      float next_stat = 0.f;
+      if (i + 1 < n_q) next_stat = load_stat(i + 1);
       mbar_wait(s_full, i & 1);  // also implies dV_{i-1} / dK_{i-1} have consumed the previous P^T / dS^T
       tc_fence_after();
 #pragma unroll 1
@@ -397,6 +420,10 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
+      if (i + 1 < n_q) {
+        sStat[((i + 1) & 1) * 128 + tid] = next_stat;  // buffer (i+1)&1 was last read during tile i-1
+        named_bar_sync(1, 128);
+      }
     }
     mbar_wait(acc_done, (n_q - 1) & 1);
     tc_fence_after();

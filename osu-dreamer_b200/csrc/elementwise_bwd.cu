@@ -392,43 +392,48 @@ __global__ void __launch_bounds__(256) swiglu_norm_bwd_kernel(const __nv_bfloat1
     const __nv_bfloat16* row = vg + (size_t)t * 2 * HIDP;
     const __nv_bfloat16* drow = dhn + (size_t)t * HIDP;
     const float r = rinv[t];
-    float hs[44], dh[44], vv[44], gg[44];
+    // two passes over the row (the second one hits L1/L2): keeps the kernel at ~50 registers so that enough
+    // warps are resident to cover HBM latency
     float dot = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 11; ++i) {
       const int c0 = i * 128 + lane * 4;
-      const uint2 a = *reinterpret_cast<const uint2*>(row + c0);
-      const uint2 bq = *reinterpret_cast<const uint2*>(row + HIDP + c0);
-      const uint2 dq = *reinterpret_cast<const uint2*>(drow + c0);
-      const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&a);
-      const __nv_bfloat162* bp = reinterpret_cast<const __nv_bfloat162*>(&bq);
-      const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&dq);
-      const float v4[4] = {__low2float(ap[0]), __high2float(ap[0]), __low2float(ap[1]), __high2float(ap[1])};
-      const float g4[4] = {__low2float(bp[0]), __high2float(bp[0]), __low2float(bp[1]), __high2float(bp[1])};
-      const float d4[4] = {__low2float(dp[0]), __high2float(dp[0]), __low2float(dp[1]), __high2float(dp[1])};
+      const uint2 va = *reinterpret_cast<const uint2*>(row + c0);
+      const uint2 ga = *reinterpret_cast<const uint2*>(row + HIDP + c0);
+      const uint2 da = *reinterpret_cast<const uint2*>(drow + c0);
+      const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&va);
+      const __nv_bfloat162* bp = reinterpret_cast<const __nv_bfloat162*>(&ga);
+      const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&da);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = 4 * i + e;
-        vv[j] = v4[e];
-        gg[j] = g4[e];
-        hs[j] = v4[e] * silu_f(g4[e]);
-        dh[j] = d4[e];
-        dot = fmaf(d4[e], hs[j] * r, dot);
+      for (int h = 0; h < 2; ++h) {
+        const float2 v2 = __bfloat1622float2(ap[h]), g2 = __bfloat1622float2(bp[h]), d2 = __bfloat1622float2(dp[h]);
+        dot = fmaf(d2.x, v2.x * silu_f(g2.x), dot);
+        dot = fmaf(d2.y, v2.y * silu_f(g2.y), dot);
       }
     }
-    dot = warp_sum(dot) * (1.0f / HID);
-#pragma unroll
+    dot = warp_sum(dot) * r * (1.0f / HID);  // mean(dhn * hn), hn = hs * r
+#pragma unroll 1
     for (int i = 0; i < 11; ++i) {
       const int c0 = i * 128 + lane * 4;
+      const uint2 va = *reinterpret_cast<const uint2*>(row + c0);
+      const uint2 ga = *reinterpret_cast<const uint2*>(row + HIDP + c0);
+      const uint2 da = *reinterpret_cast<const uint2*>(drow + c0);
+      const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&va);
+      const __nv_bfloat162* bp = reinterpret_cast<const __nv_bfloat162*>(&ga);
+      const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&da);
       float ov[4], og[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = 4 * i + e;
-        const float dhs = r * (dh[j] - hs[j] * r * dot);
-        const float sg = 1.0f / (1.0f + __expf(-gg[j]));
-        const float sil = gg[j] * sg;
-        ov[e] = dhs * sil;
-        og[e] = dhs * vv[j] * (sg * (1.0f + gg[j] * (1.0f - sg)));
+      for (int h = 0; h < 2; ++h) {
+        const float2 v2 = __bfloat1622float2(ap[h]), g2 = __bfloat1622float2(bp[h]), d2 = __bfloat1622float2(dp[h]);
+        const float vv[2] = {v2.x, v2.y}, gg[2] = {g2.x, g2.y}, dd[2] = {d2.x, d2.y};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float sg = 1.0f / (1.0f + __expf(-gg[e]));
+          const float sil = gg[e] * sg;
+          const float dhs = r * (dd[e] - vv[e] * sil * r * dot);
+          ov[2 * h + e] = dhs * sil;
+          og[2 * h + e] = dhs * vv[e] * (sg * (1.0f + gg[e] * (1.0f - sg)));
+        }
       }
       *reinterpret_cast<uint2*>(dvg + (size_t)t * 2 * HIDP + c0) = make_uint2(pack_bf16(ov[0], ov[1]), pack_bf16(ov[2], ov[3]));
       *reinterpret_cast<uint2*>(dvg + (size_t)t * 2 * HIDP + HIDP + c0) =
@@ -477,10 +482,8 @@ __global__ void __launch_bounds__(256) qknorm_rope_bwd_kernel(__nv_bfloat16* __r
                                                               const float* __restrict__ rope,
                                                               const float* __restrict__ qw, const float* __restrict__ kw,
                                                               float* __restrict__ dqw, float* __restrict__ dkw,
-                                                              float* __restrict__ dbias, int L) {
-  __shared__ float sBias[3072];
+                                                              int L) {
   __shared__ float sW[2][64];
-  for (int i = threadIdx.x; i < 3072; i += 256) sBias[i] = 0.f;
   if (threadIdx.x < 128) sW[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
   __syncthreads();
   const int b = blockIdx.y, l0 = blockIdx.x * TOKB;
@@ -496,14 +499,6 @@ __global__ void __launch_bounds__(256) qknorm_rope_bwd_kernel(__nv_bfloat16* __r
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int e = 0; e < 4; ++e) adw[a][e] = 0.f;
-  float abias[16][4];  // 16 iterations x 4 elements of q/k columns handled by this lane
-#pragma unroll
-  for (int it = 0; it < 16; ++it)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) abias[it][e] = 0.f;
-  float avb[32];  // v columns: lane owns [2048 + j4*256 + lane*8 .. +8)
-#pragma unroll
-  for (int i = 0; i < 32; ++i) avb[i] = 0.f;
 
   for (int rr = warp; rr < TOKB; rr += 8) {
     const int l = l0 + rr;
@@ -551,35 +546,11 @@ __global__ void __launch_bounds__(256) qknorm_rope_bwd_kernel(__nv_bfloat16* __r
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         dxr[e] = r * (dn[e] - n[e] * dot);
-        abias[it][e] += dxr[e];
       }
       *reinterpret_cast<__nv_bfloat162*>(drow + col + 2 * j) = __floats2bfloat162_rn(dxr[0], dxr[1]);
       *reinterpret_cast<__nv_bfloat162*>(drow + col + 32 + 2 * j) = __floats2bfloat162_rn(dxr[2], dxr[3]);
     }
-    // v part: column sums only
-#pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      const uint4 q = *reinterpret_cast<const uint4*>(drow + 2048 + j4 * 256 + lane * 8);
-      const __nv_bfloat162* qp = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        avb[j4 * 8 + 2 * k] += __low2float(qp[k]);
-        avb[j4 * 8 + 2 * k + 1] += __high2float(qp[k]);
-      }
-    }
   }
-#pragma unroll
-  for (int it = 0; it < 16; ++it) {
-    const int col = (it * 2 + half) * 64;
-    atomicAdd(sBias + col + 2 * j, abias[it][0]);
-    atomicAdd(sBias + col + 2 * j + 1, abias[it][1]);
-    atomicAdd(sBias + col + 32 + 2 * j, abias[it][2]);
-    atomicAdd(sBias + col + 33 + 2 * j, abias[it][3]);
-  }
-#pragma unroll
-  for (int j4 = 0; j4 < 4; ++j4)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(sBias + 2048 + j4 * 256 + lane * 8 + k, avb[j4 * 8 + k]);
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
     atomicAdd(&sW[a][2 * j], adw[a][0]);
@@ -588,7 +559,6 @@ __global__ void __launch_bounds__(256) qknorm_rope_bwd_kernel(__nv_bfloat16* __r
     atomicAdd(&sW[a][2 * j + 33], adw[a][3]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3072; i += 256) atomicAdd(dbias + i, sBias[i]);
   if (threadIdx.x < 64) atomicAdd(dqw + threadIdx.x, sW[0][threadIdx.x]);
   else if (threadIdx.x < 128) atomicAdd(dkw + threadIdx.x - 64, sW[1][threadIdx.x - 64]);
 }
@@ -596,9 +566,9 @@ int launch_qknorm_rope_bwd(void* dqkv, const void* raw, const float* rope, const
                            float* dqw, float* dkw, float* dbias, int B, int L, cudaStream_t s) {
   dim3 grid(ceil_div(L, TOKB), B);
   qknorm_rope_bwd_kernel<<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(raw),
-                                              rope, qw, kw, dqw, dkw, dbias, L);
+                                              rope, qw, kw, dqw, dkw, L);
   OSD_LAUNCHED();
-  return 0;
+  return launch_colsum_bf16(dqkv, dbias, B * L, 3072, s);  // dbqkv = column sums of the raw-projection gradients
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -702,9 +672,10 @@ __global__ void linear_small_bwd_in_kernel(const float* __restrict__ dpre, const
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (k >= K) return;
+  const int n0 = blockIdx.z * 64, n1 = min(N, n0 + 64);
   float acc = 0.f;
-  for (int n = 0; n < N; ++n) acc = fmaf(dpre[(size_t)b * N + n], __ldg(W + (size_t)n * K + k), acc);
-  din[(size_t)b * K + k] += acc;
+  for (int n = n0; n < n1; ++n) acc = fmaf(dpre[(size_t)b * N + n], __ldg(W + (size_t)n * K + k), acc);
+  atomicAdd(din + (size_t)b * K + k, acc);
 }
 int launch_linear_small_bwd(const float* dout, const float* pre_or_null, const float* in, const float* W, float* dW,
                             float* db, float* din, float* dpre_scratch, int Bn, int N, int K, int silu,
@@ -713,7 +684,7 @@ int launch_linear_small_bwd(const float* dout, const float* pre_or_null, const f
                                                            Bn, N, K, silu);
   OSD_LAUNCHED();
   if (din != nullptr) {
-    dim3 grid(ceil_div(K, 128), Bn);
+    dim3 grid(ceil_div(K, 128), Bn, ceil_div(N, 64));
     linear_small_bwd_in_kernel<<<grid, 128, 0, s>>>(silu ? dpre_scratch : dout, W, din, Bn, N, K);
     OSD_LAUNCHED();
   }
