@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
   uint64_t* ds_full = bars + 6;
   uint64_t* dq_done = bars + 7;
   uint64_t* qt_ready = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* dp_full = bars + 9;   // dP_j complete
+  uint64_t* p1_done = bars + 10;  // softmax has consumed S_j (phase 1 finished)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = (p.L + 127) / 128;
@@ -104,6 +106,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
     mbar_init(ds_full, 4);
     mbar_init(dq_done, 1);
     mbar_init(qt_ready, 4);
+    mbar_init(dp_full, 1);
+    mbar_init(p1_done, 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -134,23 +138,34 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
       const uint32_t id_o = make_idesc(FMT_BF16, 0, 1, 128, 64);   // dQ    : dS K-major x K_j MN-major
       const uint32_t tS = tmem_base, tDP = tmem_base + 64, tDQ = tmem_base + 128;
       const uint32_t tQ = tmem_base + 192, tDO = tmem_base + 224, tDS = tDP;
+      // Software pipeline (per kv tile j):  S_j | dP_j | S_{j+1} (once phase 1 of j is done) | dQ_j (needs dS_j) | dP_{j+1}
       auto issue_s = [&](int j) {
         const int st = j & 1;
         mbar_wait(&kv_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t aK = smem_u32(sK + st * T64), aV = smem_u32(sV + st * T64);
+        const uint32_t aK = smem_u32(sK + st * T64);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_ts(tS, tQ + k * 8, make_smem_desc(aK + k * 32, 0, 1024), id_s, k > 0);
+        umma_commit(s_full);
+      };
+      auto issue_dp = [&](int j) {
+        const uint32_t aV = smem_u32(sV + (j & 1) * T64);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_ts(tDP, tDO + k * 8, make_smem_desc(aV + k * 32, 0, 1024), id_s, k > 0);
-        umma_commit(s_full);
+        umma_commit(dp_full);
       };
       mbar_wait(qt_ready, 0);  // Q / dO copied into TMEM by the softmax warps
       tc_fence_after();
       issue_s(0);
+      issue_dp(0);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
-        mbar_wait(ds_full, j & 1);  // dS_j written (over dP_j); S_j / dP_j consumed
+        if (j + 1 < n_kv) {
+          mbar_wait(p1_done, j & 1);  // S_j consumed
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        mbar_wait(ds_full, j & 1);  // dS_j written over dP_j
         tc_fence_after();
         const uint32_t aK = smem_u32(sK + st * T64);
 #pragma unroll
@@ -158,7 +173,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
           umma_f16_ts(tDQ, tDS + k * 8, make_smem_desc(aK + k * 16 * 128, 0, 1024), id_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
         umma_commit(dq_done);
-        if (j + 1 < n_kv) issue_s(j + 1);
+        if (j + 1 < n_kv) issue_dp(j + 1);  // overwrites dS_j only after dQ_j has read it
       }
     }
   } else {
@@ -193,28 +208,42 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
     const float dsum = ok ? p.dsum[sidx] : 0.f;
     const float c = p.scale_log2;
     for (int j = 0; j < n_kv; ++j) {
+      const int valid = p.L - j * 64;
+      // ---- phase 1: P = exp2(S * c - lse2)  (while the dP MMA is in flight)
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int valid = p.L - j * 64;
-#pragma unroll 1
+      float pr[64];
+#pragma unroll
       for (int cch = 0; cch < 2; ++cch) {
-        uint32_t rs[32], rp[32];
+        uint32_t rs[32];
         __syncwarp();
         tmem_ld32(tS + cch * 32, rs);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pr[cch * 32 + i] = ex2f(fmaf(__uint_as_float(rs[i]), c, -lse2));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p1_done);
+      // ---- phase 2: dS = P o (dP - D) * scale -> bf16 over dP's first 32 columns
+      mbar_wait(dp_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cch = 0; cch < 2; ++cch) {
+        uint32_t rp[32];
+        __syncwarp();
         tmem_ld32(tDP + cch * 32, rp);
         tmem_wait_ld();
-        float ds[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pr = ex2f(fmaf(__uint_as_float(rs[i]), c, -lse2));
-          const float d = pr * (__uint_as_float(rp[i]) - dsum) * p.scale;
-          ds[i] = (cch * 32 + i < valid) ? d : 0.f;
-        }
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(ds[2 * i], ds[2 * i + 1]);
-        __syncwarp();
-        tmem_st16(tDS + cch * 16, pk);  // over dP columns [16*cch, 16*cch+16): already consumed above
+        for (int i = 0; i < 16; ++i) {
+          float d0 = pr[cch * 32 + 2 * i] * (__uint_as_float(rp[2 * i]) - dsum) * p.scale;
+          float d1 = pr[cch * 32 + 2 * i + 1] * (__uint_as_float(rp[2 * i + 1]) - dsum) * p.scale;
+          if (cch * 32 + 2 * i >= valid) d0 = 0.f;
+          if (cch * 32 + 2 * i + 1 >= valid) d1 = 0.f;
+          pk[i] = pack_bf16(d0, d1);
+        }
+        tmem_st16(tDS + cch * 16, pk);  // over dP columns [16*cch, 16*cch+16): already consumed
       }
       tmem_wait_st();
       tc_fence_before();
@@ -277,10 +306,12 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
   uint64_t* kv_full = bars + 0;
   uint64_t* q_full = bars + 1;   // [2]
   uint64_t* q_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* ds_full = bars + 6;
-  uint64_t* acc_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_full = bars + 5;    // S^T_i complete
+  uint64_t* ds_full = bars + 6;   // dS^T_i written (TMEM)
+  uint64_t* acc_done = bars + 7;  // dK_i issued-and-complete (everything before it too)
+  uint64_t* dp_full = bars + 8;   // dP^T_i complete
+  uint64_t* pt_full = bars + 9;   // P^T_i written (TMEM)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kt = (p.L + 127) / 128;
@@ -299,6 +330,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
     mbar_init(s_full, 1);
     mbar_init(ds_full, 4);
     mbar_init(acc_done, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(pt_full, 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -329,35 +362,47 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
       const uint32_t id_o = make_idesc(FMT_BF16, 0, 1, 128, 64);  // dV = P^T dO_i, dK = dS^T Q_i (B MN-major)
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
       const uint32_t tS = tmem_base, tDP = tmem_base + 64, tDV = tmem_base + 128, tDK = tmem_base + 192;
-      auto issue_s = [&](int i) {
+      // Software pipeline (per q tile i):   S^T_i | dP^T_i | dV_i (needs P^T_i) | S^T_{i+1} | dK_i (needs dS^T_i) | dP^T_{i+1}
+      // so that the exp phase of the softmax overlaps the dP^T MMA, the dS phase overlaps dV and the next S^T,
+      // and the softmax warps never idle in steady state.  The bf16 P^T / dS^T tiles alias the first 32 columns of
+      // S^T / dP^T, which the in-order tensor pipe makes safe with exactly this issue order.
+      auto issue_st = [&](int i) {
         const int st = i & 1;
         mbar_wait(&q_full[st], (i >> 1) & 1);
         tc_fence_after();
-        const uint32_t aQ = smem_u32(sQ + st * T64), aDO = smem_u32(sDO + st * T64);
+        const uint32_t aQ = smem_u32(sQ + st * T64);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ss(tS, make_smem_desc(aK + k * 32, 0, 1024), make_smem_desc(aQ + k * 32, 0, 1024), id_s, k > 0);
+        umma_commit(s_full);
+      };
+      auto issue_dpt = [&](int i) {
+        const uint32_t aDO = smem_u32(sDO + (i & 1) * T64);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ss(tDP, make_smem_desc(aV + k * 32, 0, 1024), make_smem_desc(aDO + k * 32, 0, 1024), id_s, k > 0);
-        umma_commit(s_full);
+        umma_commit(dp_full);
       };
       mbar_wait(kv_full, 0);
-      issue_s(0);
+      issue_st(0);
+      issue_dpt(0);
       for (int i = 0; i < n_q; ++i) {
         const int st = i & 1;
-        mbar_wait(ds_full, i & 1);
-        tc_fence_after();
         const uint32_t aQ = smem_u32(sQ + st * T64), aDO = smem_u32(sDO + st * T64);
+        mbar_wait(pt_full, i & 1);
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ts(tDV, tS + k * 8, make_smem_desc(aDO + k * 16 * 128, 0, 1024), id_o, (i > 0 || k > 0) ? 1u : 0u);
+        if (i + 1 < n_q) issue_st(i + 1);  // overwrites P^T_i only after dV_i has read it
+        mbar_wait(ds_full, i & 1);
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ts(tDK, tDP + k * 8, make_smem_desc(aQ + k * 16 * 128, 0, 1024), id_o, (i > 0 || k > 0) ? 1u : 0u);
         umma_commit(&q_empty[st]);
         umma_commit(acc_done);
-        if (i + 1 < n_q) issue_s(i + 1);  // overwrites P^T / dS^T only after the two MMAs above have read them
+        if (i + 1 < n_q) issue_dpt(i + 1);  // overwrites dS^T_i only after dK_i has read it
       }
     }
   } else {
@@ -383,38 +428,56 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
       float* st = sStat + (i & 1) * 128;
       float next_stat = 0.f;
       if (i + 1 < n_q) next_stat = load_stat(i + 1);
-      mbar_wait(s_full, i & 1);  // also implies dV_{i-1} / dK_{i-1} have consumed the previous P^T / dS^T
+      // ---- phase 1: P^T = exp2(S^T * c - lse2[q])  (needs only S^T; runs while the dP^T MMA is in flight)
+      mbar_wait(s_full, i & 1);
       tc_fence_after();
-#pragma unroll 1
+      float pt[64];
+#pragma unroll
       for (int cch = 0; cch < 2; ++cch) {
-        uint32_t rs[32], rp[32];
+        uint32_t rs[32];
         __syncwarp();
         tmem_ld32(tS + cch * 32, rs);
-        tmem_ld32(tDP + cch * 32, rp);
         tmem_wait_ld();
-        float pt[32], ds[32];
-        const float4* l4 = reinterpret_cast<const float4*>(st + cch * 32);       // broadcast LDS.128
-        const float4* d4 = reinterpret_cast<const float4*>(st + 64 + cch * 32);
+        const float4* l4 = reinterpret_cast<const float4*>(st + cch * 32);  // broadcast LDS.128
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-          const float4 lv = l4[k4], dv = d4[k4];
-          const float l2[4] = {lv.x, lv.y, lv.z, lv.w};
-          const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int k = k4 * 4 + e;
-            const float pr = ex2f(fmaf(__uint_as_float(rs[k]), c, -l2[e]));
-            pt[k] = pr;
-            ds[k] = pr * (__uint_as_float(rp[k]) - dd[e]) * p.scale;
-          }
+          const float4 lv = l4[k4];
+          pt[cch * 32 + k4 * 4 + 0] = ex2f(fmaf(__uint_as_float(rs[k4 * 4 + 0]), c, -lv.x));
+          pt[cch * 32 + k4 * 4 + 1] = ex2f(fmaf(__uint_as_float(rs[k4 * 4 + 1]), c, -lv.y));
+          pt[cch * 32 + k4 * 4 + 2] = ex2f(fmaf(__uint_as_float(rs[k4 * 4 + 2]), c, -lv.z));
+          pt[cch * 32 + k4 * 4 + 3] = ex2f(fmaf(__uint_as_float(rs[k4 * 4 + 3]), c, -lv.w));
         }
         uint32_t pk[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(pt[2 * k], pt[2 * k + 1]);
-        tmem_st16(tS + cch * 16, pk);
+        for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(pt[cch * 32 + 2 * k], pt[cch * 32 + 2 * k + 1]);
+        tmem_st16(tS + cch * 16, pk);  // over S^T columns already consumed
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pt_full);
+      // ---- phase 2: dS^T = P^T o (dP^T - D[q]) * scale  (runs while dV_i and S^T_{i+1} are in flight)
+      mbar_wait(dp_full, i & 1);
+      tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(ds[2 * k], ds[2 * k + 1]);
-        tmem_st16(tDP + cch * 16, pk);
+      for (int cch = 0; cch < 2; ++cch) {
+        uint32_t rp[32];
+        __syncwarp();
+        tmem_ld32(tDP + cch * 32, rp);
+        tmem_wait_ld();
+        const float4* d4 = reinterpret_cast<const float4*>(st + 64 + cch * 32);
+        uint32_t pk[16];
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 dv = d4[k4];
+          const float d0 = pt[cch * 32 + k4 * 4 + 0] * (__uint_as_float(rp[k4 * 4 + 0]) - dv.x) * p.scale;
+          const float d1 = pt[cch * 32 + k4 * 4 + 1] * (__uint_as_float(rp[k4 * 4 + 1]) - dv.y) * p.scale;
+          const float d2 = pt[cch * 32 + k4 * 4 + 2] * (__uint_as_float(rp[k4 * 4 + 2]) - dv.z) * p.scale;
+          const float d3 = pt[cch * 32 + k4 * 4 + 3] * (__uint_as_float(rp[k4 * 4 + 3]) - dv.w) * p.scale;
+          pk[k4 * 2] = pack_bf16(d0, d1);
+          pk[k4 * 2 + 1] = pack_bf16(d2, d3);
+        }
+        tmem_st16(tDP + cch * 16, pk);  // over dP^T columns already consumed
       }
       tmem_wait_st();
       tc_fence_before();
