@@ -16,6 +16,8 @@ static constexpr int ROW_BYTES = 128;  // one swizzle row: 64 bf16 or 32 tf32
 struct GemmParams {
   CUtensorMap tma_a;
   CUtensorMap tma_b;
+  CUtensorMap tma_c;    // output, box (128 bytes, 32 rows), SW128
+  CUtensorMap tma_raw;  // EPI_QKV: second output (pre-norm projections)
   int M, N, K;
   int a_major, b_major;
   int num_kb;        // total k-blocks
@@ -45,7 +47,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulators (power of two: 256 or 512)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STG_BYTES = 4 * 2 * 4096;  // epilogue staging: 4 warps x 2 buffers x [32 rows x 128 B]
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -55,7 +58,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* stg_base = smem + C::STAGES * C::STAGE_BYTES;  // 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + C::STG_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tfull_bar = bars + 2 * C::STAGES;
@@ -68,6 +72,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tma_a);
     tma_prefetch_desc(&p.tma_b);
+    tma_prefetch_desc(&p.tma_c);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -175,7 +180,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
   } else {
     // ================================================================== epilogue (4 warps)
+    // Each warp owns 32 accumulator rows.  Output leaves in 128-byte row segments (64 bf16 or 32 fp32 columns):
+    // the thread writes its segment into a swizzled [32 x 128 B] staging tile, one lane issues a TMA tensor
+    // store (or a TMA reduce-add for split-K / gradient accumulation).  Full-line, coalesced writes; rows past
+    // M and columns past N are clipped by the tensor map.
     const int quad = warp & 3;
+    uint8_t* stg = stg_base + (warp - 2) * 8192;
+    uint32_t n_st = 0;  // stores issued by this warp (staging buffer = n_st & 1)
+    auto stage_out = [&](const CUtensorMap* map, const uint32_t (&w)[32], int c0, int r0, bool reduce) {
+      uint8_t* buf = stg + (n_st & 1) * 4096;
+      if (n_st >= 2) {
+        if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer two stores ago has read it
+        __syncwarp();
+      }
+      const uint32_t rowb = smem_u32(buf) + lane * 128;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((u ^ (lane & 7)) << 4)), "r"(w[4 * u]),
+                     "r"(w[4 * u + 1]), "r"(w[4 * u + 2]), "r"(w[4 * u + 3])
+                     : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (reduce)
+          tma_reduce_add_2d(map, buf, c0, r0);
+        else
+          tma_store_2d(map, buf, c0, r0);
+        tma_store_commit();
+      }
+      ++n_st;
+    };
     int it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int tile = item / p.split_k;
@@ -184,70 +218,73 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int m = tm * BM + quad * 32 + lane;
-      const bool row_ok = m < p.M;
+      const int r0 = tm * BM + quad * 32;
+      const int m = r0 + lane;
       const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
 
       if constexpr (QKV) {
         // 64-column chunks = one attention head of q, k or v
         const float inv_d = 1.0f / 64.0f;
         const float eps = 1.1920929e-07f;  // torch.finfo(float32).eps: nn.RMSNorm(eps=None)
-        const int pos = row_ok ? (m % p.L) : 0;
+        const int pos = (m < p.M) ? (m % p.L) : 0;
 #pragma unroll 1
         for (int c = 0; c < BN / 64; ++c) {
           const int n0 = tn * BN + c * 64;
-          uint32_t r0[32], r1[32];
+          uint32_t r0v[32], r1v[32];
           __syncwarp();
-          tmem_ld32(trow + c * 64, r0);
-          tmem_ld32(trow + c * 64 + 32, r1);
+          tmem_ld32(trow + c * 64, r0v);
+          tmem_ld32(trow + c * 64 + 32, r1v);
           tmem_wait_ld();
           if (n0 >= p.N) continue;
           float x[64];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            x[j] = __uint_as_float(r0[j]) + __ldg(p.bias + n0 + j);
-            x[j + 32] = __uint_as_float(r1[j]) + __ldg(p.bias + n0 + 32 + j);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32) + j4);
+            x[4 * j4] = __uint_as_float(r0v[4 * j4]) + b0.x, x[4 * j4 + 1] = __uint_as_float(r0v[4 * j4 + 1]) + b0.y;
+            x[4 * j4 + 2] = __uint_as_float(r0v[4 * j4 + 2]) + b0.z, x[4 * j4 + 3] = __uint_as_float(r0v[4 * j4 + 3]) + b0.w;
+            x[32 + 4 * j4] = __uint_as_float(r1v[4 * j4]) + b1.x, x[33 + 4 * j4] = __uint_as_float(r1v[4 * j4 + 1]) + b1.y;
+            x[34 + 4 * j4] = __uint_as_float(r1v[4 * j4 + 2]) + b1.z, x[35 + 4 * j4] = __uint_as_float(r1v[4 * j4 + 3]) + b1.w;
           }
           const int which = n0 / p.dh;
-          if (p.raw_out != nullptr && row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.raw_out) + (size_t)m * p.ldc + n0);
+          uint32_t w[32];
+          if (p.raw_out != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              dst[j] = make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                                  pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+            for (int j = 0; j < 32; ++j) w[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+            stage_out(&p.tma_raw, w, n0, r0, false);
           }
           if (which < 2) {
             float ss = 0.f;
 #pragma unroll
             for (int j = 0; j < 64; ++j) ss = fmaf(x[j], x[j], ss);
             const float r = rsqrtf(ss * inv_d + eps);
-            const float* w = which == 0 ? p.qnorm_w : p.knorm_w;
+            const float4* wn = reinterpret_cast<const float4*>(which == 0 ? p.qnorm_w : p.knorm_w);
             const float4* cs = reinterpret_cast<const float4*>(p.rope + (size_t)pos * 64);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 cc = __ldg(cs + j4);
               const float4 sn = __ldg(cs + 8 + j4);
+              const float4 wa = __ldg(wn + j4), wb = __ldg(wn + 8 + j4);
               const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
               const float sv[4] = {sn.x, sn.y, sn.z, sn.w};
+              const float wav[4] = {wa.x, wa.y, wa.z, wa.w};
+              const float wbv[4] = {wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int j = j4 * 4 + e;
-                const float a = x[j] * r * __ldg(w + j);
-                const float b = x[j + 32] * r * __ldg(w + j + 32);
+                const float a = x[j] * r * wav[e];
+                const float b = x[j + 32] * r * wbv[e];
                 x[j] = a * cv[e] - b * sv[e];
                 x[j + 32] = a * sv[e] + b * cv[e];
               }
             }
           }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + (size_t)m * p.ldc + n0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              dst[j] = make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                                  pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
-          }
+          for (int j = 0; j < 32; ++j) w[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+          stage_out(&p.tma_c, w, n0, r0, false);
         }
-      } else {
+      } else if (p.c_fp32) {
+        // fp32 output (or fp32 reduce-add): 32 columns = 128 bytes per row segment
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           const int n0 = tn * BN + c * 32;
@@ -256,44 +293,56 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           tmem_ld32(trow + c * 32, r);
           tmem_wait_ld();
           if (n0 >= p.N) continue;  // warp-uniform
-          if (row_ok) {
-          float x[32];
           if (p.bias != nullptr && p.epi != EPI_ATOMIC) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) + __ldg(p.bias + n0 + j);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+              r[4 * j4] = __float_as_uint(__uint_as_float(r[4 * j4]) + b.x);
+              r[4 * j4 + 1] = __float_as_uint(__uint_as_float(r[4 * j4 + 1]) + b.y);
+              r[4 * j4 + 2] = __float_as_uint(__uint_as_float(r[4 * j4 + 2]) + b.z);
+              r[4 * j4 + 3] = __float_as_uint(__uint_as_float(r[4 * j4 + 3]) + b.w);
+            }
           }
           if (p.epi == EPI_SILU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(silu_f(__uint_as_float(r[j])));
           }
-          if (p.epi == EPI_ATOMIC) {
-            float* dst = static_cast<float*>(p.C) + (size_t)m * p.ldc + n0;
+          stage_out(&p.tma_c, r, n0, r0, p.epi == EPI_ATOMIC);
+        }
+      } else {
+        // bf16 output: 64 columns = 128 bytes per row segment
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          const int n0 = tn * BN + c * 64;
+          uint32_t ra[32], rb[32];
+          __syncwarp();
+          tmem_ld32(trow + c * 64, ra);
+          tmem_ld32(trow + c * 64 + 32, rb);
+          tmem_wait_ld();
+          if (n0 >= p.N) continue;  // warp-uniform
+          uint32_t w[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(x[j]), "f"(x[j + 1]),
-                           "f"(x[j + 2]), "f"(x[j + 3])
-                           : "memory");
-          } else if (p.c_fp32) {
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.C) + (size_t)m * p.ldc + n0);
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t* rr = half == 0 ? ra : rb;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + (size_t)m * p.ldc + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                                  pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias != nullptr && n0 + half * 32 < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + half * 32) + j4);
+              float v0 = __uint_as_float(rr[4 * j4]) + b.x, v1 = __uint_as_float(rr[4 * j4 + 1]) + b.y;
+              float v2 = __uint_as_float(rr[4 * j4 + 2]) + b.z, v3 = __uint_as_float(rr[4 * j4 + 3]) + b.w;
+              if (p.epi == EPI_SILU) v0 = silu_f(v0), v1 = silu_f(v1), v2 = silu_f(v2), v3 = silu_f(v3);
+              w[half * 16 + 2 * j4] = pack_bf16(v0, v1);
+              w[half * 16 + 2 * j4 + 1] = pack_bf16(v2, v3);
+            }
           }
-          }  // row_ok
+          stage_out(&p.tma_c, w, n0, r0, false);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (lane == 0) tma_store_wait<0>();  // all bulk stores of this warp complete before the CTA retires its smem
   }
 
   tc_fence_before();
@@ -320,6 +369,14 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
     OSD_TRY(make_tmap_2d(&p.tma_b, a.B, eb, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb * eb, C::EPR, BN));
   else
     OSD_TRY(make_tmap_2d(&p.tma_b, a.B, eb, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb * eb, C::EPR, C::BK));
+  {
+    const int ce = a.c_fp32 ? 4 : 2;
+    OSD_TRY(make_tmap_2d(&p.tma_c, a.C, ce, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldc * ce, 128 / ce, 32));
+    if (a.raw_out != nullptr)
+      OSD_TRY(make_tmap_2d(&p.tma_raw, a.raw_out, 2, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldc * 2, 64, 32));
+    else
+      p.tma_raw = p.tma_c;
+  }
   p.M = a.M;
   p.N = a.N;
   p.K = a.K;

@@ -186,6 +186,56 @@ def cases():
         ms = e0.elapsed_time(e1) / 5
         return {'ms': ms, 'tflops': 2 * M * N * K / ms / 1e9}
     cs.append(('gemm_speed_qkv_shape', gemm_speed))
+
+    def timeit(fn, n=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def speed_qkv_epi():
+        T, L = 131072, 8192
+        x = rnd(T, 512)
+        w = rnd(3072, 512)
+        b = rnd(3072, dtype=f32)
+        qw, kw = rnd(64, dtype=f32), rnd(64, dtype=f32)
+        rope = lib.rope_table(L, dev)
+        raw = torch.empty(T, 3072, dtype=bf, device=dev)
+        ms1 = timeit(lambda: lib.qkv_proj(x, w, b, qw, kw, rope, L, raw_out=raw))
+        ms0 = timeit(lambda: lib.qkv_proj(x, w, b, qw, kw, rope, L))
+        return {'ms_with_raw': ms1, 'ms_no_raw': ms0, 'tflops_with_raw': 2 * T * 3072 * 512 / ms1 / 1e9}
+    cs.append(('speed_qkv_epilogue', speed_qkv_epi))
+
+    def speed_wgrad():
+        T = 131072
+        dy, x = rnd(T, 3072), rnd(T, 512)
+        C = torch.zeros(3072, 512, dtype=f32, device=dev)
+        ms = timeit(lambda: lib.gemm(dy, x, C, a_major=1, b_major=1, epi=2, split_k=12))
+        return {'ms': ms, 'tflops': 2 * T * 3072 * 512 / ms / 1e9}
+    cs.append(('speed_wgrad_qkv', speed_wgrad))
+
+    def speed_dgrad():
+        T = 131072
+        dy, w = rnd(T, 3072), rnd(3072, 512)
+        C = torch.empty(T, 512, dtype=bf, device=dev)
+        ms = timeit(lambda: lib.gemm(dy, w, C, b_major=1))
+        return {'ms': ms, 'tflops': 2 * T * 3072 * 512 / ms / 1e9}
+    cs.append(('speed_dgrad_qkv', speed_dgrad))
+
+    def speed_f32out():
+        T = 131072
+        y, w = rnd(T, 1024), rnd(512, 1024)
+        b = rnd(512, dtype=f32)
+        C = torch.empty(T, 512, dtype=f32, device=dev)
+        ms = timeit(lambda: lib.gemm(y, w, C, bias=b))
+        return {'ms': ms, 'tflops': 2 * T * 512 * 1024 / ms / 1e9}
+    cs.append(('speed_outproj_f32', speed_f32out))
     return cs
 
 
