@@ -13,7 +13,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libosd_b200.so')
+LIB_PATH = os.environ.get('OSD_LIB_PATH', os.path.join(_HERE, 'libosd_b200.so'))  # override: A/B kernel experiments
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'osd_b200.h')
 
 _lib = None
