@@ -219,8 +219,13 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
         __syncwarp();
         tmem_ld32(tS + cch * 32, rs);
         tmem_wait_ld();
+        const float2 c2 = make_float2(c, c), nl2 = make_float2(-lse2, -lse2);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) pr[cch * 32 + i] = ex2f(fmaf(__uint_as_float(rs[i]), c, -lse2));
+        for (int i = 0; i < 32; i += 2) {
+          const float2 a = ffma2(make_float2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1])), c2, nl2);
+          pr[cch * 32 + i] = ex2f(a.x);
+          pr[cch * 32 + i + 1] = ex2f(a.y);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -235,13 +240,17 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
         tmem_ld32(tDP + cch * 32, rp);
         tmem_wait_ld();
         uint32_t pk[16];
+        const float2 nd2 = make_float2(-dsum, -dsum);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float d0 = pr[cch * 32 + 2 * i] * (__uint_as_float(rp[2 * i]) - dsum) * p.scale;
-          float d1 = pr[cch * 32 + 2 * i + 1] * (__uint_as_float(rp[2 * i + 1]) - dsum) * p.scale;
-          if (cch * 32 + 2 * i >= valid) d0 = 0.f;
-          if (cch * 32 + 2 * i + 1 >= valid) d1 = 0.f;
-          pk[i] = pack_bf16(d0, d1);
+          // dS / scale = P o (dP - D); the 1/sqrt(d) factor is applied once to the dQ accumulator in the epilogue
+          float2 d = fmul2(make_float2(pr[cch * 32 + 2 * i], pr[cch * 32 + 2 * i + 1]),
+                           fadd2(make_float2(__uint_as_float(rp[2 * i]), __uint_as_float(rp[2 * i + 1])), nd2));
+          if (valid < 64) {
+            if (cch * 32 + 2 * i >= valid) d.x = 0.f;
+            if (cch * 32 + 2 * i + 1 >= valid) d.y = 0.f;
+          }
+          pk[i] = pack_bf16(d.x, d.y);
         }
         tmem_st16(tDS + cch * 16, pk);  // over dP columns [16*cch, 16*cch+16): already consumed
       }
@@ -262,10 +271,10 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
         uint4* dst = reinterpret_cast<uint4*>(p.dqkv + ((size_t)b * p.L + q) * (3 * p.dh) + h * 64 + cch * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          dst[i] = make_uint4(pack_bf16(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1])),
-                              pack_bf16(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])),
-                              pack_bf16(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])),
-                              pack_bf16(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])));
+          dst[i] = make_uint4(pack_bf16(__uint_as_float(r[8 * i]) * p.scale, __uint_as_float(r[8 * i + 1]) * p.scale),
+                              pack_bf16(__uint_as_float(r[8 * i + 2]) * p.scale, __uint_as_float(r[8 * i + 3]) * p.scale),
+                              pack_bf16(__uint_as_float(r[8 * i + 4]) * p.scale, __uint_as_float(r[8 * i + 5]) * p.scale),
+                              pack_bf16(__uint_as_float(r[8 * i + 6]) * p.scale, __uint_as_float(r[8 * i + 7]) * p.scale));
       }
     }
     tc_fence_before();
@@ -419,8 +428,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
     auto load_stat = [&](int i) -> float {
       const int qi = i * 64 + (tid & 63);
       const bool okq = qi < p.L;
-      if (tid < 64) return okq ? p.lse[sbase + qi] * 1.4426950408889634f : INFINITY;
-      return okq ? p.dsum[sbase + qi] : 0.f;
+      if (tid < 64) return okq ? -p.lse[sbase + qi] * 1.4426950408889634f : -INFINITY;  // stored negated
+      return okq ? -p.dsum[sbase + qi] : 0.f;  // stored negated: dS uses dP + (-D)
     };
     sStat[tid] = load_stat(0);
     named_bar_sync(1, 128);
@@ -439,13 +448,18 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
         tmem_ld32(tS + cch * 32, rs);
         tmem_wait_ld();
         const float4* l4 = reinterpret_cast<const float4*>(st + cch * 32);  // broadcast LDS.128
+        const float2 c2 = make_float2(c, c);
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-          const float4 lv = l4[k4];
-          pt[cch * 32 + k4 * 4 + 0] = ex2f(fmaf(__uint_as_float(rs[k4 * 4 + 0]), c, -lv.x));
-          pt[cch * 32 + k4 * 4 + 1] = ex2f(fmaf(__uint_as_float(rs[k4 * 4 + 1]), c, -lv.y));
-          pt[cch * 32 + k4 * 4 + 2] = ex2f(fmaf(__uint_as_float(rs[k4 * 4 + 2]), c, -lv.z));
-          pt[cch * 32 + k4 * 4 + 3] = ex2f(fmaf(__uint_as_float(rs[k4 * 4 + 3]), c, -lv.w));
+          const float4 lv = l4[k4];  // -lse2 of 4 consecutive q columns (stored negated)
+          const float2 a = ffma2(make_float2(__uint_as_float(rs[k4 * 4 + 0]), __uint_as_float(rs[k4 * 4 + 1])), c2,
+                                 make_float2(lv.x, lv.y));
+          const float2 b = ffma2(make_float2(__uint_as_float(rs[k4 * 4 + 2]), __uint_as_float(rs[k4 * 4 + 3])), c2,
+                                 make_float2(lv.z, lv.w));
+          pt[cch * 32 + k4 * 4 + 0] = ex2f(a.x);
+          pt[cch * 32 + k4 * 4 + 1] = ex2f(a.y);
+          pt[cch * 32 + k4 * 4 + 2] = ex2f(b.x);
+          pt[cch * 32 + k4 * 4 + 3] = ex2f(b.y);
         }
         uint32_t pk[16];
 #pragma unroll
@@ -469,13 +483,16 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
         uint32_t pk[16];
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-          const float4 dv = d4[k4];
-          const float d0 = pt[cch * 32 + k4 * 4 + 0] * (__uint_as_float(rp[k4 * 4 + 0]) - dv.x) * p.scale;
-          const float d1 = pt[cch * 32 + k4 * 4 + 1] * (__uint_as_float(rp[k4 * 4 + 1]) - dv.y) * p.scale;
-          const float d2 = pt[cch * 32 + k4 * 4 + 2] * (__uint_as_float(rp[k4 * 4 + 2]) - dv.z) * p.scale;
-          const float d3 = pt[cch * 32 + k4 * 4 + 3] * (__uint_as_float(rp[k4 * 4 + 3]) - dv.w) * p.scale;
-          pk[k4 * 2] = pack_bf16(d0, d1);
-          pk[k4 * 2 + 1] = pack_bf16(d2, d3);
+          const float4 dv = d4[k4];  // -D of 4 consecutive q columns
+          // dS^T / scale = P^T o (dP^T - D); 1/sqrt(d) is applied to the dK accumulator in the epilogue
+          const float2 e0 = fmul2(make_float2(pt[cch * 32 + k4 * 4 + 0], pt[cch * 32 + k4 * 4 + 1]),
+                                  fadd2(make_float2(__uint_as_float(rp[k4 * 4 + 0]), __uint_as_float(rp[k4 * 4 + 1])),
+                                        make_float2(dv.x, dv.y)));
+          const float2 e1 = fmul2(make_float2(pt[cch * 32 + k4 * 4 + 2], pt[cch * 32 + k4 * 4 + 3]),
+                                  fadd2(make_float2(__uint_as_float(rp[k4 * 4 + 2]), __uint_as_float(rp[k4 * 4 + 3])),
+                                        make_float2(dv.z, dv.w)));
+          pk[k4 * 2] = pack_bf16(e0.x, e0.y);
+          pk[k4 * 2 + 1] = pack_bf16(e1.x, e1.y);
         }
         tmem_st16(tDP + cch * 16, pk);  // over dP^T columns already consumed
       }
@@ -500,6 +517,10 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
         __syncwarp();
         tmem_ld32((which == 0 ? tDK : tDV) + cch * 32, r);
         tmem_wait_ld();
+        if (which == 0) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * p.scale);
+        }
         if (ok) {
           uint4* dst = reinterpret_cast<uint4*>(p.dqkv + ((size_t)b * p.L + kv) * (3 * p.dh) + (1 + which) * p.dh +
                                                 h * 64 + cch * 32);

@@ -267,18 +267,26 @@ __global__ void __launch_bounds__(AT_THREADS, AtCfg<BKV, PT>::CTAS) attn_fwd_ker
         tmem_wait_ld();
         float pv[32];
         if (valid >= BKV) {
+          const float2 c2 = make_float2(c, c), n2 = make_float2(neg_mc, neg_mc);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) pv[i] = ex2(fmaf(__uint_as_float(r[i]), c, neg_mc));
+          for (int i = 0; i < 32; i += 2) {
+            const float2 a = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, n2);
+            pv[i] = ex2(a.x);
+            pv[i + 1] = ex2(a.y);
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             pv[i] = (cch * 32 + i < valid) ? ex2(fmaf(__uint_as_float(r[i]), c, neg_mc)) : 0.f;
         }
         {  // four independent partial sums: the serial FADD chain was a visible stall
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) s0 += pv[i], s1 += pv[i + 1], s2 += pv[i + 2], s3 += pv[i + 3];
-          sum += (s0 + s1) + (s2 + s3);
+          for (int i = 0; i < 32; i += 4) {
+            s01 = fadd2(s01, make_float2(pv[i], pv[i + 1]));
+            s23 = fadd2(s23, make_float2(pv[i + 2], pv[i + 3]));
+          }
+          sum += (s01.x + s01.y) + (s23.x + s23.y);
         }
         if (PT) {
           uint32_t pk[16];

@@ -247,6 +247,35 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int a_mn_major, int b
 constexpr int FMT_BF16 = 1;
 constexpr int FMT_TF32 = 2;
 
+// ----------------------------------------------------------------------------- packed fp32x2 math (sm_100: FFMA2/FADD2/FMUL2)
+// Two fp32 operations per issued instruction: the softmax loops of the attention kernels are issue-bound, so
+// halving the FFMA/FADD/FMUL count matters as much as the SFU rate.
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float2 upk2(unsigned long long v) {
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(v));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)), "l"(pk2(c.x, c.y)));
+  return upk2(rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+  return upk2(rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+  return upk2(rd);
+}
+
 // ----------------------------------------------------------------------------- small math helpers
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
