@@ -158,6 +158,13 @@ OSD_API int osd_adamw_ema_step(float* p, const float* g, float* m, float* v, flo
                                float grad_scale, float ema_decay, int ema_copy, double* acc_scratch, float* scal_out,
                                void* stream);
 
+/* Fused distance-marching loss of DiffusionTrainer.forward (train.py:86-108): given xt, x1 [B,6,L], u_pred [B],
+ * v_pred [B,6,L] writes out4 = {loss, osl, del, u_mape} and the gradients of loss w.r.t. u_pred (du [B]) and
+ * v_pred (dv [B,6,L]).  scratch: 4*B floats.  The random draws (t, x0) stay with the caller's generator. */
+OSD_API int osd_loss_fwd_bwd(const float* xt, const float* x1, const float* u_pred, const float* v_pred, float c0,
+                             float osl_weight, float del_weight, int B, int L, float* out4, float* du, float* dv,
+                             float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,10 @@ int launch_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, s
                      float beta1, float beta2, float eps, float wd, float max_norm, float grad_scale, float ema_decay,
                      int ema_copy, double* acc_scratch, float* scal_out, cudaStream_t s);
 
+// loss (loss.cu)
+int launch_loss(const float* xt, const float* x1, const float* u, const float* v, float c0, float osl_w, float del_w,
+                int B, int L, float* out4, float* du, float* dv, float* acc, cudaStream_t s);
+
 // attention (attn_fwd.cu, attn_bwd.cu)
 int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, void* dqkv, int B,
                     int L, int H, cudaStream_t stream);

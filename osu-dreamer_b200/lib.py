@@ -225,3 +225,16 @@ def launch_count() -> int:
     f = load().osd_launch_count
     f.restype = ctypes.c_ulonglong
     return int(f())
+
+
+def loss_fwd_bwd(xt, x1, u, v, c0, osl_w, del_w):
+    """-> (out4 = [loss, osl, del, u_mape], du [B], dv [B,6,L]) -- fused loss value + output gradients."""
+    B, _, L = xt.shape
+    dev = xt.device
+    out4 = torch.empty(4, dtype=torch.float32, device=dev)
+    du = torch.empty(B, dtype=torch.float32, device=dev)
+    dv = torch.empty_like(v)
+    scratch = torch.empty(4 * B, dtype=torch.float32, device=dev)
+    _check(load().osd_loss_fwd_bwd(ptr(xt), ptr(x1), ptr(u), ptr(v), c_float(c0), c_float(osl_w), c_float(del_w),
+                                   c_int(B), c_int(L), ptr(out4), ptr(du), ptr(dv), ptr(scratch), stream()))
+    return out4, du, dv

@@ -44,6 +44,23 @@ def make_lr_schedule(lr: LRScheduleArgs):
     return schedule
 
 
+class _FusedLoss(torch.autograd.Function):
+    """loss(u_pred, v_pred) with the value and both gradients produced by one fused CUDA pass (osd_loss_fwd_bwd)."""
+
+    @staticmethod
+    def forward(ctx, u_pred, v_pred, xt, x1, c0, osl_w, del_w):
+        out4, du, dv = lib.loss_fwd_bwd(xt.float().contiguous(), x1.float().contiguous(), u_pred.float().contiguous(),
+                                        v_pred.float().contiguous(), c0, osl_w, del_w)
+        ctx.save_for_backward(du, dv)
+        ctx.mark_non_differentiable(out4)
+        return out4[0].clone(), out4
+
+    @staticmethod
+    def backward(ctx, g, _g4):
+        du, dv = ctx.saved_tensors
+        return du * g, dv * g, None, None, None, None, None
+
+
 def frame_dist_sq(a: Tensor, b: Tensor) -> Tensor:
     """train.py:22-31: squared distance in the per-frame metric (sum over channels, mean over length)."""
     return (a - b).square().sum(1).mean(1)
@@ -125,6 +142,11 @@ class DiffusionTrainer(nn.Module):
         x0 = torch.randn_like(x1)
         xt = torch.lerp(x0, x1, t[:, None, None])
         u_pred, v_pred = model.forward(h, s, xt)
+
+        if x1.is_cuda:  # fused loss + output gradients (the torch expression below is its specification)
+            loss, out4 = _FusedLoss.apply(u_pred, v_pred, xt, x1, float(model.c0), float(self.osl_weight),
+                                          float(self.del_weight))
+            return loss, {'loss': out4[0], 'osl': out4[1], 'del': out4[2], 'u_mape': out4[3]}
 
         d_sq = frame_dist_sq(xt, x1)
         u_target = (d_sq + model.c0).sqrt()

@@ -29,6 +29,30 @@ def test_fused_adamw_ema_matches_torch_golden(golden_dir):
         assert np.allclose(ema.cpu().numpy(), g['emas'][step], rtol=2e-5, atol=2e-6)
 
 
+def test_fused_loss_matches_torch_expression():
+    """osd_loss_fwd_bwd vs the reference's torch expression (train.py:86-101) and its autograd gradients."""
+    from osu_dreamer_b200 import lib
+    B, L = 3, 700
+    g = torch.Generator().manual_seed(3)
+    xt, x1 = torch.randn(B, 6, L, generator=g).cuda(), torch.randn(B, 6, L, generator=g).cuda()
+    u = (torch.rand(B, generator=g) * 3 + 0.2).cuda().requires_grad_(True)
+    v = torch.randn(B, 6, L, generator=g).cuda().requires_grad_(True)
+    c0, ow, dw = 0.0949756, 1.0, 30.0
+    d_sq = O.frame_dist_sq(xt, x1)
+    ut = (d_sq + c0).sqrt()
+    osl = (O.frame_dist_sq(xt - u[:, None, None] * v, x1) / (d_sq + c0)).mean()
+    del_ = O.frame_dist_sq(v, (xt - x1) / ut[:, None, None]).mean()
+    loss = ow * osl + dw * del_
+    loss.backward()
+    mape = ((u - ut) / ut).abs().mean()
+    out4, du, dv = lib.loss_fwd_bwd(xt, x1, u.detach(), v.detach(), c0, ow, dw)
+    torch.cuda.synchronize()
+    ref = torch.stack([loss, osl, del_, mape]).detach()
+    assert torch.allclose(out4, ref, rtol=2e-5, atol=1e-6), (out4, ref)
+    assert torch.allclose(du, u.grad, rtol=1e-4, atol=1e-7)
+    assert float((dv - v.grad).abs().max()) <= 1e-5 * float(v.grad.abs().max())
+
+
 def test_trainer_steps_and_state_dict_keys(oracle_sd):
     from osu_dreamer_b200.trainer import DiffusionTrainer, LRScheduleArgs
     from osu_dreamer_b200.denoiser import default_args
