@@ -49,7 +49,8 @@ extern "C" {
 
 /* precision modes */
 #define OSD_BF16 0     /* bf16 tensor-core operands, fp32 accumulate / residual / statistics */
-#define OSD_TF32 1     /* fp32 storage, tf32 tensor-core operands */
+#define OSD_F32X3 1    /* fp32-grade: every tensor-core product as the 3-term bf16 split a_hi*b_hi + a_lo*b_hi + a_hi*b_lo
+                          (operands stored as (hi | lo) bf16 pairs); inference only */
 
 OSD_API int osd_abi_version(void);
 OSD_API const char* osd_last_error(void);

@@ -9,6 +9,19 @@ namespace osd {
 static constexpr int D = 512;
 static constexpr float RMS_EPS = 1e-6f;  // osu_dreamer/common/rms_norm.py:12
 
+// 4 consecutive values -> bf16; in split mode the row is (hi | lo) with lo = bf16(x - float(hi)) at column +width
+__device__ __forceinline__ void store4_bf16(__nv_bfloat16* row, int width, int c0, const float (&o)[4], int split) {
+  const uint32_t h0 = pack_bf16(o[0], o[1]), h1 = pack_bf16(o[2], o[3]);
+  *reinterpret_cast<uint2*>(row + c0) = make_uint2(h0, h1);
+  if (split) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&h0);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&h1);
+    *reinterpret_cast<uint2*>(row + width + c0) =
+        make_uint2(pack_bf16(o[0] - __low2float(a), o[1] - __high2float(a)),
+                   pack_bf16(o[2] - __low2float(b), o[3] - __high2float(b)));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 struct InvFreq {
   float v[32];
@@ -52,6 +65,32 @@ __global__ void cf_to_tm_kernel(const float* __restrict__ in, TOut* __restrict__
     const int l = l0 + i, c = c0 + tx;
     if (l < L && c < C) out[((size_t)b * L + l) * C + c] = static_cast<TOut>(tile[tx][i]);
   }
+}
+__global__ void cf_to_tm_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int L) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, l = l0 + tx;
+    tile[i][tx] = (c < C && l < L) ? in[((size_t)b * C + c) * L + l] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int l = l0 + i, c = c0 + tx;
+    if (l < L && c < C) {
+      const float v = tile[tx][i];
+      const __nv_bfloat16 h = __float2bfloat16(v);
+      out[((size_t)b * L + l) * 2 * C + c] = h;
+      out[((size_t)b * L + l) * 2 * C + C + c] = __float2bfloat16(v - __bfloat162float(h));
+    }
+  }
+}
+int launch_cf_to_tm_split(const float* in, void* out, int B, int C, int L, cudaStream_t stream) {
+  dim3 grid(ceil_div(L, 32), ceil_div(C, 32), B), block(32, 8);
+  cf_to_tm_split_kernel<<<grid, block, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), C, L);
+  OSD_LAUNCHED();
+  return 0;
 }
 int launch_cf_to_tm(const float* in, void* out, int out_bf16, int B, int C, int L, cudaStream_t stream) {
   dim3 grid(ceil_div(L, 32), ceil_div(C, 32), B), block(32, 8);
@@ -174,7 +213,7 @@ __device__ __forceinline__ float row_inv_rms(const float (&r)[16]) {
 template <typename TOut>
 __global__ void prenorm_mod_kernel(const float* __restrict__ x, const float* __restrict__ mod,
                                    const __nv_bfloat16* __restrict__ cl, TOut* __restrict__ z, int L, int T,
-                                   int cl_bcast) {
+                                   int cl_bcast, int split, const float* __restrict__ cl_f32) {
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= T) return;
@@ -192,29 +231,32 @@ __global__ void prenorm_mod_kernel(const float* __restrict__ x, const float* __r
     const float4 h4 = *reinterpret_cast<const float4*>(sh + c0);
     float o[4] = {r[4 * v] * inv * (1.f + s4.x) + h4.x, r[4 * v + 1] * inv * (1.f + s4.y) + h4.y,
                   r[4 * v + 2] * inv * (1.f + s4.z) + h4.z, r[4 * v + 3] * inv * (1.f + s4.w) + h4.w};
-    if (cl != nullptr) {
+    if (cl_f32 != nullptr) {
+      const float4 c4 = *reinterpret_cast<const float4*>(cl_f32 + tcl * D + c0);
+      o[0] += c4.x, o[1] += c4.y, o[2] += c4.z, o[3] += c4.w;
+    } else if (cl != nullptr) {
       const uint2 c2 = *reinterpret_cast<const uint2*>(cl + tcl * D + c0);
       const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&c2.x);
       const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&c2.y);
       o[0] += __low2float(p0), o[1] += __high2float(p0), o[2] += __low2float(p1), o[3] += __high2float(p1);
     }
     if constexpr (sizeof(TOut) == 2) {
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(z) + (size_t)t * D + c0) =
-          make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+      store4_bf16(reinterpret_cast<__nv_bfloat16*>(z) + (size_t)t * (split ? 2 * D : D), D, c0, o, split);
     } else {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(z) + (size_t)t * D + c0) = make_float4(o[0], o[1], o[2], o[3]);
     }
   }
 }
 int launch_prenorm_mod(const float* x, const float* mod, const void* cl, void* z, int z_fp32, int B, int L,
-                       int cl_bcast, cudaStream_t stream) {
+                       int cl_bcast, cudaStream_t stream, int split, int cl_is_f32) {
   const int T = B * L;
   if (z_fp32)
     prenorm_mod_kernel<float><<<ceil_div(T, 8), 256, 0, stream>>>(x, mod, static_cast<const __nv_bfloat16*>(cl),
-                                                                  static_cast<float*>(z), L, T, cl_bcast);
+                                                                  static_cast<float*>(z), L, T, cl_bcast, 0, nullptr);
   else
     prenorm_mod_kernel<__nv_bfloat16><<<ceil_div(T, 8), 256, 0, stream>>>(
-        x, mod, static_cast<const __nv_bfloat16*>(cl), static_cast<__nv_bfloat16*>(z), L, T, cl_bcast);
+        x, mod, cl_is_f32 ? nullptr : static_cast<const __nv_bfloat16*>(cl), static_cast<__nv_bfloat16*>(z), L, T,
+        cl_bcast, split, cl_is_f32 ? static_cast<const float*>(cl) : nullptr);
   OSD_LAUNCHED();
   return 0;
 }
@@ -255,7 +297,7 @@ static constexpr int DW_TOK = 32;
 template <typename TOut>
 __global__ void __launch_bounds__(256) prenorm_mod_dwconv_kernel(
     const float* __restrict__ x, const float* __restrict__ mod, const float* __restrict__ wconv /*[512][5]*/,
-    const float* __restrict__ bconv, TOut* __restrict__ z, __nv_bfloat16* __restrict__ hmod_out, int L) {
+    const float* __restrict__ bconv, TOut* __restrict__ z, __nv_bfloat16* __restrict__ hmod_out, int L, int split) {
   extern __shared__ float sh[];  // [DW_TOK + 4][512]
   const int b = blockIdx.y;
   const int l0 = blockIdx.x * DW_TOK;
@@ -307,25 +349,32 @@ __global__ void __launch_bounds__(256) prenorm_mod_dwconv_kernel(
         float acc = bb;
 #pragma unroll
         for (int k = 0; k < 5; ++k) acc = fmaf(w[k], win[k], acc);
-        z[((size_t)b * L + l) * D + c] = static_cast<TOut>(acc);
+        if (split) {  // (hi | lo) row of width 2*D (bf16 only)
+          const __nv_bfloat16 hh = __float2bfloat16(acc);
+          __nv_bfloat16* zr = reinterpret_cast<__nv_bfloat16*>(z) + ((size_t)b * L + l) * 2 * D;
+          zr[c] = hh;
+          zr[D + c] = __float2bfloat16(acc - __bfloat162float(hh));
+        } else {
+          z[((size_t)b * L + l) * D + c] = static_cast<TOut>(acc);
+        }
       }
     }
   }
 }
 int launch_prenorm_mod_dwconv(const float* x, const float* mod, const float* wconv, const float* bconv, void* z,
-                              int z_fp32, void* hmod_out, int B, int L, cudaStream_t stream) {
+                              int z_fp32, void* hmod_out, int B, int L, cudaStream_t stream, int split) {
   dim3 grid(ceil_div(L, DW_TOK), B);
   const int smem = (DW_TOK + 4) * D * 4;
   if (z_fp32) {
     auto k = prenorm_mod_dwconv_kernel<float>;
     OSD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k<<<grid, 256, smem, stream>>>(x, mod, wconv, bconv, static_cast<float*>(z),
-                                   static_cast<__nv_bfloat16*>(hmod_out), L);
+                                   static_cast<__nv_bfloat16*>(hmod_out), L, 0);
   } else {
     auto k = prenorm_mod_dwconv_kernel<__nv_bfloat16>;
     OSD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k<<<grid, 256, smem, stream>>>(x, mod, wconv, bconv, static_cast<__nv_bfloat16*>(z),
-                                   static_cast<__nv_bfloat16*>(hmod_out), L);
+                                   static_cast<__nv_bfloat16*>(hmod_out), L, split);
   }
   OSD_LAUNCHED();
   return 0;
@@ -336,7 +385,7 @@ int launch_prenorm_mod_dwconv(const float* x, const float* mod, const float* wco
 static constexpr int HID = 1365, HIDP = 1408;
 template <typename T>
 __global__ void swiglu_norm_kernel(const T* __restrict__ vg, T* __restrict__ hn, float* __restrict__ rinv_out,
-                                   int Tn) {
+                                   int Tn, __nv_bfloat16* __restrict__ hn_split) {
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= Tn) return;
@@ -376,19 +425,26 @@ __global__ void swiglu_norm_kernel(const T* __restrict__ vg, T* __restrict__ hn,
     if constexpr (sizeof(T) == 2) {
       *reinterpret_cast<uint2*>(hn + (size_t)t * HIDP + c0) =
           make_uint2(pack_bf16(hs[4 * i] * inv, hs[4 * i + 1] * inv), pack_bf16(hs[4 * i + 2] * inv, hs[4 * i + 3] * inv));
+    } else if (hn_split != nullptr) {
+      const float o4[4] = {hs[4 * i] * inv, hs[4 * i + 1] * inv, hs[4 * i + 2] * inv, hs[4 * i + 3] * inv};
+      store4_bf16(hn_split + (size_t)t * 2 * HIDP, HIDP, c0, o4, 1);
     } else {
       *reinterpret_cast<float4*>(hn + (size_t)t * HIDP + c0) =
           make_float4(hs[4 * i] * inv, hs[4 * i + 1] * inv, hs[4 * i + 2] * inv, hs[4 * i + 3] * inv);
     }
   }
 }
+// is_fp32 = 2: fp32 vg in, bf16 (hi | lo) hn out [T, 2*HIDP]
 int launch_swiglu_norm(const void* vg, void* hn, float* rinv_out, int is_fp32, int T, cudaStream_t stream) {
-  if (is_fp32)
+  if (is_fp32 == 2)
+    swiglu_norm_kernel<float><<<ceil_div(T, 8), 256, 0, stream>>>(static_cast<const float*>(vg), nullptr, rinv_out, T,
+                                                                  static_cast<__nv_bfloat16*>(hn));
+  else if (is_fp32)
     swiglu_norm_kernel<float><<<ceil_div(T, 8), 256, 0, stream>>>(static_cast<const float*>(vg),
-                                                                  static_cast<float*>(hn), rinv_out, T);
+                                                                  static_cast<float*>(hn), rinv_out, T, nullptr);
   else
     swiglu_norm_kernel<__nv_bfloat16><<<ceil_div(T, 8), 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(vg), static_cast<__nv_bfloat16*>(hn), rinv_out, T);
+        static_cast<const __nv_bfloat16*>(vg), static_cast<__nv_bfloat16*>(hn), rinv_out, T, nullptr);
   OSD_LAUNCHED();
   return 0;
 }
@@ -622,6 +678,36 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, TOut* __restri
   float v = 0.f;
   if (sr >= 0 && c < cols_src) v = src[(size_t)sr * cols_src + c];
   dst[i] = static_cast<TOut>(v);
+}
+__global__ void pack_weight_split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows_src,
+                                         int cols_src, int rows_dst, int cols_dst, int split_at, int split_pad) {
+  // like pack_weight_kernel but every destination row is (hi | lo): [rows_dst, 2 * cols_dst]
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = (size_t)rows_dst * cols_dst;
+  if (i >= n) return;
+  const int r = (int)(i / cols_dst), c = (int)(i % cols_dst);
+  int sr = -1;
+  if (split_at > 0) {
+    if (r < split_at)
+      sr = r;
+    else if (r >= split_pad && r < split_pad + split_at)
+      sr = r - split_pad + split_at;
+  } else if (r < rows_src) {
+    sr = r;
+  }
+  float v = 0.f;
+  if (sr >= 0 && c < cols_src) v = src[(size_t)sr * cols_src + c];
+  const __nv_bfloat16 h = __float2bfloat16(v);
+  dst[(size_t)r * 2 * cols_dst + c] = h;
+  dst[(size_t)r * 2 * cols_dst + cols_dst + c] = __float2bfloat16(v - __bfloat162float(h));
+}
+int launch_pack_weight_split(const float* src, void* dst, int rows_src, int cols_src, int rows_dst, int cols_dst,
+                             int split_at, int split_pad, cudaStream_t stream) {
+  const size_t n = (size_t)rows_dst * cols_dst;
+  pack_weight_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+      src, static_cast<__nv_bfloat16*>(dst), rows_src, cols_src, rows_dst, cols_dst, split_at, split_pad);
+  OSD_LAUNCHED();
+  return 0;
 }
 int launch_pack_weight(const float* src, void* dst, int dst_fp32, int rows_src, int cols_src, int rows_dst,
                        int cols_dst, int split_at, int split_pad, cudaStream_t stream) {

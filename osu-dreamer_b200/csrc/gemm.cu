@@ -21,6 +21,9 @@ struct GemmParams {
   int M, N, K;
   int a_major, b_major;
   int num_kb;        // total k-blocks
+  int split3;        // 3x-bf16: num_kb = 3 * kb_seg, operands (hi | lo) along K
+  int kb_seg;        // k-blocks of one K-long segment
+  int c_split;       // bf16 output as (hi | lo)
   int kb_per_split;  // k-blocks per split
   int split_k;
   int tiles_m, tiles_n;
@@ -110,7 +113,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          const int k0 = kb * C::BK;
+          int k0 = kb * C::BK, k0b = k0;
+          if (p.split3) {  // segments: (A_hi, B_hi), (A_lo, B_hi), (A_hi, B_lo)
+            const int seg = kb / p.kb_seg, off = kb - seg * p.kb_seg;
+            k0 = ((seg == 1 ? p.kb_seg : 0) + off) * C::BK;
+            k0b = ((seg == 2 ? p.kb_seg : 0) + off) * C::BK;
+          }
           if (p.a_major == MAJOR_K) {
             tma_load_2d(sa, &p.tma_a, &full_bar[stage], k0, tm * BM);
           } else {
@@ -119,11 +127,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
               tma_load_2d(sa + c * (C::BK * ROW_BYTES), &p.tma_a, &full_bar[stage], tm * BM + c * C::EPR, k0);
           }
           if (p.b_major == MAJOR_K) {
-            tma_load_2d(sb, &p.tma_b, &full_bar[stage], k0, tn * BN);
+            tma_load_2d(sb, &p.tma_b, &full_bar[stage], k0b, tn * BN);
           } else {
 #pragma unroll
             for (int c = 0; c < BN / C::EPR; ++c)
-              tma_load_2d(sb + c * (C::BK * ROW_BYTES), &p.tma_b, &full_bar[stage], tn * BN + c * C::EPR, k0);
+              tma_load_2d(sb + c * (C::BK * ROW_BYTES), &p.tma_b, &full_bar[stage], tn * BN + c * C::EPR, k0b);
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -282,6 +290,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) w[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
           stage_out(&p.tma_c, w, n0, r0, false);
+          if (p.c_split) {  // lo = bf16(x - float(hi))
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+              w[j] = pack_bf16(x[2 * j] - __low2float(h2), x[2 * j + 1] - __high2float(h2));
+            }
+            stage_out(&p.tma_c, w, p.N + n0, r0, false);
+          }
         }
       } else if (p.c_fp32) {
         // fp32 output (or fp32 reduce-add): 32 columns = 128 bytes per row segment
@@ -333,9 +349,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
               if (p.epi == EPI_SILU) v0 = silu_f(v0), v1 = silu_f(v1), v2 = silu_f(v2), v3 = silu_f(v3);
               w[half * 16 + 2 * j4] = pack_bf16(v0, v1);
               w[half * 16 + 2 * j4 + 1] = pack_bf16(v2, v3);
+              if (p.c_split) {  // keep the residuals in place of the accumulators for the (lo) store below
+                const __nv_bfloat162 ha = *reinterpret_cast<const __nv_bfloat162*>(&w[half * 16 + 2 * j4]);
+                const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&w[half * 16 + 2 * j4 + 1]);
+                uint32_t* rw = half == 0 ? ra : rb;
+                rw[4 * j4] = __float_as_uint(v0 - __low2float(ha)), rw[4 * j4 + 1] = __float_as_uint(v1 - __high2float(ha));
+                rw[4 * j4 + 2] = __float_as_uint(v2 - __low2float(hb)), rw[4 * j4 + 3] = __float_as_uint(v3 - __high2float(hb));
+              }
             }
           }
           stage_out(&p.tma_c, w, n0, r0, false);
+          if (p.c_split) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              w[j] = pack_bf16(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1]));
+              w[16 + j] = pack_bf16(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1]));
+            }
+            stage_out(&p.tma_c, w, p.N + n0, r0, false);
+          }
         }
       }
       tc_fence_before();
@@ -361,17 +392,19 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   GemmParams p;
   const int eb = (ELEM == ELEM_BF16) ? 2 : 4;
   // A operand
+  const uint64_t Kphys = a.split3 ? 2 * (uint64_t)a.K : (uint64_t)a.K;
   if (a.a_major == MAJOR_K)
-    OSD_TRY(make_tmap_2d(&p.tma_a, a.A, eb, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * eb, C::EPR, BM));
+    OSD_TRY(make_tmap_2d(&p.tma_a, a.A, eb, Kphys, (uint64_t)a.M, (uint64_t)a.lda * eb, C::EPR, BM));
   else
     OSD_TRY(make_tmap_2d(&p.tma_a, a.A, eb, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda * eb, C::EPR, C::BK));
   if (a.b_major == MAJOR_K)
-    OSD_TRY(make_tmap_2d(&p.tma_b, a.B, eb, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb * eb, C::EPR, BN));
+    OSD_TRY(make_tmap_2d(&p.tma_b, a.B, eb, Kphys, (uint64_t)a.N, (uint64_t)a.ldb * eb, C::EPR, BN));
   else
     OSD_TRY(make_tmap_2d(&p.tma_b, a.B, eb, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb * eb, C::EPR, C::BK));
   {
     const int ce = a.c_fp32 ? 4 : 2;
-    OSD_TRY(make_tmap_2d(&p.tma_c, a.C, ce, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldc * ce, 128 / ce, 32));
+    OSD_TRY(make_tmap_2d(&p.tma_c, a.C, ce, (uint64_t)a.N * (a.c_split ? 2 : 1), (uint64_t)a.M, (uint64_t)a.ldc * ce,
+                         128 / ce, 32));
     if (a.raw_out != nullptr)
       OSD_TRY(make_tmap_2d(&p.tma_raw, a.raw_out, 2, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldc * 2, 64, 32));
     else
@@ -382,7 +415,10 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   p.K = a.K;
   p.a_major = a.a_major;
   p.b_major = a.b_major;
-  p.num_kb = ceil_div(a.K, C::BK);
+  p.kb_seg = ceil_div(a.K, C::BK);
+  p.split3 = a.split3;
+  p.c_split = a.c_split;
+  p.num_kb = a.split3 ? 3 * p.kb_seg : p.kb_seg;
   int split = a.split_k < 1 ? 1 : a.split_k;
   if (split > p.num_kb) split = p.num_kb;
   p.kb_per_split = ceil_div(p.num_kb, split);
@@ -420,6 +456,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   OSD_CHECK(a.N % 32 == 0, "gemm: N=%d must be a multiple of 32", a.N);
   OSD_CHECK(a.epi != EPI_ATOMIC || a.c_fp32, "gemm: EPI_ATOMIC needs an fp32 output");
   OSD_CHECK(a.split_k <= 1 || a.epi == EPI_ATOMIC, "gemm: split-K needs EPI_ATOMIC");
+  OSD_CHECK(!a.split3 || (a.elem == ELEM_BF16 && a.a_major == MAJOR_K && a.b_major == MAJOR_K && a.K % 64 == 0 &&
+                          a.split_k <= 1),
+            "gemm: split3 needs bf16 K-major operands with K %% 64 == 0");
+  OSD_CHECK(!a.c_split || (!a.c_fp32 && a.epi != EPI_ATOMIC && a.N % 64 == 0), "gemm: c_split needs a bf16 store epilogue");
   const int align = a.c_fp32 ? 4 : 8;
   OSD_CHECK(a.ldc % align == 0, "gemm: ldc=%lld must be a multiple of %d", (long long)a.ldc, align);
   if (a.epi == EPI_QKV) {

@@ -26,6 +26,11 @@ struct GemmArgs {
   int c_fp32 = 0;
   const float* bias = nullptr;
   int split_k = 1;
+  // 3x-bf16 split precision ("fp32-grade" path): A is [M, 2K] = (hi | lo), B is [N, 2K] = (hi | lo), both K-major;
+  // the kernel runs the three partial products A_hi B_hi + A_lo B_hi + A_hi B_lo as one 3K-long reduction.
+  int split3 = 0;
+  // bf16 outputs written as (hi | lo) pairs: C is [M, 2N], hi in columns [0,N), lo = bf16(x - hi) in [N,2N)
+  int c_split = 0;
   // EPI_QKV
   const float* qnorm_w = nullptr;  // [64]
   const float* knorm_w = nullptr;  // [64]

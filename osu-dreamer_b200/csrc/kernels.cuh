@@ -11,11 +11,14 @@ int launch_linear_small(const float* in, const float* W, const float* bias, floa
                         int silu, cudaStream_t stream);
 int launch_proj_in(const float* xt, const float* W, const float* bias, float* x, int B, int L, cudaStream_t stream);
 int launch_prenorm_mod(const float* x, const float* mod, const void* cl, void* z, int z_fp32, int B, int L,
-                       int cl_bcast, cudaStream_t stream);
+                       int cl_bcast, cudaStream_t stream, int split = 0, int cl_is_f32 = 0);
+int launch_cf_to_tm_split(const float* in, void* out, int B, int C, int L, cudaStream_t stream);
+int launch_pack_weight_split(const float* src, void* dst, int rows_src, int cols_src, int rows_dst, int cols_dst,
+                             int split_at, int split_pad, cudaStream_t stream);
 int launch_postnorm_gate_add(const float* x, const float* h, const float* mod, float* x_out, int B, int L,
                              cudaStream_t stream);
 int launch_prenorm_mod_dwconv(const float* x, const float* mod, const float* wconv, const float* bconv, void* z,
-                              int z_fp32, void* hmod_out, int B, int L, cudaStream_t stream);
+                              int z_fp32, void* hmod_out, int B, int L, cudaStream_t stream, int split = 0);
 int launch_swiglu_norm(const void* vg, void* hn, float* rinv_out, int is_fp32, int T, cudaStream_t stream);
 int launch_final_norm_proj_out(const float* x, const float* Wo, const float* bo, float* v, int B, int L,
                                cudaStream_t stream);
@@ -70,6 +73,8 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
                     int L, int H, cudaStream_t stream);
 int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int variant,
                     cudaStream_t stream);
+int launch_attn_fwd_x3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                       cudaStream_t stream);
 int launch_qk_bound(const float* qw, const float* kw, float* out, cudaStream_t stream);
 
 }  // namespace osd

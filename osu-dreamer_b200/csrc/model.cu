@@ -9,26 +9,29 @@
 
 namespace osd {
 
-static inline size_t esz_of(int mode) { return mode == OSD_BF16 ? 2 : 4; }
+static inline size_t esz_of(int) { return 2; }              // operands are bf16 in both modes
+static inline int kmul_of(int mode) { return mode == OSD_F32X3 ? 2 : 1; }  // (hi | lo) pairs double the K extent
 static inline size_t al(size_t x) { return align_up(x, 1024); }
 
 PackedLayout packed_layout(int mode) {
   PackedLayout p;
   p.esz = esz_of(mode);
+  p.kmul = kmul_of(mode);
+  const size_t e = p.esz * p.kmul;
   size_t off = 0;
   p.wa = off;
-  off += al((size_t)128 * 128 * p.esz);
+  off += al((size_t)128 * 128 * e);
   size_t lo = 0;
   p.l_cl = lo;
-  lo += al((size_t)512 * 128 * p.esz);
+  lo += al((size_t)512 * 128 * e);
   p.l_qkv = lo;
-  lo += al((size_t)3072 * 512 * p.esz);
+  lo += al((size_t)3072 * 512 * e);
   p.l_out = lo;
-  lo += al((size_t)512 * 1024 * p.esz);
+  lo += al((size_t)512 * 1024 * e);
   p.l_vg = lo;
-  lo += al((size_t)2 * OSD_HIDP * 512 * p.esz);
+  lo += al((size_t)2 * OSD_HIDP * 512 * e);
   p.l_po = lo;
-  lo += al((size_t)512 * OSD_HIDP * p.esz);
+  lo += al((size_t)512 * OSD_HIDP * e);
   p.layer0 = off;
   p.layer_stride = lo;
   off += 8 * lo;
@@ -43,7 +46,8 @@ PackedLayout packed_layout(int mode) {
 ActPlan make_plan(int B, int L, int a_batch, int mode, int save) {
   ActPlan a;
   const size_t T = (size_t)B * L, Ta = (size_t)a_batch * L;
-  const size_t e = esz_of(mode);
+  const bool X = mode == OSD_F32X3;
+  const size_t e = esz_of(mode) * kmul_of(mode);  // bytes per operand element ((hi | lo) pairs in split mode)
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t r = o;
@@ -51,17 +55,17 @@ ActPlan make_plan(int B, int L, int a_batch, int mode, int save) {
     return r;
   };
   a.x0 = take(T * 512 * 4);
-  a.cl = take(Ta * 512 * 2);  // proj_cl output is always bf16 (added in fp32 inside prenorm_mod)
+  a.cl = take(Ta * 512 * (X ? 4 : 2));  // proj_cl output: bf16, or fp32 in split mode (added inside prenorm_mod)
   a.z = take(T * 512 * e);
   a.qkv_raw = save ? take(T * 3072 * 2) : 0;
-  a.qkv = take(T * 3072 * 2);
+  a.qkv = take(T * 3072 * e);
   a.y = take(T * 1024 * e);
   a.lse = take(T * 16 * 4);
   a.o = take(T * 512 * 4);
   a.x1 = take(T * 512 * 4);
   a.hmod = save ? take(T * 512 * 2) : 0;
   a.z2 = take(T * 512 * e);
-  a.vg = take(T * 2 * OSD_HIDP * e);
+  a.vg = take(T * 2 * OSD_HIDP * (X ? 4 : 2));  // consumed by swiglu_norm only: fp32 in split mode
   a.hn = take(T * OSD_HIDP * e);
   a.rinv2 = take(T * 4);
   a.f = take(T * 512 * 4);
@@ -84,16 +88,19 @@ ActPlan make_plan(int B, int L, int a_batch, int mode, int save) {
 // ------------------------------------------------------------------------------------------------
 static int pack_weights(const float* const* P, uint8_t* packed, int mode, cudaStream_t s) {
   const PackedLayout lay = packed_layout(mode);
-  const int f32 = mode != OSD_BF16;
-  OSD_TRY(launch_pack_weight(P[P_AUDIO_W], packed + lay.wa, f32, 128, 128, 128, 128, 0, 0, s));
+  const bool X = mode == OSD_F32X3;
+  auto pack = [&](const float* src, void* dst, int rs, int cs, int rd, int cd, int sa, int sp) -> int {
+    if (X) return launch_pack_weight_split(src, dst, rs, cs, rd, cd, sa, sp, s);
+    return launch_pack_weight(src, dst, 0, rs, cs, rd, cd, sa, sp, s);
+  };
+  OSD_TRY(pack(P[P_AUDIO_W], packed + lay.wa, 128, 128, 128, 128, 0, 0));
   for (int l = 0; l < 8; ++l) {
     uint8_t* lb = packed + lay.layer0 + l * lay.layer_stride;
-    OSD_TRY(launch_pack_weight(P[lp(l, L_CL_W)], lb + lay.l_cl, f32, 512, 128, 512, 128, 0, 0, s));
-    OSD_TRY(launch_pack_weight(P[lp(l, L_QKV_W)], lb + lay.l_qkv, f32, 3072, 512, 3072, 512, 0, 0, s));
-    OSD_TRY(launch_pack_weight(P[lp(l, L_OUT_W)], lb + lay.l_out, f32, 512, 1024, 512, 1024, 0, 0, s));
-    OSD_TRY(launch_pack_weight(P[lp(l, L_VG_W)], lb + lay.l_vg, f32, 2 * OSD_HID, 512, 2 * OSD_HIDP, 512, OSD_HID,
-                               OSD_HIDP, s));
-    OSD_TRY(launch_pack_weight(P[lp(l, L_PO_W)], lb + lay.l_po, f32, 512, OSD_HID, 512, OSD_HIDP, 0, 0, s));
+    OSD_TRY(pack(P[lp(l, L_CL_W)], lb + lay.l_cl, 512, 128, 512, 128, 0, 0));
+    OSD_TRY(pack(P[lp(l, L_QKV_W)], lb + lay.l_qkv, 3072, 512, 3072, 512, 0, 0));
+    OSD_TRY(pack(P[lp(l, L_OUT_W)], lb + lay.l_out, 512, 1024, 512, 1024, 0, 0));
+    OSD_TRY(pack(P[lp(l, L_VG_W)], lb + lay.l_vg, 2 * OSD_HID, 512, 2 * OSD_HIDP, 512, OSD_HID, OSD_HIDP));
+    OSD_TRY(pack(P[lp(l, L_PO_W)], lb + lay.l_po, 512, OSD_HID, 512, OSD_HIDP, 0, 0));
     OSD_TRY(launch_pack_weight(P[lp(l, L_VG_B)], packed + lay.bvg + (size_t)l * 2 * OSD_HIDP * 4, 1, 2 * OSD_HID, 1,
                                2 * OSD_HIDP, 1, OSD_HID, OSD_HIDP, s));
     OSD_TRY(launch_qk_bound(P[lp(l, L_QN_W)], P[lp(l, L_KN_W)], reinterpret_cast<float*>(packed + lay.bounds) + l, s));
@@ -105,12 +112,17 @@ static int precompute_conditioning(const float* const* P, const PackedW& W, int 
                                    const float* style, int B, int L, void* a_tok, float* cond, void* scratch,
                                    cudaStream_t s) {
   const int Ta = a_batch * L;
-  const int f32 = mode != OSD_BF16;
-  // audio [Ba,128,L] fp32 -> token-major operand dtype -> a = silu(proj_audio(audio))  (model.py:45,82)
-  OSD_TRY(launch_cf_to_tm(audio, scratch, !f32, a_batch, 128, L, s));
+  const int X = mode == OSD_F32X3;
+  const int km = X ? 2 : 1;
+  // audio [Ba,128,L] fp32 -> token-major bf16 operand ((hi | lo) in split mode) -> a = silu(proj_audio(audio))
+  // (model.py:45,82)
+  if (X)
+    OSD_TRY(launch_cf_to_tm_split(audio, scratch, a_batch, 128, L, s));
+  else
+    OSD_TRY(launch_cf_to_tm(audio, scratch, 1, a_batch, 128, L, s));
   GemmArgs g;
-  g.A = scratch; g.B = W.wa(); g.lda = 128; g.ldb = 128; g.M = Ta; g.N = 128; g.K = 128;
-  g.elem = f32 ? ELEM_TF32 : ELEM_BF16; g.epi = EPI_SILU; g.C = a_tok; g.ldc = 128; g.c_fp32 = f32;
+  g.A = scratch; g.B = W.wa(); g.lda = 128 * km; g.ldb = 128 * km; g.M = Ta; g.N = 128; g.K = 128;
+  g.elem = ELEM_BF16; g.epi = EPI_SILU; g.C = a_tok; g.ldc = 128 * km; g.c_fp32 = 0; g.split3 = X; g.c_split = X;
   g.bias = P[P_AUDIO_B];
   OSD_TRY(launch_gemm(g, s));
   // cg = silu(proj_style(style)) (model.py:46,83); modulation vectors for every layer (backbone.py:76,82) and u_mod
@@ -130,9 +142,10 @@ static int precompute_conditioning(const float* const* P, const PackedW& W, int 
 // proj_cl for one layer: cl = a_tok * Wcl^T + b  -> bf16 [Ta, 512]   (backbone.py:63,78)
 static int proj_cl(const float* const* P, const PackedW& W, int mode, int l, const void* a_tok, int Ta, void* cl,
                    cudaStream_t s) {
+  const int X = mode == OSD_F32X3, km = X ? 2 : 1;
   GemmArgs g;
-  g.A = a_tok; g.B = W.cl(l); g.lda = 128; g.ldb = 128; g.M = Ta; g.N = 512; g.K = 128;
-  g.elem = mode == OSD_BF16 ? ELEM_BF16 : ELEM_TF32; g.epi = EPI_STORE; g.C = cl; g.ldc = 512; g.c_fp32 = 0;
+  g.A = a_tok; g.B = W.cl(l); g.lda = 128 * km; g.ldb = 128 * km; g.M = Ta; g.N = 512; g.K = 128;
+  g.elem = ELEM_BF16; g.epi = EPI_STORE; g.C = cl; g.ldc = 512; g.c_fp32 = X; g.split3 = X;
   g.bias = P[lp(l, L_CL_B)];
   return launch_gemm(g, s);
 }
@@ -153,12 +166,13 @@ struct FwdCtx {
 static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cudaStream_t s) {
   const int B = c.B, L = c.L, T = B * L, Ta = c.a_batch * L;
   const int mode = c.mode;
-  const int f32 = mode != OSD_BF16;
-  const int elem = f32 ? ELEM_TF32 : ELEM_BF16;
-  OSD_CHECK(!f32, "pred_forward: the fp32/tf32 path is not enabled in this build");
+  const int X = mode == OSD_F32X3;  // fp32-grade: split-precision operands (hi | lo), inference only
+  const int km = X ? 2 : 1;
+  OSD_CHECK(!(X && c.save), "pred_forward: the fp32-grade (3x bf16) path is inference-only");
   const ActPlan& pl = c.plan;
   auto LB = [&](int l) { return c.ws + (size_t)l * pl.layer_stride; };
   const void* a_tok = c.a_tok;
+  const size_t cl_bytes = al((size_t)Ta * 512 * (X ? 4 : 2));
 
   OSD_TRY(launch_proj_in(xt, c.P[P_IN_W], c.P[P_IN_B], reinterpret_cast<float*>(LB(0) + pl.x0), B, L, s));
   for (int l = 0; l < 8; ++l) {
@@ -169,36 +183,44 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
                          : reinterpret_cast<float*>(LB(l + 1) + pl.x0);
     const void* cl;
     if (c.cl_hoisted != nullptr) {
-      cl = c.cl_hoisted + (size_t)l * al((size_t)Ta * 512 * 2);
+      cl = c.cl_hoisted + (size_t)l * cl_bytes;
     } else {
       OSD_TRY(proj_cl(c.P, c.W, mode, l, a_tok, Ta, lb + pl.cl, s));
       cl = lb + pl.cl;
     }
     // ---- attention sub-block (backbone.py:76-80)
-    OSD_TRY(launch_prenorm_mod(x0, c.cond.mod1(l), cl, lb + pl.z, f32, B, L, c.a_batch == 1, s));
+    OSD_TRY(launch_prenorm_mod(x0, c.cond.mod1(l), cl, lb + pl.z, 0, B, L, c.a_batch == 1, s, X, X));
     GemmArgs q;
-    q.A = lb + pl.z; q.B = c.W.qkv(l); q.lda = 512; q.ldb = 512; q.M = T; q.N = 3072; q.K = 512; q.elem = elem;
-    q.epi = EPI_QKV; q.C = lb + pl.qkv; q.ldc = 3072; q.c_fp32 = 0; q.bias = c.P[lp(l, L_QKV_B)];
+    q.A = lb + pl.z; q.B = c.W.qkv(l); q.lda = 512 * km; q.ldb = 512 * km; q.M = T; q.N = 3072; q.K = 512;
+    q.elem = ELEM_BF16; q.split3 = X; q.c_split = X;
+    q.epi = EPI_QKV; q.C = lb + pl.qkv; q.ldc = 3072 * km; q.c_fp32 = 0; q.bias = c.P[lp(l, L_QKV_B)];
     q.qnorm_w = c.P[lp(l, L_QN_W)]; q.knorm_w = c.P[lp(l, L_KN_W)]; q.rope = c.rope; q.L = L; q.dh = 1024;
     q.raw_out = c.save ? lb + pl.qkv_raw : nullptr;
     OSD_TRY(launch_gemm(q, s));
-    OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), c.W.bound(l), B, L, 16, 2, s));
+    if (X)
+      OSD_TRY(launch_attn_fwd_x3(lb + pl.qkv, lb + pl.y, nullptr, c.W.bound(l), B, L, 16, s));
+    else
+      OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), c.W.bound(l), B, L, 16, 2,
+                              s));
     GemmArgs o;
-    o.A = lb + pl.y; o.B = c.W.out(l); o.lda = 1024; o.ldb = 1024; o.M = T; o.N = 512; o.K = 1024; o.elem = elem;
+    o.A = lb + pl.y; o.B = c.W.out(l); o.lda = 1024 * km; o.ldb = 1024 * km; o.M = T; o.N = 512; o.K = 1024;
+    o.elem = ELEM_BF16; o.split3 = X;
     o.epi = EPI_STORE; o.C = lb + pl.o; o.ldc = 512; o.c_fp32 = 1; o.bias = c.P[lp(l, L_OUT_B)];
     OSD_TRY(launch_gemm(o, s));
     OSD_TRY(launch_postnorm_gate_add(x0, reinterpret_cast<float*>(lb + pl.o), c.cond.mod1(l), x1, B, L, s));
     // ---- ffn sub-block (backbone.py:82-86, swiglu.py:27-32)
-    OSD_TRY(launch_prenorm_mod_dwconv(x1, c.cond.mod2(l), c.P[lp(l, L_DW_W)], c.P[lp(l, L_DW_B)], lb + pl.z2, f32,
-                                      c.save ? lb + pl.hmod : nullptr, B, L, s));
+    OSD_TRY(launch_prenorm_mod_dwconv(x1, c.cond.mod2(l), c.P[lp(l, L_DW_W)], c.P[lp(l, L_DW_B)], lb + pl.z2, 0,
+                                      c.save ? lb + pl.hmod : nullptr, B, L, s, X));
     GemmArgs g;
-    g.A = lb + pl.z2; g.B = c.W.vg(l); g.lda = 512; g.ldb = 512; g.M = T; g.N = 2 * OSD_HIDP; g.K = 512; g.elem = elem;
-    g.epi = EPI_STORE; g.C = lb + pl.vg; g.ldc = 2 * OSD_HIDP; g.c_fp32 = f32; g.bias = c.W.bvg(l);
+    g.A = lb + pl.z2; g.B = c.W.vg(l); g.lda = 512 * km; g.ldb = 512 * km; g.M = T; g.N = 2 * OSD_HIDP; g.K = 512;
+    g.elem = ELEM_BF16; g.split3 = X;
+    g.epi = EPI_STORE; g.C = lb + pl.vg; g.ldc = 2 * OSD_HIDP; g.c_fp32 = X; g.bias = c.W.bvg(l);
     OSD_TRY(launch_gemm(g, s));
-    OSD_TRY(launch_swiglu_norm(lb + pl.vg, lb + pl.hn, reinterpret_cast<float*>(lb + pl.rinv2), f32, T, s));
+    OSD_TRY(launch_swiglu_norm(lb + pl.vg, lb + pl.hn, reinterpret_cast<float*>(lb + pl.rinv2), X ? 2 : 0, T, s));
     GemmArgs po;
-    po.A = lb + pl.hn; po.B = c.W.po(l); po.lda = OSD_HIDP; po.ldb = OSD_HIDP; po.M = T; po.N = 512; po.K = OSD_HIDP;
-    po.elem = elem; po.epi = EPI_STORE; po.C = lb + pl.f; po.ldc = 512; po.c_fp32 = 1; po.bias = c.P[lp(l, L_PO_B)];
+    po.A = lb + pl.hn; po.B = c.W.po(l); po.lda = OSD_HIDP * km; po.ldb = OSD_HIDP * km; po.M = T; po.N = 512;
+    po.K = OSD_HIDP; po.elem = ELEM_BF16; po.split3 = X;
+    po.epi = EPI_STORE; po.C = lb + pl.f; po.ldc = 512; po.c_fp32 = 1; po.bias = c.P[lp(l, L_PO_B)];
     OSD_TRY(launch_gemm(po, s));
     OSD_TRY(launch_postnorm_gate_add(x1, reinterpret_cast<float*>(lb + pl.f), c.cond.mod2(l), xo, B, L, s));
   }
@@ -397,12 +419,12 @@ size_t osd_workspace_bytes(int B, int L, int a_batch, int mode, int save) {
 }
 size_t osd_sample_extra_bytes(int B, int L, int a_batch) {
   // hoisted proj_cl outputs [8][Ta,512] bf16 + v [B,6,L] + u [B] + eta [2]
-  return 8 * al((size_t)a_batch * L * 512 * 2) + al((size_t)B * 6 * L * 4) + al((size_t)B * 4) + 1024;
+  return 8 * al((size_t)a_batch * L * 512 * 4) + al((size_t)B * 6 * L * 4) + al((size_t)B * 4) + 1024;
 }
 
 int osd_pack_weights(const float* const* params, void* packed, int mode, void* stream) {
   OSD_CHECK(params && packed, "osd_pack_weights: null argument");
-  OSD_CHECK(mode == OSD_BF16 || mode == OSD_TF32, "osd_pack_weights: bad mode %d", mode);
+  OSD_CHECK(mode == OSD_BF16 || mode == OSD_F32X3, "osd_pack_weights: bad mode %d", mode);
   return pack_weights(params, static_cast<uint8_t*>(packed), mode, static_cast<cudaStream_t>(stream));
 }
 
@@ -462,7 +484,7 @@ int osd_sample(const float* const* params, const void* packed, int mode, const v
   c.save = 0;
   uint8_t* ex = static_cast<uint8_t*>(extra);
   const int Ta = a_batch * L;
-  const size_t cl_bytes = al((size_t)Ta * 512 * 2);
+  const size_t cl_bytes = al((size_t)Ta * 512 * (mode == OSD_F32X3 ? 4 : 2));
   for (int l = 0; l < 8; ++l) OSD_TRY(proj_cl(params, c.W, mode, l, a_tok, Ta, ex + l * cl_bytes, s));
   c.cl_hoisted = ex;
   float* v = reinterpret_cast<float*>(ex + 8 * cl_bytes);

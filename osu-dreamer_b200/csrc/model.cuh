@@ -19,7 +19,8 @@ inline int lp(int layer, int which) { return P_LAYER0 + layer * P_LAYER_STRIDE +
 
 // ---- packed operand weights (bf16 or fp32-for-tf32), one buffer ----
 struct PackedLayout {
-  size_t esz;  // operand element size
+  size_t esz;  // operand element size (bf16)
+  int kmul;    // 2 in the split-precision mode: every weight row is (hi | lo)
   size_t wa;   // [128,128]
   size_t layer0, layer_stride;
   size_t l_cl, l_qkv, l_out, l_vg, l_po;  // offsets inside a layer block (bytes)

@@ -144,9 +144,14 @@ class DiffusionModel(nn.Module):
 
     # ------------------------------------------------------------------ runtime plumbing
     def _mode(self):
+        """'bf16': bf16 tensor-core operands, fp32 accumulate / residual / statistics (training + inference).
+        'fp32': fp32-grade inference -- every tensor-core product runs as the 3-term bf16 split
+        a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (tcgen05 has no fp32 MMA and kind::tf32 truncates its operands)."""
         if self.precision == 'bf16':
-            return lib.BF16
-        raise lib.OsdError("precision 'fp32' (tf32 tensor-core path) is not enabled yet; use 'bf16'")
+            return lib.MODE_BF16
+        if self.precision == 'fp32':
+            return lib.MODE_F32X3
+        raise lib.OsdError(f"unknown precision {self.precision!r}: use 'bf16' or 'fp32'")
 
     def _params(self):
         return [p for p in self.parameters()]
@@ -191,8 +196,8 @@ class DiffusionModel(nn.Module):
         a_batch, _, L = audio.shape
         B = style.shape[0]
         mode = self._mode()
-        op = torch.bfloat16 if mode == lib.BF16 else torch.float32
-        a_tok = torch.empty(a_batch * L, 128, dtype=op, device=audio.device)
+        km = 2 if mode == lib.MODE_F32X3 else 1  # (hi | lo) bf16 pairs in the fp32-grade mode
+        a_tok = torch.empty(a_batch * L, 128 * km, dtype=torch.bfloat16, device=audio.device)
         cond = torch.empty(lib.cond_floats(B), dtype=torch.float32, device=audio.device)
         scratch = torch.empty(a_batch * L * 128, dtype=torch.float32, device=audio.device)
         lib.precompute_conditioning(rt.parr, rt.packed, mode, audio.float().contiguous(), style.float().contiguous(),
@@ -204,7 +209,10 @@ class DiffusionModel(nn.Module):
         """model.py:73-84 -> (a [#B,A,l], cg [B,C]) in the reference's channels-first layout."""
         a_tok, cond = self._conditioning_tokens(audio, style)
         a_batch, _, L = audio.shape
-        a = lib.tokens_to_channels(a_tok, a_batch, 128, L)
+        if a_tok.shape[1] == 256:  # fp32-grade mode: a = hi + lo
+            a = lib.tokens_to_channels((a_tok[:, :128].float() + a_tok[:, 128:].float()).contiguous(), a_batch, 128, L)
+        else:
+            a = lib.tokens_to_channels(a_tok, a_batch, 128, L)
         a._osd_tok = (a_tok, cond)  # fast path for _pred: skip the layout round trip
         cg = cond[: style.shape[0] * 512].view(style.shape[0], 512)
         return a, cg
@@ -231,6 +239,8 @@ class DiffusionModel(nn.Module):
     def forward(self, audio: Tensor, style: Tensor, xt: Tensor):
         """model.py:105-114."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if self.precision != 'bf16':
+                raise lib.OsdError("training runs in precision='bf16' (the fp32-grade path is inference-only)")
             from .autograd import denoiser_apply
             return denoiser_apply(self, audio, style, xt)
         a_tok, cond = self._conditioning_tokens(audio, style)

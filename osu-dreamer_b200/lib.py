@@ -18,7 +18,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'osd_b200.h')
 
 _lib = None
 
-BF16, TF32 = 0, 1
+BF16, TF32 = 0, 1   # operand element kinds of osd_gemm
+MODE_BF16, MODE_F32X3 = 0, 1  # model precision modes (include/osd_b200.h)
 MAJOR_K, MAJOR_MN = 0, 1
 EPI_STORE, EPI_SILU, EPI_ATOMIC = 0, 1, 2
 

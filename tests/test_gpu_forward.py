@@ -61,6 +61,37 @@ def test_forward_matches_reference_golden(golden_dir, oracle_sd, B, L, seed):
     assert eu < BF16_TOL and ev < BF16_TOL
 
 
+FP32_TOL = 1e-3
+
+
+@pytest.mark.parametrize('B,L,seed', [(2, 128, 7), (2, 320, 8), (1, 1000, 9)])
+def test_forward_fp32_grade_matches_reference_golden(golden_dir, oracle_sd, B, L, seed):
+    """precision='fp32' (3x bf16 split products): 1e-3 max-normalised vs the fp32 reference (north_star)."""
+    g = np.load(os.path.join(golden_dir, f'fwd_B{B}_L{L}.npz'))
+    inp = O.make_inputs(B, L, seed=seed)
+    xt = torch.lerp(inp['x0'], inp['x1'], inp['t'][:, None, None])
+    m = _model(oracle_sd)
+    m.precision = 'fp32'
+    with torch.no_grad():
+        u, v = m(inp['h'].cuda(), inp['s'].cuda(), xt.cuda())
+    torch.cuda.synchronize()
+    eu, ev = _maxnorm(u, g['u32']), _maxnorm(v, g['v32'])
+    print(f'fp32-grade B={B} L={L} u err {eu:.3e} v err {ev:.3e}; vs fp64 reference {_maxnorm(v, g["v64"]):.3e}')
+    assert eu < FP32_TOL and ev < FP32_TOL
+
+
+def test_sampler_fp32_grade_matches_reference_golden(golden_dir, oracle_sd):
+    g = np.load(os.path.join(golden_dir, 'sample_B2_L128_N8.npz'))
+    inp = O.make_inputs(2, 128, seed=31)
+    m = _model(oracle_sd)
+    m.precision = 'fp32'
+    x = m.sample_from(inp['h'].cuda(), inp['s'].cuda(), torch.from_numpy(g['x_init']).cuda(), 8)
+    torch.cuda.synchronize()
+    err = _maxnorm(x, g['x_final'])
+    print(f'fp32-grade 8-step sampler err {err:.3e}')
+    assert err < 2e-3  # 9 chained forwards
+
+
 def test_forward_broadcast_audio(golden_dir, oracle_sd):
     g = np.load(os.path.join(golden_dir, 'fwd_bcast_B3_L96.npz'))
     inp = O.make_inputs(3, 96, seed=10, a_batch=1)
