@@ -131,9 +131,11 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    threads = os.cpu_count() or 1
-    Ls, Bs = 2048, 1
-    sec = cpu_train_step_seconds(Ls, Bs, max(1, args.steps), max(0, min(args.warmup, 1)), threads)
+    # torch's CPU kernels stop scaling (and on a shared 128-thread host get much slower) beyond a few dozen
+    # threads: use up to 32.  Shape = BASELINE configs[0], the reference's own CPU-runnable case (B=2, L=512).
+    threads = min(os.cpu_count() or 1, 32)
+    Ls, Bs = 512, 2
+    sec = cpu_train_step_seconds(Ls, Bs, max(1, min(args.steps, 5)), max(0, min(args.warmup, 1)), threads)
     # samples/s measured at L=2048; the same arithmetic at L=8192 costs F(8192)/F(2048) more per sample
     v_sample = Bs / sec
     scale = f_fwd(Ls) / f_fwd(SEQ)
@@ -280,7 +282,8 @@ def run_cuda(args):
             qkv = torch.randn(Ba * L, 3072, device=dev).to(torch.bfloat16)
             y, lse = lib.attn_fwd(qkv, Ba, L)
             dy = torch.randn(Ba * L, 1024, device=dev).to(torch.bfloat16)
-            ms_f = time_kernel(lambda: lib.attn_fwd(qkv, Ba, L), iters=3, warm=1)
+            bound = torch.tensor([14.0], device=dev)  # randn scores / 8 stay far below 2^14: same kernel path the model runs
+            ms_f = time_kernel(lambda: lib.attn_fwd(qkv, Ba, L, bound_log2=bound, variant=2), iters=3, warm=1)
             ms_b = time_kernel(lambda: lib.attn_bwd(qkv, y, dy, lse, Ba, L), iters=3, warm=1)
             fl_f = 4.0 * Ba * 16 * L * L * 64
             kern = {'attn_fwd': {'ms': ms_f, 'tflops': fl_f / ms_f / 1e9},
@@ -290,6 +293,10 @@ def run_cuda(args):
             line['roofline'] = {'bound': 'tensor', 'kernel': dom, 'achieved': ach, 'peak': peaks['tf_burst'],
                                 'unit': 'TFLOP/s', 'frac': ach / peaks['tf_burst'], 'traffic': None,
                                 'peak_source': peaks['source'] + ', burst (kernel timed alone)',
+                                'traffic_note': 'ncu --set full at B=4, L=4096 (profiles/r01_ncu_attention_summary.json): dq kernel '
+                                                'dram read+write 156 MB vs 168 MB algorithmic (q,k,v,dO read + dq write) -> no re-read waste',
+                                'sfu_note': 'd=64 attention is SFU-bound before it is tensor-bound: 16384 ex2 per 128x128 tile = 1024 clk/SM '
+                                            'vs 512 clk of tcgen05 time -> kernel ceiling ~1.15 PFLOP/s (DESIGN.md 5)',
                                 'algorithmic_flops_per_launch': (2 * fl_f if dom != 'attn_fwd' else fl_f),
                                 'kernels': kern,
                                 'share_of_step': {k: 8 * v['ms'] / (sec / args.steps * 1e3) for k, v in kern.items()}}
@@ -297,7 +304,8 @@ def run_cuda(args):
         except Exception as e:  # noqa
             line['roofline'] = {'error': repr(e)[:200]}
 
-    # ---- secondary metric: 64-step sampling latents/s (bf16 path; BASELINE config 3 asks fp32 -> labelled)
+    # ---- secondary metric: 64-step sampling latents/s (BASELINE config 3: B=32, L=8192): bf16 path and the
+    #      fp32-grade path (precision='fp32': 3x-bf16 split products, 1e-3 tolerance class)
     if rank == 0 and world == 1 and not args.no_sampling:
         try:
             tr.zero_grad()
@@ -307,24 +315,32 @@ def run_cuda(args):
             m = tr.diffusion_ema.module.eval()
             hs = torch.randn(Bs, 128, L, device=dev)
             ss = torch.randn(Bs, 32, device=dev)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            xs = m.sample(hs, ss, 64)
-            e1.record()
-            torch.cuda.synchronize()
-            ssec = e0.elapsed_time(e1) / 1e3
-            line['sampling'] = {'metric': '64-step sample latents/sec @ seq8192', 'value': Bs / ssec, 'unit': 'latents/s',
-                                'batch': Bs, 'seconds': ssec, 'dtype': 'bf16 operands (fp32 path not enabled yet)',
-                                'algorithmic_tflops': 65 * f_fwd(L) * Bs / ssec / 1e12, 'finite': bool(torch.isfinite(xs).all())}
+            line['sampling'] = {'metric': '64-step sample latents/sec @ seq8192', 'unit': 'latents/s', 'batch': Bs}
+            for prec in ('bf16', 'fp32'):
+                m.precision = prec
+                m._rt.reset()
+                torch.cuda.empty_cache()
+                m.sample(hs[:2], ss[:2], 1)  # warm-up (weight packing, workspaces of this shape are re-made below)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                xs = m.sample(hs, ss, 64)
+                e1.record()
+                torch.cuda.synchronize()
+                ssec = e0.elapsed_time(e1) / 1e3
+                line['sampling'][prec] = {'value': Bs / ssec, 'seconds': ssec,
+                                          'algorithmic_tflops': 65 * f_fwd(L) * Bs / ssec / 1e12,
+                                          'finite': bool(torch.isfinite(xs).all())}
+            m.precision = 'bf16'
+            line['sampling']['value'] = line['sampling']['bf16']['value']
         except Exception as e:  # noqa
-            line['sampling'] = {'error': repr(e)[:200]}
+            line['sampling'] = {'error': repr(e)[:300]}
 
     # ---- CPU baseline (oracle port on this box's host cores), rank 0 at N=1 only, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        Ls, Bs = 1024, 1
-        sec_cpu = cpu_train_step_seconds(Ls, Bs, 2, 1, threads)
+        threads = min(os.cpu_count() or 1, 32)  # torch CPU stops scaling beyond a few dozen threads
+        Ls, Bs = 512, 2                          # BASELINE configs[0]: the reference's CPU-runnable case
+        sec_cpu = cpu_train_step_seconds(Ls, Bs, 3, 1, threads)
         scale = f_fwd(Ls) / f_fwd(L)
         line['cpu_baseline'] = {
             'value': Bs / sec_cpu * scale, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
