@@ -1,0 +1,297 @@
+// Flash attention forward, variant "db": two S accumulators in TMEM ping-pong, so the QK^T MMA of tile j+1 (and
+// j+2) runs while the softmax warps are still working on tile j -- the softmax never waits for the tensor pipe
+// and the SFU (the binding unit at head_dim 64) stays busy.  Profile that motivated it (ncu, variant 2):
+// 20 % of all warp samples sat on the s_full wait because the co-resident CTAs fall into lockstep.
+//   CTA = 128 q rows of one (b,h); 64-row kv tiles, 3-stage K/V ring; 2 CTAs/SM (192 of 256 TMEM columns)
+//   TMEM: S0 cols [0,64) | S1 [64,128) | O [128,192); bf16 P_j is written back over the first 32 columns of
+//         S_{j&1} and consumed from there as the A operand of O += P_j V_j; S_{j+2} is issued right after that MMA
+//         (in-order tensor pipe), so the aliasing is safe.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace osd {
+
+static constexpr int DB_THREADS = 192;
+static constexpr int DB_T128 = 128 * 128;
+static constexpr int DB_T64 = 64 * 128;
+static constexpr int DB_STAGES = 3;
+static constexpr int DB_SMEM_TILES = DB_T128 + 2 * DB_STAGES * DB_T64;
+static constexpr int DB_SMEM_BYTES = DB_SMEM_TILES + 256;
+static constexpr uint32_t DB_TMEM_COLS = 256;
+
+struct AttnDbParams {
+  CUtensorMap tma_q;   // dims (3*dh, L, B), box (64, 128, 1)
+  CUtensorMap tma_kv;  // box (64, 64, 1)
+  const float* bound_log2;
+  __nv_bfloat16* y;
+  float* lse;
+  int B, H, L, dh;
+  float scale_log2, scale;
+};
+
+__device__ __forceinline__ float db_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid_constant__ AttnDbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  {
+    uint32_t dyn;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if (pad + DB_SMEM_TILES + 160 > dyn) __trap();
+  }
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + DB_T128;
+  uint8_t* sV = sK + DB_STAGES * DB_T64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + DB_STAGES * DB_T64);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [3]
+  uint64_t* k_empty = bars + 4;   // [3]
+  uint64_t* v_full = bars + 7;    // [3]
+  uint64_t* v_empty = bars + 10;  // [3]
+  uint64_t* s_full = bars + 13;   // [2]
+  uint64_t* p_full = bars + 15;
+  uint64_t* o_ready = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_qt = (p.L + 127) / 128;
+  const int qt = blockIdx.x % n_qt;
+  const int bh = blockIdx.x / n_qt;
+  const int h = bh % p.H, b = bh / p.H;
+  const int q0 = qt * 128;
+  const int n_kv = (p.L + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < DB_STAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, DB_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, DB_T128);
+      tma_load_3d(sQ, &p.tma_q, q_full, h * 64, q0, b);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], DB_T64);
+        tma_load_3d(sK + st * DB_T64, &p.tma_kv, &k_full[st], p.dh + h * 64, j * 64, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], DB_T64);
+        tma_load_3d(sV + st * DB_T64, &p.tma_kv, &v_full[st], 2 * p.dh + h * 64, j * 64, b);
+        if (++st == DB_STAGES) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc_s = make_idesc(FMT_BF16, 0, 0, 128, 64);
+      const uint32_t idesc_o = make_idesc(FMT_BF16, 0, 1, 128, 64);
+      const uint32_t aQ = smem_u32(sQ);
+      const uint32_t tO = tmem_base + 128;
+      auto issue_s = [&](int j) {
+        const int st = j % DB_STAGES;
+        mbar_wait(&k_full[st], (j / DB_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sK + st * DB_T64);
+        const uint32_t tS = tmem_base + (j & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tS, make_smem_desc(aQ + k * 32, 0, 1024), make_smem_desc(aK + k * 32, 0, 1024), idesc_s, k > 0);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (n_kv > 1) issue_s(1);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % DB_STAGES;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[st], (j / DB_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t aV = smem_u32(sV + st * DB_T64);
+        const uint32_t tP = tmem_base + (j & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ts(tO, tP + k * 8, make_smem_desc(aV + k * 16 * 128, 0, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&v_empty[st]);
+        umma_commit(o_ready);
+        if (j + 2 < n_kv) issue_s(j + 2);  // reuses S_{j&1}: issued after the MMA that read P_j from it
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tO = tmem_base + 128 + lane_off;
+    const float c = p.scale_log2;
+    float bound = INFINITY;
+    if (p.bound_log2 != nullptr) bound = __ldg(p.bound_log2);
+    const bool fixed = bound < 3.0e38f;
+    float m = fixed ? bound / c : -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t tS = tmem_base + (j & 1) * 64 + lane_off;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const int valid = p.L - j * 64;
+      uint32_t r0[32], r1[32];
+      __syncwarp();
+      tmem_ld32(tS, r0);
+      tmem_ld32(tS + 32, r1);
+      tmem_wait_ld();
+      float m_new = m, alpha = 1.0f;
+      if (!fixed) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < valid) mx = fmaxf(mx, __uint_as_float(r0[i]));
+          if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(r1[i]));
+        }
+        m_new = fmaxf(m, mx);
+        alpha = db_ex2((m - m_new) * c);
+      }
+      const float neg_mc = -m_new * c;
+      const float2 c2 = make_float2(c, c), n2 = make_float2(neg_mc, neg_mc);
+      uint32_t pk[32];
+      float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+      if (valid >= 64) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 a = ffma2(make_float2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])), c2, n2);
+          const float2 bb = ffma2(make_float2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])), c2, n2);
+          const float2 ea = make_float2(db_ex2(a.x), db_ex2(a.y));
+          const float2 eb = make_float2(db_ex2(bb.x), db_ex2(bb.y));
+          s01 = fadd2(s01, ea);
+          s23 = fadd2(s23, eb);
+          pk[i >> 1] = pack_bf16(ea.x, ea.y);
+          pk[16 + (i >> 1)] = pack_bf16(eb.x, eb.y);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float a0 = (i < valid) ? db_ex2(fmaf(__uint_as_float(r0[i]), c, neg_mc)) : 0.f;
+          const float a1 = (i + 1 < valid) ? db_ex2(fmaf(__uint_as_float(r0[i + 1]), c, neg_mc)) : 0.f;
+          const float b0 = (32 + i < valid) ? db_ex2(fmaf(__uint_as_float(r1[i]), c, neg_mc)) : 0.f;
+          const float b1 = (33 + i < valid) ? db_ex2(fmaf(__uint_as_float(r1[i + 1]), c, neg_mc)) : 0.f;
+          s01 = fadd2(s01, make_float2(a0, a1));
+          s23 = fadd2(s23, make_float2(b0, b1));
+          pk[i >> 1] = pack_bf16(a0, a1);
+          pk[16 + (i >> 1)] = pack_bf16(b0, b1);
+        }
+      }
+      const float sum = (s01.x + s01.y) + (s23.x + s23.y);
+      // O_{j-1} must be complete before (a) it is rescaled (online mode) and (b) this warp runs further ahead of the
+      // o_ready phase counter; by now that MMA has long retired, so this wait is free in steady state.
+      if (j > 0) {
+        mbar_wait(o_ready, (j - 1) & 1);
+        tc_fence_after();
+        if (!fixed && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+          for (int cch = 0; cch < 2; ++cch) {
+            uint32_t ro[32];
+            __syncwarp();
+            tmem_ld32(tO + cch * 32, ro);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+            tmem_st32(tO + cch * 32, ro);
+          }
+          tmem_wait_st();
+        }
+      }
+      __syncwarp();
+      tmem_st32(tS, pk);  // P_j (64 bf16 = 32 columns) over the consumed S_j
+      tmem_wait_st();
+      l = l * alpha + sum;
+      m = m_new;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    mbar_wait(o_ready, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int q = q0 + row;
+    const bool ok = q < p.L;
+#pragma unroll 1
+    for (int cch = 0; cch < 2; ++cch) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(tO + cch * 32, r);
+      tmem_wait_ld();
+      if (ok) {
+        uint4* dst = reinterpret_cast<uint4*>(p.y + ((size_t)b * p.L + q) * p.dh + h * 64 + cch * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          dst[i] = make_uint4(pack_bf16(__uint_as_float(r[8 * i]) * inv_l, __uint_as_float(r[8 * i + 1]) * inv_l),
+                              pack_bf16(__uint_as_float(r[8 * i + 2]) * inv_l, __uint_as_float(r[8 * i + 3]) * inv_l),
+                              pack_bf16(__uint_as_float(r[8 * i + 4]) * inv_l, __uint_as_float(r[8 * i + 5]) * inv_l),
+                              pack_bf16(__uint_as_float(r[8 * i + 6]) * inv_l, __uint_as_float(r[8 * i + 7]) * inv_l));
+      }
+    }
+    if (ok && p.lse != nullptr) p.lse[((size_t)b * p.H + h) * p.L + q] = m * p.scale + __logf(l);
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, DB_TMEM_COLS);
+  }
+}
+
+int launch_attn_fwd_db(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                       cudaStream_t stream) {
+  OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd_db: bad arguments");
+  AttnDbParams p;
+  const int dh = H * 64;
+  uint64_t dims[3] = {(uint64_t)3 * dh, (uint64_t)L, (uint64_t)B};
+  uint64_t strides[2] = {(uint64_t)3 * dh * 2, (uint64_t)L * 3 * dh * 2};
+  uint32_t box_q[3] = {64, 128, 1}, box_kv[3] = {64, 64, 1};
+  OSD_TRY(make_tmap(&p.tma_q, qkv, 2, 3, dims, strides, box_q));
+  OSD_TRY(make_tmap(&p.tma_kv, qkv, 2, 3, dims, strides, box_kv));
+  p.bound_log2 = bound_log2;
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.lse = lse;
+  p.B = B; p.H = H; p.L = L; p.dh = dh;
+  p.scale = 0.125f;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long grid = (long long)ceil_div(L, 128) * H * B;
+  OSD_CHECK(grid < (1ll << 31), "attn_fwd_db: grid too large");
+  attn_fwd_db_kernel<<<(unsigned)grid, DB_THREADS, DB_SMEM_BYTES, stream>>>(p);
+  OSD_LAUNCHED();
+  return 0;
+}
+
+}  // namespace osd

@@ -73,6 +73,8 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
                     int L, int H, cudaStream_t stream);
 int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int variant,
                     cudaStream_t stream);
+int launch_attn_fwd_db(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                       cudaStream_t stream);
 int launch_attn_fwd_x3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                        cudaStream_t stream);
 int launch_qk_bound(const float* qw, const float* kw, float* out, cudaStream_t stream);

@@ -200,7 +200,7 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
     if (X)
       OSD_TRY(launch_attn_fwd_x3(lb + pl.qkv, lb + pl.y, nullptr, c.W.bound(l), B, L, 16, s));
     else
-      OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), c.W.bound(l), B, L, 16, 2,
+      OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), c.W.bound(l), B, L, 16, 4,
                               s));
     GemmArgs o;
     o.A = lb + pl.y; o.B = c.W.out(l); o.lda = 1024 * km; o.ldb = 1024 * km; o.M = T; o.N = 512; o.K = 1024;
