@@ -137,6 +137,11 @@ OSD_API int osd_sample(const float* const* params, const void* packed, int mode,
 OSD_API int osd_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, void* dqkv,
                          int B, int L, int H, void* stream);
 
+/* Same gradient in one pass (five GEMMs, one exponential per score): dq is accumulated in fp32 through TMA
+ * reduce-add into dq_acc [B*L, H*64] (scratch, zeroed by the call) and converted to bf16 into dqkv. */
+OSD_API int osd_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum,
+                               float* dq_acc, void* dqkv, int B, int L, int H, void* stream);
+
 /* Gradient of DiffusionModel.forward (what autograd computes for the reference at train.py:84 + Lightning's
  * backward): given du [B] and dv [B,6,L], ACCUMULATES the parameter gradients into grads[164] (HOST array of
  * DEVICE fp32 pointers, parameter shapes).  `workspace` is the save=1 workspace the forward filled;

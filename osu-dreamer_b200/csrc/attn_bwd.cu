@@ -572,6 +572,13 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ y, const 
   }
 }
 
+int launch_attn_bwd_prep(const void* y, const void* dy, float* dsum, int B, int L, int H, cudaStream_t stream) {
+  attn_bwd_prep_kernel<<<ceil_div(B * L, 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(y),
+                                                               static_cast<const __nv_bfloat16*>(dy), dsum, B, H, L);
+  OSD_LAUNCHED();
+  return 0;
+}
+
 int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, void* dqkv, int B,
                     int L, int H, cudaStream_t stream) {
   OSD_CHECK(qkv && y && dy && lse && dsum && dqkv && B > 0 && L > 0 && H == 16, "attn_bwd: bad arguments");

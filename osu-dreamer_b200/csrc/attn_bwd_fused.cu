@@ -1,0 +1,451 @@
+// Single-pass flash attention backward on tcgen05 (head_dim 64, bf16 operands, fp32 accumulation in TMEM).
+// Gradient of F.scaled_dot_product_attention (osu_dreamer/common/attn.py:82):
+//   P = exp(S*scale - lse),  dP = dO V^T,  dS = P o (dP - D) * scale,  D = rowsum(dO o O)
+//   dV = P^T dO,  dK = dS^T Q,  dQ = dS K
+// One kernel, five GEMMs and ONE exponential per score element (the two-kernel path in attn_bwd.cu recomputes S
+// and P in both kernels: seven GEMMs, two exponentials).  CTA = one 128-row kv tile of one (batch, head); it
+// loops over all 128-row q tiles, keeps dK / dV in TMEM, and adds its [128 x 64] fp32 partial of dQ into a
+// global fp32 accumulator with TMA reduce-add (cp.reduce.async.bulk.tensor ... .add), as many flash-attention
+// backward kernels do.  Each CTA starts its q loop at a different tile so that the 64 CTAs of one (b, h) do not
+// hit the same dQ rows at the same time.
+//
+//   warps    : 0 TMA producer | 1 TMEM allocator + UMMA issuer | 2-9 softmax (2 column groups x 4 lane quadrants,
+//              thread = kv row); between the two softmax phases of tile i the same warps drain dQ_{i-1}
+//              (TMEM -> swizzled smem -> TMA reduce-add; warp = 32 q rows x 32 d columns).  10 warps keep the
+//              register file at <= 3 warps per SM sub-partition (200 registers per thread available).
+//   TMEM     : S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | dQ_i [384,448) | K bf16 [448,480) |
+//              V bf16 [480,512).  K and V are the A operands of S^T = K Q_i^T and dP^T = V dO_i^T straight from TMEM;
+//              the bf16 P^T / dS^T tiles are written back over the consumed S^T / dP^T columns (column group g at
+//              +64g) and are the TMEM A operands of dV += P^T dO_i and dK += dS^T Q_i.
+//   smem     : K | V (staging for the TMEM copy; K also B operand of dQ) | Q_i x2 | dO_i x2 | dS^T (bf16, MN-major
+//              A operand of dQ_i = dS_i K) | dQ staging | lse/D staging | barriers
+//   pipeline : S^T_0 | dP^T_0 | { dV_i | S^T_{i+1} | dK_i | dP^T_{i+1} | dQ_i } -- the in-order tensor pipe makes the
+//              TMEM aliasing safe with exactly this issue order.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace osd {
+
+static constexpr int FB_THREADS = 320;
+static constexpr int FT = 128 * 128;  // bytes of a [128 x 64] bf16 tile
+static constexpr uint32_t FB_TMEM_COLS = 512;
+static constexpr int FB_STAT_BYTES = 2 * 256 * 4;
+static constexpr int FB_STG_BYTES = 8 * 4096;  // 8 softmax warps x [32 rows x 128 B]
+static constexpr int FB_SMEM_TILES = 8 * FT + FB_STG_BYTES + FB_STAT_BYTES;
+static constexpr int FB_SMEM_BYTES = FB_SMEM_TILES + 256 + 1024;
+
+__device__ __forceinline__ float fb_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void fb_named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct AttnBwdFusedParams {
+  CUtensorMap tma_qkv;  // qkv    dims (3*dh, L, B), box (64, 128, 1)
+  CUtensorMap tma_dy;   // dy     dims (dh, L, B),   box (64, 128, 1)
+  CUtensorMap tma_dq;   // dq_acc dims (dh, L, B) fp32, box (32, 32, 1)
+  const float* lse;     // [B, H, L]
+  const float* dsum;    // [B, H, L]  D = rowsum(dO o O)
+  __nv_bfloat16* dqkv;  // [B*L, 3*dh]: this kernel writes the dk and dv column blocks
+  int B, H, L, dh;
+  float scale, scale_log2;
+};
+
+__global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __grid_constant__ AttnBwdFusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  {
+    uint32_t dyn;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if (pad + FB_SMEM_TILES + 256 > dyn) __trap();
+  }
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + FT;
+  uint8_t* sQ = sV + FT;        // 2 stages [128 x 64]
+  uint8_t* sDO = sQ + 2 * FT;   // 2 stages
+  uint8_t* sDS = sDO + 2 * FT;  // [2 q-chunks][128 kv rows][64 q] bf16
+  uint8_t* sStg = sDS + 2 * FT;
+  float* sStat = reinterpret_cast<float*>(sStg + FB_STG_BYTES);  // [2 buf][-lse2 128 | -D 128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + FB_STG_BYTES + FB_STAT_BYTES);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;    // [2]
+  uint64_t* q_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;    // S^T_i complete
+  uint64_t* dp_full = bars + 6;   // dP^T_i complete
+  uint64_t* pt_full = bars + 7;   // P^T_i written (TMEM)
+  uint64_t* ds_full = bars + 8;   // dS^T_i written (TMEM + smem)
+  uint64_t* dq_full = bars + 9;   // dQ_i complete (also: dS^T smem tile consumed)
+  uint64_t* dq_empty = bars + 10; // dQ_i drained out of TMEM
+  uint64_t* kvt_ready = bars + 11;  // K / V copied into TMEM
+  uint64_t* acc_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_t = (p.L + 127) / 128;  // kv tiles == q tiles
+  const int kt = blockIdx.x % n_t;
+  const int bh = blockIdx.x / n_t;
+  const int h = bh % p.H, b = bh / p.H;
+  const int kv0 = kt * 128;
+  const int n_q = n_t;
+  const int i0 = kt;  // q-loop rotation: iteration i works on q tile (i0 + i) % n_q
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_qkv);
+    tma_prefetch_desc(&p.tma_dy);
+    tma_prefetch_desc(&p.tma_dq);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(pt_full, 8);
+    mbar_init(ds_full, 8);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 8);
+    mbar_init(kvt_ready, 8);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, FB_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (elect_one()) {
+      mbar_expect_tx(kv_full, 2 * FT);
+      tma_load_3d(sK, &p.tma_qkv, kv_full, p.dh + h * 64, kv0, b);
+      tma_load_3d(sV, &p.tma_qkv, kv_full, 2 * p.dh + h * 64, kv0, b);
+      int qi = i0;
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i & 1;
+        mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[st], 2 * FT);
+        tma_load_3d(sQ + st * FT, &p.tma_qkv, &q_full[st], h * 64, qi * 128, b);
+        tma_load_3d(sDO + st * FT, &p.tma_dy, &q_full[st], h * 64, qi * 128, b);
+        if (++qi == n_q) qi = 0;
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== UMMA issuer
+    if (elect_one()) {
+      const uint32_t id_s = make_idesc(FMT_BF16, 0, 0, 128, 128);  // S^T, dP^T: A in TMEM, B K-major, N = 128 q
+      const uint32_t id_o = make_idesc(FMT_BF16, 0, 1, 128, 64);   // dV, dK  : A in TMEM, B MN-major, N = 64 d
+      const uint32_t id_q = make_idesc(FMT_BF16, 1, 1, 128, 64);   // dQ      : A = dS MN-major smem, B = K MN-major
+      const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320;
+      const uint32_t tDQ = tmem_base + 384, tK = tmem_base + 448, tV = tmem_base + 480;
+      const uint32_t aK = smem_u32(sK), aDS = smem_u32(sDS);
+      auto issue_s = [&](int i) {
+        const int st = i & 1;
+        mbar_wait(&q_full[st], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ + st * FT);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ts(tS, tK + k * 8, make_smem_desc(aQ + k * 32, 0, 1024), id_s, k > 0);
+        umma_commit(s_full);
+      };
+      auto issue_dp = [&](int i) {
+        const uint32_t aDO = smem_u32(sDO + (i & 1) * FT);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ts(tDP, tV + k * 8, make_smem_desc(aDO + k * 32, 0, 1024), id_s, k > 0);
+        umma_commit(dp_full);
+      };
+      mbar_wait(kvt_ready, 0);
+      tc_fence_after();
+      issue_s(0);
+      issue_dp(0);
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i & 1;
+        const uint32_t aQ = smem_u32(sQ + st * FT), aDO = smem_u32(sDO + st * FT);
+        const uint32_t acc = i > 0 ? 1u : 0u;
+        mbar_wait(pt_full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV += P^T_i dO_i : q (K dim) chunk k lives at columns (k/4)*64 + (k%4)*8
+          umma_f16_ts(tDV, tS + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc(aDO + k * 16 * 128, 0, 1024), id_o,
+                      (k > 0) ? 1u : acc);
+        if (i + 1 < n_q) issue_s(i + 1);  // overwrites P^T_i only after dV_i has read it
+        mbar_wait(ds_full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16_ts(tDK, tDP + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc(aQ + k * 16 * 128, 0, 1024), id_o,
+                      (k > 0) ? 1u : acc);
+        umma_commit(&q_empty[st]);
+        if (i + 1 < n_q) issue_dp(i + 1);  // overwrites dS^T_i (TMEM) only after dK_i has read it
+        if (i > 0) {
+          mbar_wait(dq_empty, (i - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ_i = dS_i K : contraction over the 128 kv rows, 16 per instruction
+          umma_f16_ss(tDQ, make_smem_desc(aDS + k * 16 * 128, FT, 1024), make_smem_desc(aK + k * 16 * 128, 0, 1024), id_q,
+                      k > 0);
+        umma_commit(dq_full);
+      }
+      umma_commit(acc_done);
+    }
+  } else {
+    // ================================================================== softmax (thread = kv row, 64 q columns)
+    const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;   // q-column group: columns [64 grp, 64 grp + 64)
+    const int row = quad * 32 + lane;  // kv row
+    const int tid = threadIdx.x - 64;  // 0..255
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    {  // one-time copy of this thread's K (grp 0) or V (grp 1) row (128 B, SW128 smem) into TMEM
+      mbar_wait(kv_full, 0);
+      const uint32_t base = smem_u32(grp == 0 ? sK : sV) + row * 128;
+      uint32_t r[32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[4 * u]), "=r"(r[4 * u + 1]), "=r"(r[4 * u + 2]), "=r"(r[4 * u + 3])
+                     : "r"(base + ((u ^ (row & 7)) << 4)));
+      __syncwarp();
+      tmem_st32(tmem_base + 448 + grp * 32 + lane_off, r);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(kvt_ready);
+    }
+    const uint32_t tS = tmem_base + lane_off + grp * 64, tDP = tmem_base + 128 + lane_off + grp * 64;
+    const uint32_t ds_row = smem_u32(sDS) + grp * FT + row * 128;
+    const int sw = row & 7;
+    const float c = p.scale_log2;
+    const size_t sbase = ((size_t)b * p.H + h) * p.L;
+    // -lse2 / -D of a q tile are staged in smem (double-buffered); q rows past L: -lse2 = -inf -> P = 0
+    auto load_stat = [&](int qt) -> float {
+      const int qi = qt * 128 + (tid & 127);
+      const bool okq = qi < p.L;
+      if (tid < 128) return okq ? -p.lse[sbase + qi] * 1.4426950408889634f : -INFINITY;
+      return okq ? -p.dsum[sbase + qi] : 0.f;
+    };
+    // dQ drain: this warp moves rows [32 quad, +32) x columns [32 grp, +32) of the finished dQ tile j (q tile qj)
+    const uint32_t tDQ = tmem_base + 384 + lane_off + grp * 32;
+    uint8_t* stg = sStg + (warp - 2) * 4096;
+    const uint32_t stg_row = smem_u32(stg) + lane * 128;
+    auto drain_dq = [&](int j, int qj) {
+      mbar_wait(dq_full, j & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(tDQ, r);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(dq_empty);
+        tma_store_wait_read<0>();  // the previous reduce-add of this warp has read the staging tile
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((u ^ (lane & 7)) << 4)),
+                     "r"(__float_as_uint(__uint_as_float(r[4 * u]) * p.scale)),
+                     "r"(__float_as_uint(__uint_as_float(r[4 * u + 1]) * p.scale)),
+                     "r"(__float_as_uint(__uint_as_float(r[4 * u + 2]) * p.scale)),
+                     "r"(__float_as_uint(__uint_as_float(r[4 * u + 3]) * p.scale))
+                     : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_3d(&p.tma_dq, stg, h * 64 + grp * 32, qj * 128 + quad * 32, b);
+        tma_store_commit();
+      }
+    };
+    int qt = i0, qprev = i0;
+    sStat[tid] = load_stat(qt);
+    fb_named_bar(1, 256);
+    for (int i = 0; i < n_q; ++i) {
+      const float* st = sStat + (i & 1) * 256 + grp * 64;
+      int qn = qt + 1;
+      if (qn == n_q) qn = 0;
+      float next_stat = 0.f;
+      if (i + 1 < n_q) next_stat = load_stat(qn);
+      // ---- phase 1: P^T = exp2(S^T * c - lse2[q])
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      float pt[64];
+#pragma unroll
+      for (int cch = 0; cch < 2; ++cch) {
+        uint32_t rs[32];
+        __syncwarp();
+        tmem_ld32(tS + cch * 32, rs);
+        tmem_wait_ld();
+        const float4* l4 = reinterpret_cast<const float4*>(st + cch * 32);  // broadcast LDS.128
+        const float2 c2 = make_float2(c, c);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 lv = l4[k4];
+          const float2 a = ffma2(make_float2(__uint_as_float(rs[k4 * 4 + 0]), __uint_as_float(rs[k4 * 4 + 1])), c2,
+                                 make_float2(lv.x, lv.y));
+          const float2 bb = ffma2(make_float2(__uint_as_float(rs[k4 * 4 + 2]), __uint_as_float(rs[k4 * 4 + 3])), c2,
+                                  make_float2(lv.z, lv.w));
+          pt[cch * 32 + k4 * 4 + 0] = fb_ex2(a.x);
+          pt[cch * 32 + k4 * 4 + 1] = fb_ex2(a.y);
+          pt[cch * 32 + k4 * 4 + 2] = fb_ex2(bb.x);
+          pt[cch * 32 + k4 * 4 + 3] = fb_ex2(bb.y);
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(pt[cch * 32 + 2 * k], pt[cch * 32 + 2 * k + 1]);
+        tmem_st16(tS + cch * 16, pk);  // over S^T columns this thread has already consumed
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pt_full);
+      // ---- phase 2: dS^T = P^T o (dP^T - D[q])   (1/sqrt(d) is applied to the dK / dQ accumulators on the way out)
+      if (i > 0) drain_dq(i - 1, qprev);  // also: dQ_{i-1} has consumed the dS^T smem tile
+      mbar_wait(dp_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cch = 0; cch < 2; ++cch) {
+        uint32_t rp[32];
+        __syncwarp();
+        tmem_ld32(tDP + cch * 32, rp);
+        tmem_wait_ld();
+        const float4* d4 = reinterpret_cast<const float4*>(st + 128 + cch * 32);
+        uint32_t pk[16];
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 dv = d4[k4];  // -D of 4 consecutive q columns
+          const float2 e0 = fmul2(make_float2(pt[cch * 32 + k4 * 4 + 0], pt[cch * 32 + k4 * 4 + 1]),
+                                  fadd2(make_float2(__uint_as_float(rp[k4 * 4 + 0]), __uint_as_float(rp[k4 * 4 + 1])),
+                                        make_float2(dv.x, dv.y)));
+          const float2 e1 = fmul2(make_float2(pt[cch * 32 + k4 * 4 + 2], pt[cch * 32 + k4 * 4 + 3]),
+                                  fadd2(make_float2(__uint_as_float(rp[k4 * 4 + 2]), __uint_as_float(rp[k4 * 4 + 3])),
+                                        make_float2(dv.z, dv.w)));
+          pk[k4 * 2] = pack_bf16(e0.x, e0.y);
+          pk[k4 * 2 + 1] = pack_bf16(e1.x, e1.y);
+        }
+        tmem_st16(tDP + cch * 16, pk);  // TMEM copy: A operand of dK += dS^T Q_i
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4)  // smem copy (row = kv, 64 q contiguous): MN-major A operand of dQ_i = dS_i K
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + (((cch * 4 + u4) ^ sw) << 4)),
+                       "r"(pk[4 * u4]), "r"(pk[4 * u4 + 1]), "r"(pk[4 * u4 + 2]), "r"(pk[4 * u4 + 3])
+                       : "memory");
+      }
+      tmem_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+      if (i + 1 < n_q) {
+        sStat[((i + 1) & 1) * 256 + tid] = next_stat;  // buffer (i+1)&1 was last read during tile i-1
+        fb_named_bar(1, 256);
+      }
+      qprev = qt;
+      qt = qn;
+    }
+    drain_dq(n_q - 1, qprev);
+    // ---- epilogue: group 0 writes dK (x scale), group 1 writes dV
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    const int kv = kv0 + row;
+    const bool ok = kv < p.L;
+    const uint32_t tACC = tmem_base + (grp == 0 ? 320 : 256) + lane_off;
+    const float mul = grp == 0 ? p.scale : 1.0f;
+#pragma unroll 1
+    for (int cch = 0; cch < 2; ++cch) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(tACC + cch * 32, r);
+      tmem_wait_ld();
+      if (ok) {
+        uint4* dst = reinterpret_cast<uint4*>(p.dqkv + ((size_t)b * p.L + kv) * (3 * p.dh) + (grp == 0 ? 1 : 2) * p.dh +
+                                              h * 64 + cch * 32);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          dst[k] = make_uint4(pack_bf16(__uint_as_float(r[8 * k]) * mul, __uint_as_float(r[8 * k + 1]) * mul),
+                              pack_bf16(__uint_as_float(r[8 * k + 2]) * mul, __uint_as_float(r[8 * k + 3]) * mul),
+                              pack_bf16(__uint_as_float(r[8 * k + 4]) * mul, __uint_as_float(r[8 * k + 5]) * mul),
+                              pack_bf16(__uint_as_float(r[8 * k + 6]) * mul, __uint_as_float(r[8 * k + 7]) * mul));
+      }
+    }
+    tc_fence_before();
+    if (lane == 0) tma_store_wait<0>();
+    __syncwarp();
+  }
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, FB_TMEM_COLS);
+  }
+}
+
+// dq_acc fp32 [T, dh] -> bf16 dq column block of dqkv [T, 3*dh]
+__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, size_t n8,
+                                           int dh) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const size_t e = i * 8;
+  const size_t t = e / dh, c = e % dh;
+  const float4 a = reinterpret_cast<const float4*>(acc + e)[0];
+  const float4 bb = reinterpret_cast<const float4*>(acc + e)[1];
+  *reinterpret_cast<uint4*>(dqkv + t * (3 * (size_t)dh) + c) =
+      make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(bb.x, bb.y), pack_bf16(bb.z, bb.w));
+}
+
+int launch_attn_bwd_prep(const void* y, const void* dy, float* dsum, int B, int L, int H, cudaStream_t stream);
+
+int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, float* dq_acc,
+                          void* dqkv, int B, int L, int H, cudaStream_t stream) {
+  OSD_CHECK(qkv && y && dy && lse && dsum && dq_acc && dqkv && B > 0 && L > 0 && H == 16, "attn_bwd_fused: bad arguments");
+  const int dh = H * 64;
+  OSD_TRY(launch_attn_bwd_prep(y, dy, dsum, B, L, H, stream));
+  OSD_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * L * dh * sizeof(float), stream));
+  AttnBwdFusedParams p;
+  {
+    uint64_t dims[3] = {(uint64_t)3 * dh, (uint64_t)L, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)3 * dh * 2, (uint64_t)L * 3 * dh * 2};
+    uint32_t box[3] = {64, 128, 1};
+    OSD_TRY(make_tmap(&p.tma_qkv, qkv, 2, 3, dims, strides, box));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)dh, (uint64_t)L, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)dh * 2, (uint64_t)L * dh * 2};
+    uint32_t box[3] = {64, 128, 1};
+    OSD_TRY(make_tmap(&p.tma_dy, dy, 2, 3, dims, strides, box));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)dh, (uint64_t)L, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)dh * 4, (uint64_t)L * dh * 4};
+    uint32_t box[3] = {32, 32, 1};
+    OSD_TRY(make_tmap(&p.tma_dq, dq_acc, 4, 3, dims, strides, box));
+  }
+  p.lse = lse;
+  p.dsum = dsum;
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.B = B; p.H = H; p.L = L; p.dh = dh;
+  p.scale = 0.125f;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OSD_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long grid = (long long)ceil_div(L, 128) * H * B;
+  OSD_CHECK(grid < (1ll << 31), "attn_bwd_fused: grid too large");
+  attn_bwd_fused_kernel<<<(unsigned)grid, FB_THREADS, FB_SMEM_BYTES, stream>>>(p);
+  OSD_LAUNCHED();
+  const size_t n8 = (size_t)B * L * dh / 8;
+  attn_bwd_dq_convert_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(dq_acc, p.dqkv, n8, dh);
+  OSD_LAUNCHED();
+  return 0;
+}
+
+}  // namespace osd

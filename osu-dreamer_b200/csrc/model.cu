@@ -6,6 +6,8 @@
 #include "kernels.cuh"
 
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace osd {
 
@@ -238,7 +240,7 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
 
 // ================================================================================================ backward
 struct BwdPlan {
-  size_t dx, dh, dhn, dvg, dz2, dy, dqkv, dz, dsum, da_tok, a_pre, da_pre, audio_tm, dcond, dfsum, dpre_s;
+  size_t dx, dh, dhn, dvg, dz2, dy, dqkv, dq_acc, dz, dsum, da_tok, a_pre, da_pre, audio_tm, dcond, dfsum, dpre_s;
   size_t gWvg, gWpo, gbvg;  // padded fp32 gradient scratch
   size_t total;
 };
@@ -258,6 +260,7 @@ static BwdPlan make_bwd_plan(int B, int L, int a_batch) {
   p.dz2 = take(T * 512 * 2);
   p.dy = take(T * 1024 * 2);
   p.dqkv = take(T * 3072 * 2);
+  p.dq_acc = take(T * 1024 * 4);  // fp32 dQ accumulator of the single-pass attention backward
   p.dz = take(T * 512 * 2);
   p.dsum = take(T * 16 * 4);
   p.da_tok = take(Ta * 128 * 4);
@@ -272,6 +275,15 @@ static BwdPlan make_bwd_plan(int B, int L, int a_batch) {
   p.gbvg = take((size_t)2 * OSD_HIDP * 4);
   p.total = o;
   return p;
+}
+
+// OSD_ATTN_BWD=2pass selects the two-kernel attention backward (attn_bwd.cu) for A/B measurements
+static bool attn_bwd_two_pass() {
+  static const bool v = [] {
+    const char* e = getenv("OSD_ATTN_BWD");
+    return e != nullptr && strcmp(e, "2pass") == 0;
+  }();
+  return v;
 }
 
 static int split_for(int M, int N, int K, int bn) {
@@ -363,8 +375,13 @@ static int pred_backward(const FwdCtx& c, const float* audio, const float* style
                                      G[lp(l, L_OUT_B)], B, L, s));
     OSD_TRY(gemm_dgrad(dh, 512, c.W.out(l), 1024, bw + bp.dy, 1024, 0, 0, T, 1024, 512, s));
     OSD_TRY(gemm_wgrad(dh, 512, lb + pl.y, 1024, G[lp(l, L_OUT_W)], 1024, 512, 1024, T, s));
-    OSD_TRY(launch_attn_bwd(lb + pl.qkv, lb + pl.y, bw + bp.dy, reinterpret_cast<float*>(lb + pl.lse),
-                            reinterpret_cast<float*>(bw + bp.dsum), bw + bp.dqkv, B, L, 16, s));
+    if (attn_bwd_two_pass())
+      OSD_TRY(launch_attn_bwd(lb + pl.qkv, lb + pl.y, bw + bp.dy, reinterpret_cast<float*>(lb + pl.lse),
+                              reinterpret_cast<float*>(bw + bp.dsum), bw + bp.dqkv, B, L, 16, s));
+    else
+      OSD_TRY(launch_attn_bwd_fused(lb + pl.qkv, lb + pl.y, bw + bp.dy, reinterpret_cast<float*>(lb + pl.lse),
+                                    reinterpret_cast<float*>(bw + bp.dsum), reinterpret_cast<float*>(bw + bp.dq_acc),
+                                    bw + bp.dqkv, B, L, 16, s));
     OSD_TRY(launch_qknorm_rope_bwd(bw + bp.dqkv, lb + pl.qkv_raw, c.rope, c.P[lp(l, L_QN_W)], c.P[lp(l, L_KN_W)],
                                    G[lp(l, L_QN_W)], G[lp(l, L_KN_W)], G[lp(l, L_QKV_B)], B, L, s));
     OSD_TRY(gemm_dgrad(bw + bp.dqkv, 3072, c.W.qkv(l), 512, bw + bp.dz, 512, 0, 0, T, 512, 3072, s));
@@ -532,6 +549,11 @@ int osd_pred_backward(const float* const* params, const void* packed, int mode, 
 int osd_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, void* dqkv, int B, int L,
                  int H, void* stream) {
   return launch_attn_bwd(qkv, y, dy, lse, dsum, dqkv, B, L, H, static_cast<cudaStream_t>(stream));
+}
+
+int osd_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, float* dq_acc,
+                       void* dqkv, int B, int L, int H, void* stream) {
+  return launch_attn_bwd_fused(qkv, y, dy, lse, dsum, dq_acc, dqkv, B, L, H, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

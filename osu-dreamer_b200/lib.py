@@ -214,6 +214,15 @@ def attn_bwd(qkv, y, dy, lse, B, L, H=16):
     return dqkv
 
 
+def attn_bwd_fused(qkv, y, dy, lse, B, L, H=16):
+    dqkv = torch.empty_like(qkv)
+    dsum = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device)
+    dq_acc = torch.empty(B * L, H * 64, dtype=torch.float32, device=qkv.device)
+    _check(load().osd_attn_bwd_fused(ptr(qkv), ptr(y), ptr(dy), ptr(lse), ptr(dsum), ptr(dq_acc), ptr(dqkv), c_int(B),
+                                     c_int(L), c_int(H), stream()))
+    return dqkv
+
+
 def adamw_ema_step(p, g, m, v, ema, step, lr, beta1, beta2, eps, wd, max_norm, grad_scale, ema_decay, ema_copy, acc,
                    scal):
     _check(load().osd_adamw_ema_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), c_size_t(p.numel()), c_int(step),

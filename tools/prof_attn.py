@@ -8,7 +8,7 @@ qkv = torch.randn(B * L, 3072, device='cuda').to(torch.bfloat16)
 dy = torch.randn(B * L, 1024, device='cuda').to(torch.bfloat16)
 bound = torch.tensor([14.0], device='cuda')
 for _ in range(2):
-    y, lse = lib.attn_fwd(qkv, B, L, bound_log2=bound, variant=2)
+    y, lse = lib.attn_fwd(qkv, B, L, bound_log2=bound, variant=4)
     dqkv = lib.attn_bwd(qkv, y, dy, lse, B, L)
 torch.cuda.synchronize()
 print('done')
