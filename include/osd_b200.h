@@ -138,8 +138,10 @@ OSD_API int osd_attn_bwd(const void* qkv, const void* y, const void* dy, const f
                          int B, int L, int H, void* stream);
 
 /* Same gradient in one pass (five GEMMs, one exponential per score): dq is accumulated in fp32 through TMA
- * reduce-add into dq_acc [B*L, H*64] (scratch, zeroed by the call) and converted to bf16 into dqkv. */
-OSD_API int osd_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum,
+ * reduce-add into dq_acc [B*L, H*64] (scratch, zeroed by the call) and converted to bf16 into dqkv.
+ * stats: fp32 scratch of osd_attn_bwd_fused_stats_floats(B, L, H) elements. */
+OSD_API size_t osd_attn_bwd_fused_stats_floats(int B, int L, int H);
+OSD_API int osd_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* stats,
                                float* dq_acc, void* dqkv, int B, int L, int H, void* stream);
 
 /* Gradient of DiffusionModel.forward (what autograd computes for the reference at train.py:84 + Lightning's

@@ -47,10 +47,10 @@ struct AttnBwdFusedParams {
   CUtensorMap tma_qkv;  // qkv    dims (3*dh, L, B), box (64, 128, 1)
   CUtensorMap tma_dy;   // dy     dims (dh, L, B),   box (64, 128, 1)
   CUtensorMap tma_dq;   // dq_acc dims (dh, L, B) fp32, box (32, 32, 1)
-  const float* lse;     // [B, H, L]
-  const float* dsum;    // [B, H, L]  D = rowsum(dO o O)
+  const float* lse2n;   // [B*H, Lp]  -lse * log2(e), zero past L   (Lp = L rounded up to 128)
+  const float* dneg;    // [B*H, Lp]  -D = -rowsum(dO o O), zero past L
   __nv_bfloat16* dqkv;  // [B*L, 3*dh]: this kernel writes the dk and dv column blocks
-  int B, H, L, dh;
+  int B, H, L, Lp, dh;
   float scale, scale_log2;
 };
 
@@ -132,9 +132,12 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       for (int i = 0; i < n_q; ++i) {
         const int st = i & 1;
         mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&q_full[st], 2 * FT);
+        mbar_expect_tx(&q_full[st], 2 * FT + 1024);
         tma_load_3d(sQ + st * FT, &p.tma_qkv, &q_full[st], h * 64, qi * 128, b);
         tma_load_3d(sDO + st * FT, &p.tma_dy, &q_full[st], h * 64, qi * 128, b);
+        const size_t so = ((size_t)b * p.H + h) * p.Lp + (size_t)qi * 128;
+        bulk_load_1d(sStat + st * 256, p.lse2n + so, 512, &q_full[st]);
+        bulk_load_1d(sStat + st * 256 + 128, p.dneg + so, 512, &q_full[st]);
         if (++qi == n_q) qi = 0;
       }
     }
@@ -202,7 +205,6 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
     const int quad = warp & 3;
     const int grp = (warp - 2) >> 2;   // q-column group: columns [64 grp, 64 grp + 64)
     const int row = quad * 32 + lane;  // kv row
-    const int tid = threadIdx.x - 64;  // 0..255
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     {  // one-time copy of this thread's K (grp 0) or V (grp 1) row (128 B, SW128 smem) into TMEM
       mbar_wait(kv_full, 0);
@@ -224,19 +226,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
     const uint32_t ds_row = smem_u32(sDS) + grp * FT + row * 128;
     const int sw = row & 7;
     const float c = p.scale_log2;
-    const size_t sbase = ((size_t)b * p.H + h) * p.L;
-    // -lse2 / -D of a q tile are staged in smem (double-buffered); q rows past L: -lse2 = -inf -> P = 0
-    auto load_stat = [&](int qt) -> float {
-      const int qi = qt * 128 + (tid & 127);
-      const bool okq = qi < p.L;
-      if (tid < 128) return okq ? -p.lse[sbase + qi] * 1.4426950408889634f : -INFINITY;
-      return okq ? -p.dsum[sbase + qi] : 0.f;
-    };
     // dQ drain: this warp moves rows [32 quad, +32) x columns [32 grp, +32) of the finished dQ tile j (q tile qj)
     const uint32_t tDQ = tmem_base + 384 + lane_off + grp * 32;
     uint8_t* stg = sStg + (warp - 2) * 4096;
     const uint32_t stg_row = smem_u32(stg) + lane * 128;
-    auto drain_dq = [&](int j, int qj) {
+    // part 1: TMEM -> registers -> staging smem (the proxy fence is shared with the dS^T smem writes of phase 2);
+    // part 2 (after that fence): one lane issues the TMA reduce-add
+    auto drain_load = [&](int j) {
       mbar_wait(dq_full, j & 1);
       tc_fence_after();
       uint32_t r[32];
@@ -252,29 +248,23 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       __syncwarp();
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((u ^ (lane & 7)) << 4)),
-                     "r"(__float_as_uint(__uint_as_float(r[4 * u]) * p.scale)),
-                     "r"(__float_as_uint(__uint_as_float(r[4 * u + 1]) * p.scale)),
-                     "r"(__float_as_uint(__uint_as_float(r[4 * u + 2]) * p.scale)),
-                     "r"(__float_as_uint(__uint_as_float(r[4 * u + 3]) * p.scale))
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((u ^ (lane & 7)) << 4)), "r"(r[4 * u]),
+                     "r"(r[4 * u + 1]), "r"(r[4 * u + 2]), "r"(r[4 * u + 3])
                      : "memory");
-      fence_proxy_async_smem();
-      __syncwarp();
+    };
+    auto drain_issue = [&](int qj) {
       if (lane == 0) {
         tma_reduce_add_3d(&p.tma_dq, stg, h * 64 + grp * 32, qj * 128 + quad * 32, b);
         tma_store_commit();
       }
     };
     int qt = i0, qprev = i0;
-    sStat[tid] = load_stat(qt);
-    fb_named_bar(1, 256);
     for (int i = 0; i < n_q; ++i) {
-      const float* st = sStat + (i & 1) * 256 + grp * 64;
+      const float* st = sStat + (i & 1) * 256 + grp * 64;  // [-lse2 128 | -D 128] of this q tile (bulk-copied)
       int qn = qt + 1;
       if (qn == n_q) qn = 0;
-      float next_stat = 0.f;
-      if (i + 1 < n_q) next_stat = load_stat(qn);
       // ---- phase 1: P^T = exp2(S^T * c - lse2[q])
+      mbar_wait(&q_full[i & 1], (i >> 1) & 1);  // statistics landed (already complete: S^T_i was issued after it)
       mbar_wait(s_full, i & 1);
       tc_fence_after();
       float pt[64];
@@ -308,7 +298,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       __syncwarp();
       if (lane == 0) mbar_arrive(pt_full);
       // ---- phase 2: dS^T = P^T o (dP^T - D[q])   (1/sqrt(d) is applied to the dK / dQ accumulators on the way out)
-      if (i > 0) drain_dq(i - 1, qprev);  // also: dQ_{i-1} has consumed the dS^T smem tile
+      if (i > 0) drain_load(i - 1);  // also: dQ_{i-1} has consumed the dS^T smem tile
       mbar_wait(dp_full, i & 1);
       tc_fence_after();
 #pragma unroll
@@ -343,14 +333,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
-      if (i + 1 < n_q) {
-        sStat[((i + 1) & 1) * 256 + tid] = next_stat;  // buffer (i+1)&1 was last read during tile i-1
-        fb_named_bar(1, 256);
-      }
+      if (i > 0) drain_issue(qprev);
       qprev = qt;
       qt = qn;
     }
-    drain_dq(n_q - 1, qprev);
+    drain_load(n_q - 1);
+    fence_proxy_async_smem();
+    __syncwarp();
+    drain_issue(qprev);
     // ---- epilogue: group 0 writes dK (x scale), group 1 writes dV
     mbar_wait(acc_done, 0);
     tc_fence_after();
@@ -387,9 +377,44 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
   }
 }
 
-// dq_acc fp32 [T, dh] -> bf16 dq column block of dqkv [T, 3*dh]
+// stats[0] = -lse * log2(e), stats[1] = -rowsum(dO o O), both [B*H, Lp] with zeros for Lp > l >= L
+// (warp per padded token: lane covers 32 contiguous columns of the 1024 = half a head)
+__global__ void attn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dy,
+                                      const float* __restrict__ lse, float* __restrict__ lse2n, float* __restrict__ dneg,
+                                      int B, int H, int L, int Lp) {
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= B * Lp) return;
+  const int b = t / Lp, l = t % Lp;
+  float acc = 0.f;
+  if (l < L) {
+    const size_t tok = (size_t)b * L + l;
+    const uint4* a = reinterpret_cast<const uint4*>(y + tok * (H * 64) + lane * 32);
+    const uint4* g = reinterpret_cast<const uint4*>(dy + tok * (H * 64) + lane * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 av = a[i], gv = g[i];
+      const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&av);
+      const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&gv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc = fmaf(__low2float(ap[k]), __low2float(gp[k]), acc);
+        acc = fmaf(__high2float(ap[k]), __high2float(gp[k]), acc);
+      }
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if ((lane & 1) == 0) {
+    const int hh = lane >> 1;
+    const size_t o = ((size_t)b * H + hh) * Lp + l;
+    dneg[o] = -acc;
+    lse2n[o] = (l < L) ? -lse[((size_t)b * H + hh) * L + l] * 1.4426950408889634f : 0.f;
+  }
+}
+
+// dq_acc fp32 [T, dh] (unscaled) -> bf16 dq column block of dqkv [T, 3*dh], x 1/sqrt(d)
 __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, size_t n8,
-                                           int dh) {
+                                           int dh, float scale) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const size_t e = i * 8;
@@ -397,16 +422,23 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_b
   const float4 a = reinterpret_cast<const float4*>(acc + e)[0];
   const float4 bb = reinterpret_cast<const float4*>(acc + e)[1];
   *reinterpret_cast<uint4*>(dqkv + t * (3 * (size_t)dh) + c) =
-      make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(bb.x, bb.y), pack_bf16(bb.z, bb.w));
+      make_uint4(pack_bf16(a.x * scale, a.y * scale), pack_bf16(a.z * scale, a.w * scale),
+                 pack_bf16(bb.x * scale, bb.y * scale), pack_bf16(bb.z * scale, bb.w * scale));
 }
 
-int launch_attn_bwd_prep(const void* y, const void* dy, float* dsum, int B, int L, int H, cudaStream_t stream);
+size_t attn_bwd_fused_stats_floats(int B, int L, int H) { return (size_t)2 * B * H * ((L + 127) / 128 * 128); }
 
-int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, float* dq_acc,
+int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* stats, float* dq_acc,
                           void* dqkv, int B, int L, int H, cudaStream_t stream) {
-  OSD_CHECK(qkv && y && dy && lse && dsum && dq_acc && dqkv && B > 0 && L > 0 && H == 16, "attn_bwd_fused: bad arguments");
+  OSD_CHECK(qkv && y && dy && lse && stats && dq_acc && dqkv && B > 0 && L > 0 && H == 16, "attn_bwd_fused: bad arguments");
   const int dh = H * 64;
-  OSD_TRY(launch_attn_bwd_prep(y, dy, dsum, B, L, H, stream));
+  const int Lp = (L + 127) / 128 * 128;
+  float* lse2n = stats;
+  float* dneg = stats + (size_t)B * H * Lp;
+  attn_bwd_stats_kernel<<<ceil_div(B * Lp, 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(y),
+                                                                static_cast<const __nv_bfloat16*>(dy), lse, lse2n, dneg, B,
+                                                                H, L, Lp);
+  OSD_LAUNCHED();
   OSD_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * L * dh * sizeof(float), stream));
   AttnBwdFusedParams p;
   {
@@ -427,10 +459,10 @@ int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const 
     uint32_t box[3] = {32, 32, 1};
     OSD_TRY(make_tmap(&p.tma_dq, dq_acc, 4, 3, dims, strides, box));
   }
-  p.lse = lse;
-  p.dsum = dsum;
+  p.lse2n = lse2n;
+  p.dneg = dneg;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
-  p.B = B; p.H = H; p.L = L; p.dh = dh;
+  p.B = B; p.H = H; p.L = L; p.Lp = Lp; p.dh = dh;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   static bool attr_set = false;
@@ -443,7 +475,7 @@ int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const 
   attn_bwd_fused_kernel<<<(unsigned)grid, FB_THREADS, FB_SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
   const size_t n8 = (size_t)B * L * dh / 8;
-  attn_bwd_dq_convert_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(dq_acc, p.dqkv, n8, dh);
+  attn_bwd_dq_convert_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(dq_acc, p.dqkv, n8, dh, p.scale);
   OSD_LAUNCHED();
   return 0;
 }

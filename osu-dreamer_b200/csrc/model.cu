@@ -262,7 +262,7 @@ static BwdPlan make_bwd_plan(int B, int L, int a_batch) {
   p.dqkv = take(T * 3072 * 2);
   p.dq_acc = take(T * 1024 * 4);  // fp32 dQ accumulator of the single-pass attention backward
   p.dz = take(T * 512 * 2);
-  p.dsum = take(T * 16 * 4);
+  p.dsum = take(attn_bwd_fused_stats_floats(B, L, 16) * 4);  // >= T*16*4 (the two-pass kernels use the first B*16*L)
   p.da_tok = take(Ta * 128 * 4);
   p.a_pre = take(Ta * 128 * 4);
   p.da_pre = take(Ta * 128 * 2);
@@ -551,9 +551,11 @@ int osd_attn_bwd(const void* qkv, const void* y, const void* dy, const float* ls
   return launch_attn_bwd(qkv, y, dy, lse, dsum, dqkv, B, L, H, static_cast<cudaStream_t>(stream));
 }
 
-int osd_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, float* dq_acc,
+size_t osd_attn_bwd_fused_stats_floats(int B, int L, int H) { return attn_bwd_fused_stats_floats(B, L, H); }
+
+int osd_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* stats, float* dq_acc,
                        void* dqkv, int B, int L, int H, void* stream) {
-  return launch_attn_bwd_fused(qkv, y, dy, lse, dsum, dq_acc, dqkv, B, L, H, static_cast<cudaStream_t>(stream));
+  return launch_attn_bwd_fused(qkv, y, dy, lse, stats, dq_acc, dqkv, B, L, H, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -216,9 +216,10 @@ def attn_bwd(qkv, y, dy, lse, B, L, H=16):
 
 def attn_bwd_fused(qkv, y, dy, lse, B, L, H=16):
     dqkv = torch.empty_like(qkv)
-    dsum = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device)
+    stats = torch.empty(_sz('osd_attn_bwd_fused_stats_floats', B, L, H), dtype=torch.float32,
+                        device=qkv.device)
     dq_acc = torch.empty(B * L, H * 64, dtype=torch.float32, device=qkv.device)
-    _check(load().osd_attn_bwd_fused(ptr(qkv), ptr(y), ptr(dy), ptr(lse), ptr(dsum), ptr(dq_acc), ptr(dqkv), c_int(B),
+    _check(load().osd_attn_bwd_fused(ptr(qkv), ptr(y), ptr(dy), ptr(lse), ptr(stats), ptr(dq_acc), ptr(dqkv), c_int(B),
                                      c_int(L), c_int(H), stream()))
     return dqkv
 
