@@ -284,11 +284,11 @@ def run_cuda(args):
             dy = torch.randn(Ba * L, 1024, device=dev).to(torch.bfloat16)
             bound = torch.tensor([14.0], device=dev)  # randn scores / 8 stay far below 2^14: same kernel path the model runs
             ms_f = time_kernel(lambda: lib.attn_fwd(qkv, Ba, L, bound_log2=bound, variant=4), iters=3, warm=1)
-            ms_b = time_kernel(lambda: lib.attn_bwd(qkv, y, dy, lse, Ba, L), iters=3, warm=1)
+            ms_b = time_kernel(lambda: lib.attn_bwd_fused(qkv, y, dy, lse, Ba, L), iters=3, warm=1)
             fl_f = 4.0 * Ba * 16 * L * L * 64
             kern = {'attn_fwd': {'ms': ms_f, 'tflops': fl_f / ms_f / 1e9},
-                    'attn_bwd(dkdv+dq)': {'ms': ms_b, 'tflops': 2 * fl_f / ms_b / 1e9}}
-            dom = 'attn_bwd(dkdv+dq)' if 8 * ms_b > 8 * ms_f else 'attn_fwd'
+                    'attn_bwd_fused': {'ms': ms_b, 'tflops': 2 * fl_f / ms_b / 1e9}}
+            dom = 'attn_bwd_fused' if 8 * ms_b > 8 * ms_f else 'attn_fwd'
             ach = kern[dom]['tflops']
             line['roofline'] = {'bound': 'tensor', 'kernel': dom, 'achieved': ach, 'peak': peaks['tf_burst'],
                                 'unit': 'TFLOP/s', 'frac': ach / peaks['tf_burst'], 'traffic': None,

@@ -16,14 +16,16 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
 
 
-@pytest.mark.parametrize('B,L', [(1, 128), (2, 320), (1, 1000)])
-def test_attention_backward_matches_autograd(B, L):
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('B,L', [(1, 128), (2, 320), (1, 1000), (1, 60)])
+def test_attention_backward_matches_autograd(B, L, fused):
+    """both attention-backward paths: two kernels (dK/dV, dQ) and the single-pass kernel with TMA reduce-add dQ"""
     from osu_dreamer_b200 import lib
     g = torch.Generator().manual_seed(L + 1)
     qkv = (torch.randn(B * L, 3072, generator=g)).cuda().to(torch.bfloat16)
     dy = torch.randn(B * L, 1024, generator=g).cuda().to(torch.bfloat16)
     y, lse = lib.attn_fwd(qkv, B, L)
-    dqkv = lib.attn_bwd(qkv, y, dy, lse, B, L)
+    dqkv = (lib.attn_bwd_fused if fused else lib.attn_bwd)(qkv, y, dy, lse, B, L)
     torch.cuda.synchronize()
     ref_in = qkv.float().clone().requires_grad_(True)
     q, k, v = ref_in.view(B, L, 3, 16, 64).permute(2, 0, 3, 1, 4)
