@@ -139,10 +139,16 @@ OSD_API int osd_attn_bwd(const void* qkv, const void* y, const void* dy, const f
 
 /* Same gradient in one pass (five GEMMs, one exponential per score): dq is accumulated in fp32 through TMA
  * reduce-add into dq_acc [B*L, H*64] (scratch, zeroed by the call) and converted to bf16 into dqkv.
- * stats: fp32 scratch of osd_attn_bwd_fused_stats_floats(B, L, H) elements. */
+ * Scratch: stats fp32 [osd_attn_bwd_fused_stats_floats(B, L, H)], dy_scaled bf16 [B*L, H*64].
+ * If the softmax statistics of some 128-row q tile span more than 96 octaves the call runs the two-kernel
+ * path of osd_attn_bwd instead (decided on the device, no host synchronisation). */
 OSD_API size_t osd_attn_bwd_fused_stats_floats(int B, int L, int H);
 OSD_API int osd_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* stats,
-                               float* dq_acc, void* dqkv, int B, int L, int H, void* stream);
+                               float* dq_acc, void* dy_scaled, void* dqkv, int B, int L, int H, void* stream);
+
+/* Debugging aid (tools/trace_attn_bwd.py): record the event timeline of CTA `cta` of the single-pass attention
+ * backward into buf (DEVICE memory, 3 x 1024 u64 records: (event << 48) | (tile << 32) | SM clock); null = off. */
+OSD_API void osd_debug_attn_bwd_trace(unsigned long long* buf, int cta);
 
 /* Gradient of DiffusionModel.forward (what autograd computes for the reference at train.py:84 + Lightning's
  * backward): given du [B] and dv [B,6,L], ACCUMULATES the parameter gradients into grads[164] (HOST array of

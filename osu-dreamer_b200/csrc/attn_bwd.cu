@@ -50,6 +50,7 @@ struct AttnBwdParams {
   __nv_bfloat16* dqkv;     // [B*L, 3*dh]  (dq | dk | dv), gradients w.r.t. the roped q, k and v
   int B, H, L, dh;
   float scale, scale_log2;
+  const int* gate;  // nullable: the kernels return immediately when *gate == 0 (fallback launches of the fused path)
 };
 
 // ================================================================================================= dQ
@@ -64,6 +65,7 @@ static constexpr int DQ_SMEM_BYTES = DQ_SMEM_TILES + 256;
 
 __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
+  if (p.gate != nullptr && *p.gate == 0) return;
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
@@ -298,6 +300,7 @@ static constexpr int DKV_SMEM_BYTES = DKV_SMEM_TILES + 1024 + 256;
 
 __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
+  if (p.gate != nullptr && *p.gate == 0) return;
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
@@ -579,14 +582,29 @@ int launch_attn_bwd_prep(const void* y, const void* dy, float* dsum, int B, int 
   return 0;
 }
 
+static int launch_attn_bwd_main(const void* qkv, const void* dy, const float* lse, const float* dsum, void* dqkv,
+                                int B, int L, int H, const int* gate, cudaStream_t stream);
+
 int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, void* dqkv, int B,
                     int L, int H, cudaStream_t stream) {
   OSD_CHECK(qkv && y && dy && lse && dsum && dqkv && B > 0 && L > 0 && H == 16, "attn_bwd: bad arguments");
-  const int dh = H * 64;
   attn_bwd_prep_kernel<<<ceil_div(B * L, 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(y),
                                                                static_cast<const __nv_bfloat16*>(dy), dsum, B, H, L);
   OSD_LAUNCHED();
+  return launch_attn_bwd_main(qkv, dy, lse, dsum, dqkv, B, L, H, nullptr, stream);
+}
+
+// the two kernels with dsum = rowsum(dO o O) already computed; they do nothing when *gate == 0
+int launch_attn_bwd_gated(const void* qkv, const void* dy, const float* lse, const float* dsum, void* dqkv, int B, int L,
+                          int H, const int* gate, cudaStream_t stream) {
+  return launch_attn_bwd_main(qkv, dy, lse, dsum, dqkv, B, L, H, gate, stream);
+}
+
+static int launch_attn_bwd_main(const void* qkv, const void* dy, const float* lse, const float* dsum, void* dqkv,
+                                int B, int L, int H, const int* gate, cudaStream_t stream) {
+  const int dh = H * 64;
   AttnBwdParams p;
+  p.gate = gate;
   {
     uint64_t dims[3] = {(uint64_t)3 * dh, (uint64_t)L, (uint64_t)B};
     uint64_t strides[2] = {(uint64_t)3 * dh * 2, (uint64_t)L * 3 * dh * 2};

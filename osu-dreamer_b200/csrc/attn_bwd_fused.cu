@@ -9,12 +9,9 @@
 // backward kernels do.  Each CTA starts its q loop at a different tile so that the 64 CTAs of one (b, h) do not
 // hit the same dQ rows at the same time.
 //
-//   warps    : 0 TMA producer | 1 TMEM allocator + UMMA issuer | 2-9 softmax (2 column groups x 4 lane quadrants,
-//              thread = kv row); the same warps drain the finished dQ tiles (TMEM -> swizzled smem -> TMA
-//              reduce-add; warp = 32 q rows x 32 d columns).  10 warps keep the register file at <= 3 warps per SM
-//              sub-partition (200 registers per thread available).  The two column groups have separate barriers
-//              and run half a tile period apart (see the UMMA issue order), so one group's exponentials (SFU) overlap
-//              the other group's dS phase.
+//   warps    : 0 TMA producer | 1 TMEM allocator + UMMA issuer (event-driven) | 2-9 softmax (2 column groups x 4
+//              lane quadrants, thread = kv row, separate barriers per group) | 10-13 dQ drain (TMEM -> swizzled smem
+//              -> TMA reduce-add; warp = 32 q rows x 64 d columns)
 //   TMEM     : S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | dQ_i [384,448) | K bf16 [448,480) |
 //              V bf16 [480,512).  K and V are the A operands of S^T = K Q_i^T and dP^T = V dO_i^T straight from TMEM;
 //              the bf16 P^T / dS^T tiles are written back over the consumed S^T / dP^T columns (column group g at
@@ -26,7 +23,7 @@
 
 namespace osd {
 
-static constexpr int FB_THREADS = 320;
+static constexpr int FB_THREADS = 448;
 static constexpr int FT = 128 * 128;  // bytes of a [128 x 64] bf16 tile
 static constexpr uint32_t FB_TMEM_COLS = 512;
 static constexpr int FB_QST = 3;                      // Q / dO / statistics stages
@@ -49,17 +46,29 @@ __device__ __forceinline__ float fb_ex2(float x) {
 
 struct AttnBwdFusedParams {
   CUtensorMap tma_qkv;  // qkv    dims (3*dh, L, B), box (64, 128, 1)
-  CUtensorMap tma_dy;   // dy     dims (dh, L, B),   box (64, 128, 1)
+  CUtensorMap tma_dy;   // w-scaled dO: dims (dh, L, B), box (64, 128, 1)
   CUtensorMap tma_dq;   // dq_acc dims (dh, L, B) fp32, box (32, 32, 1)
-  const float* lse2n;   // [B*H, Lp]  -lse * log2(e), zero past L   (Lp = L rounded up to 128)
-  const float* dneg;    // [B*H, Lp]  -D = -rowsum(dO o O), zero past L
+  const float* mtile;   // [B*H, n_t]  m = max over the q tile of lse * log2(e)
+  const float* dneg;    // [B*H, Lp]   -w D,  w = 2^(m - lse2), D = rowsum(dO o O); zero past L (Lp = L rounded up to 128)
+  const int* fallback;  // != 0: the statistics of some q tile span too many octaves for the w-scaling -> do nothing
   __nv_bfloat16* dqkv;  // [B*L, 3*dh]: this kernel writes the dk and dv column blocks
   int B, H, L, Lp, dh;
   float scale, scale_log2;
+  unsigned long long* trace;  // nullable (tools/trace_attn_bwd.py): event timeline of one CTA, 3 writers x 1024 records
+  int trace_cta;
 };
+
+// timeline record: (event << 48) | (tile << 32) | low 32 bits of the SM clock
+#define FB_TRACE(slot, ev, tile)                                                                                     \
+  do {                                                                                                               \
+    if (tr != nullptr && tr_n < 1024)                                                                                \
+      tr[(slot) * 1024 + tr_n++] = ((unsigned long long)(ev) << 48) | ((unsigned long long)(tile) << 32) |           \
+                                   (unsigned long long)(clock64() & 0xffffffffll);                                   \
+  } while (0)
 
 __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __grid_constant__ AttnBwdFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
+  if (*p.fallback != 0) return;
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
@@ -87,7 +96,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
   uint64_t* dq_empty = bars + 16; // dQ_i drained out of TMEM
   uint64_t* kvt_ready = bars + 17;  // K / V copied into TMEM
   uint64_t* acc_done = bars + 18;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* ds_free = bars + 19;  // [2]  dQ_j has consumed dS^T smem buffer j & 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_t = (p.L + 127) / 128;  // kv tiles == q tiles
@@ -97,6 +107,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
   const int kv0 = kt * 128;
   const int n_q = n_t;
   const int i0 = kt;  // q-loop rotation: iteration i works on q tile (i0 + i) % n_q
+  unsigned long long* tr = (p.trace != nullptr && (int)blockIdx.x == p.trace_cta && (threadIdx.x & 31) == 0) ? p.trace : nullptr;
+  int tr_n = 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tma_qkv);
@@ -114,7 +126,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       mbar_init(&ds_full[g], 4);
     }
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 8);
+    mbar_init(dq_empty, 4);
+    mbar_init(&ds_free[0], 1);
+    mbar_init(&ds_free[1], 1);
     mbar_init(kvt_ready, 8);
     mbar_init(acc_done, 1);
     fence_barrier_init();
@@ -138,11 +152,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       uint32_t ph = 0;
       for (int i = 0; i < n_q; ++i) {
         mbar_wait(&q_empty[st], ph ^ 1);
-        mbar_expect_tx(&q_full[st], 2 * FT + 1024);
+        mbar_expect_tx(&q_full[st], 2 * FT + 512);
         tma_load_3d(sQ + st * FT, &p.tma_qkv, &q_full[st], h * 64, qi * 128, b);
         tma_load_3d(sDO + st * FT, &p.tma_dy, &q_full[st], h * 64, qi * 128, b);
         const size_t so = ((size_t)b * p.H + h) * p.Lp + (size_t)qi * 128;
-        bulk_load_1d(sStat + st * 256, p.lse2n + so, 512, &q_full[st]);
         bulk_load_1d(sStat + st * 256 + 128, p.dneg + so, 512, &q_full[st]);
         if (++qi == n_q) qi = 0;
         if (++st == FB_QST) {
@@ -211,7 +224,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       bool s_pend[2] = {false, false};  // S(i+1,g) waiting for its Q stage (never blocks the other group's chain)
       int s_st[2] = {0, 0};
       uint32_t s_ph[2] = {0, 0};
-      bool started1 = false;
+      bool started1 = true;
+      issue_s(1, 0);
+      issue_dp(1, 0);
       int dk_done[2] = {0, 0};  // tiles whose dK (last reader of the Q / dO stage) has been issued
       int released = 0, rel_st = 0, dq_next = 0;
       while (ti[0] < n_q || ti[1] < n_q || dq_next < n_q) {
@@ -219,6 +234,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
         for (int g = 0; g < 2; ++g) {
           if (s_pend[g] && mbar_try_wait(&q_full[s_st[g]], s_ph[g])) {
             tc_fence_after();
+            FB_TRACE(0, 14 + g, ti[g]);
             issue_s(g, s_st[g]);
             s_pend[g] = false;
           }
@@ -227,6 +243,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
           if (!want_ds[g]) {
             if (!mbar_try_wait(&pt_full[g], i & 1)) continue;
             tc_fence_after();
+            FB_TRACE(0, 10 + g, i);
             issue_dv(g, st);
             if (i + 1 < n_q) {  // S(i+1,g) follows as soon as Q_{i+1} has landed (polled below)
               s_pend[g] = true;
@@ -246,6 +263,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
           } else {
             if (!mbar_try_wait(&ds_full[g], i & 1)) continue;
             tc_fence_after();
+            FB_TRACE(0, 12 + g, i);
             issue_dk(g, st);
             int sn = st + 1;
             if (sn == FB_QST) {
@@ -273,12 +291,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
             umma_f16_ss(tDQ, make_smem_desc(a + k * 16 * 128, FT, 1024), make_smem_desc(aK + k * 16 * 128, 0, 1024), id_q,
                         k > 0);
           umma_commit(dq_full);
+          umma_commit(&ds_free[dq_next & 1]);
+          FB_TRACE(0, 16, dq_next);
           ++dq_next;
         }
       }
       umma_commit(acc_done);
     }
-  } else {
+  } else if (warp < 10) {
     // ================================================================== softmax (thread = kv row, 64 q columns)
     const int quad = warp & 3;
     const int grp = (warp - 2) >> 2;   // q-column group: columns [64 grp, 64 grp + 64)
@@ -308,47 +328,20 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
     uint64_t* my_dp_full = &dp_full[grp];
     uint64_t* my_pt_full = &pt_full[grp];
     uint64_t* my_ds_full = &ds_full[grp];
-    // dQ drain: this warp moves rows [32 quad, +32) x columns [32 grp, +32) of the finished dQ tile j (q tile qj):
-    // part 1 = TMEM -> registers -> staging smem (the proxy fence is shared with the dS^T smem writes of phase 2),
-    // part 2 (after that fence) = one lane issues the TMA reduce-add
-    const uint32_t tDQ = tmem_base + 384 + lane_off + grp * 32;
-    uint8_t* stg = sStg + (warp - 2) * 4096;
-    const uint32_t stg_row = smem_u32(stg) + lane * 128;
-    auto drain_load = [&](int j) {
-      mbar_wait(dq_full, j & 1);
-      tc_fence_after();
-      uint32_t r[32];
-      __syncwarp();
-      tmem_ld32(tDQ, r);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(dq_empty);
-        tma_store_wait_read<0>();  // the previous reduce-add of this warp has read the staging tile
-      }
-      __syncwarp();
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((u ^ (lane & 7)) << 4)), "r"(r[4 * u]),
-                     "r"(r[4 * u + 1]), "r"(r[4 * u + 2]), "r"(r[4 * u + 3])
-                     : "memory");
-    };
-    auto drain_issue = [&](int qj) {
-      if (lane == 0) {
-        tma_reduce_add_3d(&p.tma_dq, stg, h * 64 + grp * 32, qj * 128 + quad * 32, b);
-        tma_store_commit();
-      }
-    };
-    // Drain schedule: dQ_{i-2} is drained between the two phases of tile i (it completed about a tile period ago, so
-    // the wait never blocks; it also guarantees that dS^T smem buffer i&1, last read by dQ_{i-2}, is free).
-    int qt = i0, qprev = i0, qprev2 = i0, stq = 0;
+    int qt = i0, stq = 0;
+    const float* mrow = p.mtile + (size_t)bh * n_q;
+    float m_cur = __ldg(mrow + qt);
     for (int i = 0; i < n_q; ++i) {
-      // [-lse2 128 | -D 128] of this q tile, bulk-copied on the same barrier as Q_i / dO_i (complete before S^T_i)
+      // -w D of this q tile, bulk-copied on the same barrier as Q_i / dO_i (complete before S^T_i)
       const float* st = sStat + stq * 256 + grp * 64;
-      // ---- phase 1: P^T = exp2(S^T * c - lse2[q])
+      const float m_next = __ldg(mrow + (qt + 1 == n_q ? 0 : qt + 1));  // consumed one tile later
+      // ---- phase 1: P~^T = exp2(S^T * c - m),  m = max lse2 of the q tile: no per-column statistic; the factor
+      //      w[q] = 2^(m - lse2[q]) that turns P~ into P is folded into dO (dO~ = w dO) and D (D~ = w D)
+      const bool trw = quad == 2;  // warps 2 (group 0) and 6 (group 1)
+      if (trw) FB_TRACE(1 + grp, 0, i);
       mbar_wait(my_s_full, i & 1);
       tc_fence_after();
+      if (trw) FB_TRACE(1 + grp, 1, i);
       float pt[64];
 #pragma unroll
       for (int cch = 0; cch < 2; ++cch) {
@@ -356,15 +349,11 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
         __syncwarp();
         tmem_ld32(tS + cch * 32, rs);
         tmem_wait_ld();
-        const float4* l4 = reinterpret_cast<const float4*>(st + cch * 32);  // broadcast LDS.128
-        const float2 c2 = make_float2(c, c);
+        const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_cur, -m_cur);
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-          const float4 lv = l4[k4];
-          const float2 a = ffma2(make_float2(__uint_as_float(rs[k4 * 4 + 0]), __uint_as_float(rs[k4 * 4 + 1])), c2,
-                                 make_float2(lv.x, lv.y));
-          const float2 bb = ffma2(make_float2(__uint_as_float(rs[k4 * 4 + 2]), __uint_as_float(rs[k4 * 4 + 3])), c2,
-                                  make_float2(lv.z, lv.w));
+          const float2 a = ffma2(make_float2(__uint_as_float(rs[k4 * 4 + 0]), __uint_as_float(rs[k4 * 4 + 1])), c2, nm2);
+          const float2 bb = ffma2(make_float2(__uint_as_float(rs[k4 * 4 + 2]), __uint_as_float(rs[k4 * 4 + 3])), c2, nm2);
           pt[cch * 32 + k4 * 4 + 0] = fb_ex2(a.x);
           pt[cch * 32 + k4 * 4 + 1] = fb_ex2(a.y);
           pt[cch * 32 + k4 * 4 + 2] = fb_ex2(bb.x);
@@ -379,11 +368,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(my_pt_full);
-      if (i > 1) drain_load(i - 2);
-      // ---- phase 2: dS^T = P^T o (dP^T - D[q])   (1/sqrt(d) is applied to the dK / dQ results on the way out)
+      if (trw) FB_TRACE(1 + grp, 2, i);
+      // ---- phase 2: dS^T = P~^T o (dP~^T - D~[q])   (1/sqrt(d) is applied to the dK / dQ results on the way out)
       mbar_wait(my_dp_full, i & 1);
       tc_fence_after();
-      const uint32_t ds_dst = ds_row + (i & 1) * 2 * FT;  // buffer i&1: dQ_{i-2} (its last reader) was drained by this warp
+      if (trw) FB_TRACE(1 + grp, 4, i);
+      if (i > 1) mbar_wait(&ds_free[i & 1], ((i - 2) >> 1) & 1);  // dQ_{i-2} has read dS^T smem buffer i & 1
+      const uint32_t ds_dst = ds_row + (i & 1) * 2 * FT;
 #pragma unroll
       for (int cch = 0; cch < 2; ++cch) {
         uint32_t rp[32];
@@ -416,22 +407,11 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(my_ds_full);
-      if (i > 1) drain_issue(qprev2);
-      qprev2 = qprev;
-      qprev = qt;
+      if (trw) FB_TRACE(1 + grp, 5, i);
+      m_cur = m_next;
       if (++qt == n_q) qt = 0;
       if (++stq == FB_QST) stq = 0;
     }
-    if (n_q > 1) {
-      drain_load(n_q - 2);
-      fence_proxy_async_smem();
-      __syncwarp();
-      drain_issue(qprev2);
-    }
-    drain_load(n_q - 1);
-    fence_proxy_async_smem();
-    __syncwarp();
-    drain_issue(qprev);
     // ---- epilogue: group 0 writes dK (x scale), group 1 writes dV
     mbar_wait(acc_done, 0);
     tc_fence_after();
@@ -457,6 +437,50 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       }
     }
     tc_fence_before();
+  } else {
+    // ================================================================== dQ drain (warp = 32 q rows x 64 d columns)
+    // TMEM -> registers -> swizzled smem staging -> TMA reduce-add into the fp32 dQ accumulator, as soon as dQ_j is
+    // complete: the next dQ can be issued a few hundred cycles later, independently of the softmax warps
+    const int quad = warp & 3;
+    const uint32_t tDQ = tmem_base + 384 + (static_cast<uint32_t>(quad * 32) << 16);
+    uint8_t* stg = sStg + (warp - 10) * 8192;
+    uint32_t n_st = 0;
+    int qt = i0;
+    for (int j = 0; j < n_q; ++j) {
+      mbar_wait(dq_full, j & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      __syncwarp();
+      tmem_ld32(tDQ, r0);
+      tmem_ld32(tDQ + 32, r1);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint8_t* buf = stg + (n_st & 1) * 4096;
+        if (n_st >= 2) {
+          if (lane == 0) tma_store_wait_read<1>();  // the reduce-add that used this buffer two stores ago has read it
+          __syncwarp();
+        }
+        const uint32_t rowb = smem_u32(buf) + lane * 128;
+        const uint32_t* w = half == 0 ? r0 : r1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((u ^ (lane & 7)) << 4)), "r"(w[4 * u]),
+                       "r"(w[4 * u + 1]), "r"(w[4 * u + 2]), "r"(w[4 * u + 3])
+                       : "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_3d(&p.tma_dq, buf, h * 64 + half * 32, qt * 128 + quad * 32, b);
+          tma_store_commit();
+        }
+        ++n_st;
+      }
+      if (++qt == n_q) qt = 0;
+    }
     if (lane == 0) tma_store_wait<0>();
     __syncwarp();
   }
@@ -468,44 +492,85 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
   }
 }
 
-// stats[0] = -lse * log2(e), stats[1] = -rowsum(dO o O), both [B*H, Lp] with zeros for Lp > l >= L
-// (warp per padded token: lane covers 32 contiguous columns of the 1024 = half a head)
+// ------------------------------------------------------------------------------------------------- statistics
+// per (b, h, q tile): m = max lse2 over the tile; raises *fallback when the tile's lse2 values span more than 96
+// octaves (then P~ = 2^(c s - m) could underflow for rows far below the maximum)
+__global__ void attn_bwd_tilemax_kernel(const float* __restrict__ lse, float* __restrict__ mtile, int* __restrict__ fallback,
+                                        int L, int n_t) {
+  __shared__ float smx[4], smn[4];
+  const int bh = blockIdx.x / n_t, t = blockIdx.x % n_t;
+  const int l = t * 128 + threadIdx.x;
+  const bool ok = l < L;
+  const float v = ok ? lse[(size_t)bh * L + l] * 1.4426950408889634f : 0.f;
+  float mx = ok ? v : -INFINITY, mn = ok ? v : INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    smx[threadIdx.x >> 5] = mx;
+    smn[threadIdx.x >> 5] = mn;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mx = fmaxf(fmaxf(smx[0], smx[1]), fmaxf(smx[2], smx[3]));
+    mn = fminf(fminf(smn[0], smn[1]), fminf(smn[2], smn[3]));
+    mtile[blockIdx.x] = mx;
+    if (!(mx - mn <= 96.f)) atomicOr(fallback, 1);  // also catches NaN / inf statistics
+  }
+}
+
+// warp per padded token (lane = 32 contiguous columns of the 1024 = half a head):
+//   D = rowsum(dO o O) -> dsum [B*H, L] (plain, for the two-pass fallback), dneg [B*H, Lp] = -w D (zero past L),
+//   dys [B*L, 1024] = bf16(w dO),  w = 2^(m_tile - lse2)
 __global__ void attn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dy,
-                                      const float* __restrict__ lse, float* __restrict__ lse2n, float* __restrict__ dneg,
+                                      const float* __restrict__ lse, const float* __restrict__ mtile,
+                                      float* __restrict__ dneg, float* __restrict__ dsum, __nv_bfloat16* __restrict__ dys,
                                       int B, int H, int L, int Lp) {
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= B * Lp) return;
   const int b = t / Lp, l = t % Lp;
+  const int hh = lane >> 1;
+  const size_t o = ((size_t)b * H + hh) * Lp + l;
+  if (l >= L) {
+    if ((lane & 1) == 0) dneg[o] = 0.f;
+    return;
+  }
+  const size_t tok = (size_t)b * L + l;
+  const float m = mtile[((size_t)b * H + hh) * (Lp / 128) + l / 128];
+  const float w = exp2f(m - lse[((size_t)b * H + hh) * L + l] * 1.4426950408889634f);
+  const uint4* a = reinterpret_cast<const uint4*>(y + tok * (H * 64) + lane * 32);
+  const uint4* g = reinterpret_cast<const uint4*>(dy + tok * (H * 64) + lane * 32);
+  uint4* gs = reinterpret_cast<uint4*>(dys + tok * (H * 64) + lane * 32);
   float acc = 0.f;
-  if (l < L) {
-    const size_t tok = (size_t)b * L + l;
-    const uint4* a = reinterpret_cast<const uint4*>(y + tok * (H * 64) + lane * 32);
-    const uint4* g = reinterpret_cast<const uint4*>(dy + tok * (H * 64) + lane * 32);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 av = a[i], gv = g[i];
-      const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&av);
-      const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&gv);
+  for (int i = 0; i < 4; ++i) {
+    const uint4 av = a[i], gv = g[i];
+    const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&av);
+    const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&gv);
+    uint32_t sc[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        acc = fmaf(__low2float(ap[k]), __low2float(gp[k]), acc);
-        acc = fmaf(__high2float(ap[k]), __high2float(gp[k]), acc);
-      }
+    for (int k = 0; k < 4; ++k) {
+      const float g0 = __low2float(gp[k]), g1 = __high2float(gp[k]);
+      acc = fmaf(__low2float(ap[k]), g0, acc);
+      acc = fmaf(__high2float(ap[k]), g1, acc);
+      sc[k] = pack_bf16(g0 * w, g1 * w);
     }
+    gs[i] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
   }
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   if ((lane & 1) == 0) {
-    const int hh = lane >> 1;
-    const size_t o = ((size_t)b * H + hh) * Lp + l;
-    dneg[o] = -acc;
-    lse2n[o] = (l < L) ? -lse[((size_t)b * H + hh) * L + l] * 1.4426950408889634f : 0.f;
+    dneg[o] = -w * acc;
+    dsum[((size_t)b * H + hh) * L + l] = acc;
   }
 }
 
 // dq_acc fp32 [T, dh] (unscaled) -> bf16 dq column block of dqkv [T, 3*dh], x 1/sqrt(d)
 __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, size_t n8,
-                                           int dh, float scale) {
+                                           int dh, float scale, const int* __restrict__ fallback) {
+  if (*fallback != 0) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const size_t e = i * 8;
@@ -517,18 +582,38 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_b
                  pack_bf16(bb.x * scale, bb.y * scale), pack_bf16(bb.z * scale, bb.w * scale));
 }
 
-size_t attn_bwd_fused_stats_floats(int B, int L, int H) { return (size_t)2 * B * H * ((L + 127) / 128 * 128); }
+int launch_attn_bwd_gated(const void* qkv, const void* dy, const float* lse, const float* dsum, void* dqkv, int B, int L,
+                          int H, const int* gate, cudaStream_t stream);
+
+static unsigned long long* g_fb_trace = nullptr;
+static int g_fb_trace_cta = 0;
+void attn_bwd_fused_set_trace(unsigned long long* buf, int cta) {
+  g_fb_trace = buf;
+  g_fb_trace_cta = cta;
+}
+
+// scratch layout (floats): dneg [B*H*Lp] | dsum [B*H*L] | mtile [B*H*n_t] | fallback flag (+ padding)
+size_t attn_bwd_fused_stats_floats(int B, int L, int H) {
+  const size_t n_t = (L + 127) / 128;
+  return (size_t)B * H * (n_t * 128 + L + n_t) + 64;
+}
 
 int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* stats, float* dq_acc,
-                          void* dqkv, int B, int L, int H, cudaStream_t stream) {
-  OSD_CHECK(qkv && y && dy && lse && stats && dq_acc && dqkv && B > 0 && L > 0 && H == 16, "attn_bwd_fused: bad arguments");
+                          void* dy_scaled, void* dqkv, int B, int L, int H, cudaStream_t stream) {
+  OSD_CHECK(qkv && y && dy && lse && stats && dq_acc && dy_scaled && dqkv && B > 0 && L > 0 && H == 16,
+            "attn_bwd_fused: bad arguments");
   const int dh = H * 64;
-  const int Lp = (L + 127) / 128 * 128;
-  float* lse2n = stats;
-  float* dneg = stats + (size_t)B * H * Lp;
+  const int n_t = (L + 127) / 128, Lp = n_t * 128;
+  float* dneg = stats;
+  float* dsum = dneg + (size_t)B * H * Lp;
+  float* mtile = dsum + (size_t)B * H * L;
+  int* fallback = reinterpret_cast<int*>(mtile + (size_t)B * H * n_t);
+  OSD_CUDA(cudaMemsetAsync(fallback, 0, sizeof(int), stream));
+  attn_bwd_tilemax_kernel<<<B * H * n_t, 128, 0, stream>>>(lse, mtile, fallback, L, n_t);
+  OSD_LAUNCHED();
   attn_bwd_stats_kernel<<<ceil_div(B * Lp, 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(y),
-                                                                static_cast<const __nv_bfloat16*>(dy), lse, lse2n, dneg, B,
-                                                                H, L, Lp);
+                                                                static_cast<const __nv_bfloat16*>(dy), lse, mtile, dneg,
+                                                                dsum, static_cast<__nv_bfloat16*>(dy_scaled), B, H, L, Lp);
   OSD_LAUNCHED();
   OSD_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * L * dh * sizeof(float), stream));
   AttnBwdFusedParams p;
@@ -542,7 +627,7 @@ int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const 
     uint64_t dims[3] = {(uint64_t)dh, (uint64_t)L, (uint64_t)B};
     uint64_t strides[2] = {(uint64_t)dh * 2, (uint64_t)L * dh * 2};
     uint32_t box[3] = {64, 128, 1};
-    OSD_TRY(make_tmap(&p.tma_dy, dy, 2, 3, dims, strides, box));
+    OSD_TRY(make_tmap(&p.tma_dy, dy_scaled, 2, 3, dims, strides, box));
   }
   {
     uint64_t dims[3] = {(uint64_t)dh, (uint64_t)L, (uint64_t)B};
@@ -550,25 +635,29 @@ int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const 
     uint32_t box[3] = {32, 32, 1};
     OSD_TRY(make_tmap(&p.tma_dq, dq_acc, 4, 3, dims, strides, box));
   }
-  p.lse2n = lse2n;
+  p.mtile = mtile;
   p.dneg = dneg;
+  p.fallback = fallback;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   p.B = B; p.H = H; p.L = L; p.Lp = Lp; p.dh = dh;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.trace = g_fb_trace;
+  p.trace_cta = g_fb_trace_cta;
   static bool attr_set = false;
   if (!attr_set) {
     OSD_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BYTES));
     attr_set = true;
   }
-  const long long grid = (long long)ceil_div(L, 128) * H * B;
+  const long long grid = (long long)n_t * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_bwd_fused: grid too large");
   attn_bwd_fused_kernel<<<(unsigned)grid, FB_THREADS, FB_SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
   const size_t n8 = (size_t)B * L * dh / 8;
-  attn_bwd_dq_convert_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(dq_acc, p.dqkv, n8, dh, p.scale);
+  attn_bwd_dq_convert_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(dq_acc, p.dqkv, n8, dh, p.scale, fallback);
   OSD_LAUNCHED();
-  return 0;
+  // fallback (statistics of a q tile too spread out for the w-scaling): the two-kernel path, gated on the same flag
+  return launch_attn_bwd_gated(qkv, dy, lse, dsum, dqkv, B, L, H, fallback, stream);
 }
 
 }  // namespace osd

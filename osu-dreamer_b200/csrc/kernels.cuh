@@ -72,10 +72,11 @@ int launch_loss(const float* xt, const float* x1, const float* u, const float* v
 int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, void* dqkv, int B,
                     int L, int H, cudaStream_t stream);
 // single-pass backward (attn_bwd_fused.cu): dq_acc fp32 [B*L, H*64] is scratch (zeroed and reduced into here),
-// stats fp32 [attn_bwd_fused_stats_floats()] is scratch (-lse*log2e and -rowsum(dO o O), rows padded to 128)
+// stats fp32 [attn_bwd_fused_stats_floats()] and dy_scaled bf16 [B*L, H*64] are scratch
 size_t attn_bwd_fused_stats_floats(int B, int L, int H);
+void attn_bwd_fused_set_trace(unsigned long long* buf, int cta);  // debugging aid, see osd_debug_attn_bwd_trace
 int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* stats, float* dq_acc,
-                          void* dqkv, int B, int L, int H, cudaStream_t stream);
+                          void* dy_scaled, void* dqkv, int B, int L, int H, cudaStream_t stream);
 int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int variant,
                     cudaStream_t stream);
 int launch_attn_fwd_db(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,

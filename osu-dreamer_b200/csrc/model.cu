@@ -240,7 +240,7 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
 
 // ================================================================================================ backward
 struct BwdPlan {
-  size_t dx, dh, dhn, dvg, dz2, dy, dqkv, dq_acc, dz, dsum, da_tok, a_pre, da_pre, audio_tm, dcond, dfsum, dpre_s;
+  size_t dx, dh, dhn, dvg, dz2, dy, dys, dqkv, dq_acc, dz, dsum, da_tok, a_pre, da_pre, audio_tm, dcond, dfsum, dpre_s;
   size_t gWvg, gWpo, gbvg;  // padded fp32 gradient scratch
   size_t total;
 };
@@ -259,6 +259,7 @@ static BwdPlan make_bwd_plan(int B, int L, int a_batch) {
   p.dvg = take(T * 2 * OSD_HIDP * 2);
   p.dz2 = take(T * 512 * 2);
   p.dy = take(T * 1024 * 2);
+  p.dys = take(T * 1024 * 2);  // w-scaled dO of the single-pass attention backward
   p.dqkv = take(T * 3072 * 2);
   p.dq_acc = take(T * 1024 * 4);  // fp32 dQ accumulator of the single-pass attention backward
   p.dz = take(T * 512 * 2);
@@ -381,7 +382,7 @@ static int pred_backward(const FwdCtx& c, const float* audio, const float* style
     else
       OSD_TRY(launch_attn_bwd_fused(lb + pl.qkv, lb + pl.y, bw + bp.dy, reinterpret_cast<float*>(lb + pl.lse),
                                     reinterpret_cast<float*>(bw + bp.dsum), reinterpret_cast<float*>(bw + bp.dq_acc),
-                                    bw + bp.dqkv, B, L, 16, s));
+                                    bw + bp.dys, bw + bp.dqkv, B, L, 16, s));
     OSD_TRY(launch_qknorm_rope_bwd(bw + bp.dqkv, lb + pl.qkv_raw, c.rope, c.P[lp(l, L_QN_W)], c.P[lp(l, L_KN_W)],
                                    G[lp(l, L_QN_W)], G[lp(l, L_KN_W)], G[lp(l, L_QKV_B)], B, L, s));
     OSD_TRY(gemm_dgrad(bw + bp.dqkv, 3072, c.W.qkv(l), 512, bw + bp.dz, 512, 0, 0, T, 512, 3072, s));
@@ -551,11 +552,16 @@ int osd_attn_bwd(const void* qkv, const void* y, const void* dy, const float* ls
   return launch_attn_bwd(qkv, y, dy, lse, dsum, dqkv, B, L, H, static_cast<cudaStream_t>(stream));
 }
 
+// debugging aid (tools/trace_attn_bwd.py): event timeline of one CTA of the single-pass kernel; buf = device
+// buffer of 3 x 1024 u64 records, or null to switch tracing off
+void osd_debug_attn_bwd_trace(unsigned long long* buf, int cta) { attn_bwd_fused_set_trace(buf, cta); }
+
 size_t osd_attn_bwd_fused_stats_floats(int B, int L, int H) { return attn_bwd_fused_stats_floats(B, L, H); }
 
 int osd_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* stats, float* dq_acc,
-                       void* dqkv, int B, int L, int H, void* stream) {
-  return launch_attn_bwd_fused(qkv, y, dy, lse, stats, dq_acc, dqkv, B, L, H, static_cast<cudaStream_t>(stream));
+                       void* dy_scaled, void* dqkv, int B, int L, int H, void* stream) {
+  return launch_attn_bwd_fused(qkv, y, dy, lse, stats, dq_acc, dy_scaled, dqkv, B, L, H,
+                               static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

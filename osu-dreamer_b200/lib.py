@@ -219,7 +219,8 @@ def attn_bwd_fused(qkv, y, dy, lse, B, L, H=16):
     stats = torch.empty(_sz('osd_attn_bwd_fused_stats_floats', B, L, H), dtype=torch.float32,
                         device=qkv.device)
     dq_acc = torch.empty(B * L, H * 64, dtype=torch.float32, device=qkv.device)
-    _check(load().osd_attn_bwd_fused(ptr(qkv), ptr(y), ptr(dy), ptr(lse), ptr(stats), ptr(dq_acc), ptr(dqkv), c_int(B),
+    dys = torch.empty_like(dy)
+    _check(load().osd_attn_bwd_fused(ptr(qkv), ptr(y), ptr(dy), ptr(lse), ptr(stats), ptr(dq_acc), ptr(dys), ptr(dqkv), c_int(B),
                                      c_int(L), c_int(H), stream()))
     return dqkv
 

@@ -39,6 +39,25 @@ def test_attention_backward_matches_autograd(B, L, fused):
         assert e < 2e-2, (name, e)
 
 
+def test_attention_backward_fused_falls_back_on_spread_statistics():
+    """a query row whose lse is > 96 octaves above its tile neighbours: the single-pass call must detect it on the
+    device and produce the two-kernel result (which makes no assumption on the statistics)"""
+    from osu_dreamer_b200 import lib
+    B, L = 1, 512
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(B * L, 3072, generator=g)
+    qkv[3, :1024] *= 40.0
+    qkv = qkv.cuda().to(torch.bfloat16)
+    dy = torch.randn(B * L, 1024, generator=g).cuda().to(torch.bfloat16)
+    y, lse = lib.attn_fwd(qkv, B, L)
+    assert float(lse.max() - lse.min()) * 1.4427 > 96
+    ref = lib.attn_bwd(qkv, y, dy, lse, B, L)
+    got = lib.attn_bwd_fused(qkv, y, dy, lse, B, L)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all()
+    assert torch.equal(got, ref)
+
+
 def _trainer_grads(sd, inp, x0, t):
     """parameter gradients of the reference loss through the CUDA path (torch ops only for the tiny loss)."""
     from osu_dreamer_b200.denoiser import DiffusionModel, default_args
