@@ -23,19 +23,16 @@
 
 namespace osd {
 
-static constexpr int FB_THREADS = 448;
+static constexpr int FB_THREADS = 320;
+#ifndef OSD_FB_EMU
+#define OSD_FB_EMU 2
+#endif
+static constexpr int FB_EMU = OSD_FB_EMU;  // exponentials computed on the FMA pipe: 0 none, 1 a quarter, 2 half
 static constexpr int FT = 128 * 128;  // bytes of a [128 x 64] bf16 tile
 static constexpr uint32_t FB_TMEM_COLS = 512;
-static constexpr int FB_QST = 3;                      // Q / dO / statistics stages
-static constexpr int FB_STAT_BYTES = FB_QST * 1024;   // per stage: [-lse2 128 | -D 128] fp32
-// smem map (bytes): K 16K | V 16K + 16K (V is only staging for the TMEM copy; afterwards these 32K are the dQ
-// staging tiles, 8 warps x [32 rows x 128 B]) | Q x3 | dO x3 | dS^T x2 (each 2 atoms of [128 kv x 64 q] bf16) | stats
-static constexpr int FB_OFF_V = FT;
-static constexpr int FB_OFF_Q = 3 * FT;
-static constexpr int FB_OFF_DO = FB_OFF_Q + FB_QST * FT;
-static constexpr int FB_OFF_DS = FB_OFF_DO + FB_QST * FT;
-static constexpr int FB_OFF_STAT = FB_OFF_DS + 4 * FT;
-static constexpr int FB_SMEM_TILES = FB_OFF_STAT + FB_STAT_BYTES;
+static constexpr int FB_STAT_BYTES = 2 * 256 * 4;
+static constexpr int FB_STG_BYTES = 8 * 4096;  // 8 softmax warps x [32 rows x 128 B]
+static constexpr int FB_SMEM_TILES = 8 * FT + FB_STG_BYTES + FB_STAT_BYTES;
 static constexpr int FB_SMEM_BYTES = FB_SMEM_TILES + 256 + 1024;
 
 __device__ __forceinline__ float fb_ex2(float x) {
@@ -78,26 +75,25 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
     if (pad + FB_SMEM_TILES + 256 > dyn) __trap();
   }
   uint8_t* sK = smem;
-  uint8_t* sV = smem + FB_OFF_V;
-  uint8_t* sStg = sV;  // aliases V (+16K): V is dead once it has been copied into TMEM
-  uint8_t* sQ = smem + FB_OFF_Q;
-  uint8_t* sDO = smem + FB_OFF_DO;
-  uint8_t* sDS = smem + FB_OFF_DS;  // [2 buffers][2 q-chunks][128 kv rows][64 q] bf16
-  float* sStat = reinterpret_cast<float*>(smem + FB_OFF_STAT);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FB_SMEM_TILES);
+  uint8_t* sV = sK + FT;
+  uint8_t* sQ = sV + FT;        // 2 stages [128 x 64]
+  uint8_t* sDO = sQ + 2 * FT;   // 2 stages
+  uint8_t* sDS = sDO + 2 * FT;  // [2 q-chunks][128 kv rows][64 q] bf16
+  uint8_t* sStg = sDS + 2 * FT;
+  float* sStat = reinterpret_cast<float*>(sStg + FB_STG_BYTES);  // [2 buf][-lse2 128 | -D 128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + FB_STG_BYTES + FB_STAT_BYTES);
   uint64_t* kv_full = bars + 0;
-  uint64_t* q_full = bars + 1;    // [3]
-  uint64_t* q_empty = bars + 4;   // [3]
-  uint64_t* s_full = bars + 7;    // [2 groups]  S^T_i (column group g) complete
-  uint64_t* dp_full = bars + 9;   // [2]         dP^T_i (group g) complete
-  uint64_t* pt_full = bars + 11;  // [2]         P^T_i (group g) written to TMEM
-  uint64_t* ds_full = bars + 13;  // [2]         dS^T_i (group g) written to TMEM + smem
-  uint64_t* dq_full = bars + 15;  // dQ_i complete
-  uint64_t* dq_empty = bars + 16; // dQ_i drained out of TMEM
-  uint64_t* kvt_ready = bars + 17;  // K / V copied into TMEM
-  uint64_t* acc_done = bars + 18;
-  uint64_t* ds_free = bars + 19;  // [2]  dQ_j has consumed dS^T smem buffer j & 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* q_full = bars + 1;    // [2]
+  uint64_t* q_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;    // S^T_i complete
+  uint64_t* dp_full = bars + 6;   // dP^T_i complete
+  uint64_t* pt_full = bars + 7;   // P^T_i written (TMEM)
+  uint64_t* ds_full = bars + 8;   // dS^T_i written (TMEM + smem)
+  uint64_t* dq_full = bars + 9;   // dQ_i complete (also: dS^T smem tile consumed)
+  uint64_t* dq_empty = bars + 10; // dQ_i drained out of TMEM
+  uint64_t* kvt_ready = bars + 11;  // K / V copied into TMEM
+  uint64_t* acc_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_t = (p.L + 127) / 128;  // kv tiles == q tiles
@@ -115,20 +111,16 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
     tma_prefetch_desc(&p.tma_dy);
     tma_prefetch_desc(&p.tma_dq);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < FB_QST; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
     }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(&s_full[g], 1);
-      mbar_init(&dp_full[g], 1);
-      mbar_init(&pt_full[g], 4);
-      mbar_init(&ds_full[g], 4);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(pt_full, 8);
+    mbar_init(ds_full, 8);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 4);
-    mbar_init(&ds_free[0], 1);
-    mbar_init(&ds_free[1], 1);
+    mbar_init(dq_empty, 8);
     mbar_init(kvt_ready, 8);
     mbar_init(acc_done, 1);
     fence_barrier_init();
@@ -148,157 +140,81 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       mbar_expect_tx(kv_full, 2 * FT);
       tma_load_3d(sK, &p.tma_qkv, kv_full, p.dh + h * 64, kv0, b);
       tma_load_3d(sV, &p.tma_qkv, kv_full, 2 * p.dh + h * 64, kv0, b);
-      int qi = i0, st = 0;
-      uint32_t ph = 0;
+      int qi = i0;
       for (int i = 0; i < n_q; ++i) {
-        mbar_wait(&q_empty[st], ph ^ 1);
+        const int st = i & 1;
+        mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
         mbar_expect_tx(&q_full[st], 2 * FT + 512);
         tma_load_3d(sQ + st * FT, &p.tma_qkv, &q_full[st], h * 64, qi * 128, b);
         tma_load_3d(sDO + st * FT, &p.tma_dy, &q_full[st], h * 64, qi * 128, b);
         const size_t so = ((size_t)b * p.H + h) * p.Lp + (size_t)qi * 128;
         bulk_load_1d(sStat + st * 256 + 128, p.dneg + so, 512, &q_full[st]);
         if (++qi == n_q) qi = 0;
-        if (++st == FB_QST) {
-          st = 0;
-          ph ^= 1;
-        }
       }
     }
   } else if (warp == 1) {
     // ================================================================== UMMA issuer
-    // Column group g (q columns [64g, 64g+64) of the tile) has its own S^T / dP^T halves and barriers.  Within a
-    // group the in-order tensor pipe makes the TMEM aliasing (P^T over S^T, dS^T over dP^T) safe: dV(i,g) is issued
-    // before S(i+1,g), dK(i,g) before dP(i+1,g).
     if (elect_one()) {
-      const uint32_t id_s = make_idesc(FMT_BF16, 0, 0, 128, 64);  // S^T, dP^T halves: A in TMEM, B K-major, N = 64 q
-      const uint32_t id_o = make_idesc(FMT_BF16, 0, 1, 128, 64);  // dV, dK: A in TMEM, B MN-major, N = 64 d
-      const uint32_t id_q = make_idesc(FMT_BF16, 1, 1, 128, 64);  // dQ: A = dS MN-major smem, B = K MN-major
+      const uint32_t id_s = make_idesc(FMT_BF16, 0, 0, 128, 128);  // S^T, dP^T: A in TMEM, B K-major, N = 128 q
+      const uint32_t id_o = make_idesc(FMT_BF16, 0, 1, 128, 64);   // dV, dK  : A in TMEM, B MN-major, N = 64 d
+      const uint32_t id_q = make_idesc(FMT_BF16, 1, 1, 128, 64);   // dQ      : A = dS MN-major smem, B = K MN-major
       const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320;
       const uint32_t tDQ = tmem_base + 384, tK = tmem_base + 448, tV = tmem_base + 480;
-      const uint32_t aK = smem_u32(sK), aDS = smem_u32(sDS), aQ0 = smem_u32(sQ), aDO0 = smem_u32(sDO);
-      uint32_t dv_acc = 0, dk_acc = 0;
-      // tile i lives in stage i % 3
-      auto issue_s = [&](int g, int st) {  // S^T(.,g) = K Q^T over q rows [64g, +64)
-        const uint32_t aQ = aQ0 + st * FT + g * 8192;
+      const uint32_t aK = smem_u32(sK), aDS = smem_u32(sDS);
+      auto issue_s = [&](int i) {
+        const int st = i & 1;
+        mbar_wait(&q_full[st], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ + st * FT);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ts(tS + g * 64, tK + k * 8, make_smem_desc(aQ + k * 32, 0, 1024), id_s, k > 0);
-        umma_commit(&s_full[g]);
+        for (int k = 0; k < 4; ++k) umma_f16_ts(tS, tK + k * 8, make_smem_desc(aQ + k * 32, 0, 1024), id_s, k > 0);
+        umma_commit(s_full);
       };
-      auto issue_dp = [&](int g, int st) {  // dP^T(.,g) = V dO^T
-        const uint32_t aDO = aDO0 + st * FT + g * 8192;
+      auto issue_dp = [&](int i) {
+        const uint32_t aDO = smem_u32(sDO + (i & 1) * FT);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ts(tDP + g * 64, tV + k * 8, make_smem_desc(aDO + k * 32, 0, 1024), id_s, k > 0);
-        umma_commit(&dp_full[g]);
+        for (int k = 0; k < 4; ++k) umma_f16_ts(tDP, tV + k * 8, make_smem_desc(aDO + k * 32, 0, 1024), id_s, k > 0);
+        umma_commit(dp_full);
       };
-      auto issue_dv = [&](int g, int st) {  // dV += P^T(.,g) dO[64g.., :]
-        const uint32_t aDO = aDO0 + st * FT + g * 8192;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_f16_ts(tDV, tS + g * 64 + k * 8, make_smem_desc(aDO + k * 16 * 128, 0, 1024), id_o, dv_acc);
-          dv_acc = 1;
-        }
-      };
-      auto issue_dk = [&](int g, int st) {  // dK += dS^T(.,g) Q[64g.., :]
-        const uint32_t aQ = aQ0 + st * FT + g * 8192;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_f16_ts(tDK, tDP + g * 64 + k * 8, make_smem_desc(aQ + k * 16 * 128, 0, 1024), id_o, dk_acc);
-          dk_acc = 1;
-        }
-      };
-      // Event-driven issue: each column group's chain  [P^T_i] dV(i,g) S(i+1,g)  ->  [dS^T_i] dK(i,g) dP(i+1,g)  advances
-      // as soon as its own barrier completes (polled, never blocking the other group); dQ_j is issued once both
-      // groups have produced dS^T_j and dQ_{j-1} has left TMEM.  Group 1's first tile is held back until group 0 has
-      // finished its first exponential phase, which puts the two groups about half a tile period apart.
       mbar_wait(kvt_ready, 0);
-      mbar_wait(&q_full[0], 0);
       tc_fence_after();
-      issue_s(0, 0);
-      issue_dp(0, 0);
-      int ti[2] = {0, 0};        // tile whose event group g is waiting for
-      int stg_of[2] = {0, 0};    // stage of that tile
-      uint32_t qph[2] = {0, 0};  // q_full parity of that stage
-      bool want_ds[2] = {false, false};
-      bool s_pend[2] = {false, false};  // S(i+1,g) waiting for its Q stage (never blocks the other group's chain)
-      int s_st[2] = {0, 0};
-      uint32_t s_ph[2] = {0, 0};
-      bool started1 = true;
-      issue_s(1, 0);
-      issue_dp(1, 0);
-      int dk_done[2] = {0, 0};  // tiles whose dK (last reader of the Q / dO stage) has been issued
-      int released = 0, rel_st = 0, dq_next = 0;
-      while (ti[0] < n_q || ti[1] < n_q || dq_next < n_q) {
+      issue_s(0);
+      issue_dp(0);
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i & 1;
+        const uint32_t aQ = smem_u32(sQ + st * FT), aDO = smem_u32(sDO + st * FT);
+        const uint32_t acc = i > 0 ? 1u : 0u;
+        mbar_wait(pt_full, i & 1);
+        tc_fence_after();
+        FB_TRACE(0, 10, i);
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (s_pend[g] && mbar_try_wait(&q_full[s_st[g]], s_ph[g])) {
-            tc_fence_after();
-            FB_TRACE(0, 14 + g, ti[g]);
-            issue_s(g, s_st[g]);
-            s_pend[g] = false;
-          }
-          if (ti[g] >= n_q || (g == 1 && !started1)) continue;
-          const int i = ti[g], st = stg_of[g];
-          if (!want_ds[g]) {
-            if (!mbar_try_wait(&pt_full[g], i & 1)) continue;
-            tc_fence_after();
-            FB_TRACE(0, 10 + g, i);
-            issue_dv(g, st);
-            if (i + 1 < n_q) {  // S(i+1,g) follows as soon as Q_{i+1} has landed (polled below)
-              s_pend[g] = true;
-              s_st[g] = st + 1;
-              s_ph[g] = qph[g];
-              if (s_st[g] == FB_QST) {
-                s_st[g] = 0;
-                s_ph[g] ^= 1;
-              }
-            }
-            want_ds[g] = true;
-            if (g == 0 && !started1) {
-              started1 = true;
-              issue_s(1, 0);
-              issue_dp(1, 0);
-            }
-          } else {
-            if (!mbar_try_wait(&ds_full[g], i & 1)) continue;
-            tc_fence_after();
-            FB_TRACE(0, 12 + g, i);
-            issue_dk(g, st);
-            int sn = st + 1;
-            if (sn == FB_QST) {
-              sn = 0;
-              qph[g] ^= 1;
-            }
-            if (i + 1 < n_q) issue_dp(g, sn);
-            dk_done[g] = i + 1;
-            stg_of[g] = sn;
-            ti[g] = i + 1;
-            want_ds[g] = false;
-          }
-        }
-        const int both = dk_done[0] < dk_done[1] ? dk_done[0] : dk_done[1];
-        if (released < both) {  // every MMA that reads stage rel_st has been issued
-          umma_commit(&q_empty[rel_st]);
-          ++released;
-          if (++rel_st == FB_QST) rel_st = 0;
-        }
-        if (dq_next < both && (dq_next == 0 || mbar_try_wait(dq_empty, (dq_next - 1) & 1))) {
+        for (int k = 0; k < 8; ++k)  // dV += P^T_i dO_i : q (K dim) chunk k lives at columns (k/4)*64 + (k%4)*8
+          umma_f16_ts(tDV, tS + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc(aDO + k * 16 * 128, 0, 1024), id_o,
+                      (k > 0) ? 1u : acc);
+        if (i + 1 < n_q) issue_s(i + 1);  // overwrites P^T_i only after dV_i has read it
+        mbar_wait(ds_full, i & 1);
+        tc_fence_after();
+        FB_TRACE(0, 12, i);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16_ts(tDK, tDP + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc(aQ + k * 16 * 128, 0, 1024), id_o,
+                      (k > 0) ? 1u : acc);
+        umma_commit(&q_empty[st]);
+        if (i + 1 < n_q) issue_dp(i + 1);  // overwrites dS^T_i (TMEM) only after dK_i has read it
+        if (i > 0) {
+          mbar_wait(dq_empty, (i - 1) & 1);
           tc_fence_after();
-          const uint32_t a = aDS + (dq_next & 1) * 2 * FT;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)  // dQ_j = dS_j K : contraction over the 128 kv rows, 16 per instruction
-            umma_f16_ss(tDQ, make_smem_desc(a + k * 16 * 128, FT, 1024), make_smem_desc(aK + k * 16 * 128, 0, 1024), id_q,
-                        k > 0);
-          umma_commit(dq_full);
-          umma_commit(&ds_free[dq_next & 1]);
-          FB_TRACE(0, 16, dq_next);
-          ++dq_next;
         }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ_i = dS_i K : contraction over the 128 kv rows, 16 per instruction
+          umma_f16_ss(tDQ, make_smem_desc(aDS + k * 16 * 128, FT, 1024), make_smem_desc(aK + k * 16 * 128, 0, 1024), id_q,
+                      k > 0);
+        umma_commit(dq_full);
+        FB_TRACE(0, 16, i);
       }
       umma_commit(acc_done);
     }
-  } else if (warp < 10) {
+  } else {
     // ================================================================== softmax (thread = kv row, 64 q columns)
     const int quad = warp & 3;
     const int grp = (warp - 2) >> 2;   // q-column group: columns [64 grp, 64 grp + 64)
@@ -324,31 +240,68 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
     const uint32_t ds_row = smem_u32(sDS) + grp * FT + row * 128;
     const int sw = row & 7;
     const float c = p.scale_log2;
-    uint64_t* my_s_full = &s_full[grp];
-    uint64_t* my_dp_full = &dp_full[grp];
-    uint64_t* my_pt_full = &pt_full[grp];
-    uint64_t* my_ds_full = &ds_full[grp];
-    int qt = i0, stq = 0;
+    // dQ drain: this warp moves rows [32 quad, +32) x columns [32 grp, +32) of the finished dQ tile j (q tile qj)
+    const uint32_t tDQ = tmem_base + 384 + lane_off + grp * 32;
+    uint8_t* stg = sStg + (warp - 2) * 4096;
+    const uint32_t stg_row = smem_u32(stg) + lane * 128;
+    // part 1: TMEM -> registers -> staging smem (the proxy fence is shared with the dS^T smem writes of phase 2);
+    // part 2 (after that fence): one lane issues the TMA reduce-add
+    auto drain_load = [&](int j) {
+      mbar_wait(dq_full, j & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(tDQ, r);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(dq_empty);
+        tma_store_wait_read<0>();  // the previous reduce-add of this warp has read the staging tile
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((u ^ (lane & 7)) << 4)), "r"(r[4 * u]),
+                     "r"(r[4 * u + 1]), "r"(r[4 * u + 2]), "r"(r[4 * u + 3])
+                     : "memory");
+    };
+    auto drain_issue = [&](int qj) {
+      if (lane == 0) {
+        tma_reduce_add_3d(&p.tma_dq, stg, h * 64 + grp * 32, qj * 128 + quad * 32, b);
+        tma_store_commit();
+      }
+    };
+    int qt = i0, qprev = i0;
     const float* mrow = p.mtile + (size_t)bh * n_q;
     float m_cur = __ldg(mrow + qt);
+    const bool trw = quad == 2;  // traced warps: 2 (group 0) and 6 (group 1)
     for (int i = 0; i < n_q; ++i) {
-      // -w D of this q tile, bulk-copied on the same barrier as Q_i / dO_i (complete before S^T_i)
-      const float* st = sStat + stq * 256 + grp * 64;
-      const float m_next = __ldg(mrow + (qt + 1 == n_q ? 0 : qt + 1));  // consumed one tile later
+      // -w D of this q tile, bulk-copied on the same barrier as Q_i / dO_i (complete before S^T_i was issued)
+      const float* st = sStat + (i & 1) * 256 + grp * 64;
+      int qn = qt + 1;
+      if (qn == n_q) qn = 0;
+      const float m_next = __ldg(mrow + qn);  // consumed one tile later
       // ---- phase 1: P~^T = exp2(S^T * c - m),  m = max lse2 of the q tile: no per-column statistic; the factor
       //      w[q] = 2^(m - lse2[q]) that turns P~ into P is folded into dO (dO~ = w dO) and D (D~ = w D)
-      const bool trw = quad == 2;  // warps 2 (group 0) and 6 (group 1)
       if (trw) FB_TRACE(1 + grp, 0, i);
-      mbar_wait(my_s_full, i & 1);
+      mbar_wait(s_full, i & 1);
       tc_fence_after();
       if (trw) FB_TRACE(1 + grp, 1, i);
       float pt[64];
+      uint32_t rsb[2][32];
+      __syncwarp();
+      tmem_ld32(tS, rsb[0]);
+      tmem_wait_ld();
 #pragma unroll
       for (int cch = 0; cch < 2; ++cch) {
-        uint32_t rs[32];
-        __syncwarp();
-        tmem_ld32(tS + cch * 32, rs);
-        tmem_wait_ld();
+        const uint32_t(&rs)[32] = rsb[cch];
+        if (cch == 0) {
+          __syncwarp();
+          tmem_ld32(tS + 32, rsb[1]);  // second half streams out of TMEM while the first half is processed
+        } else {
+          tmem_wait_ld();
+        }
         const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_cur, -m_cur);
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
@@ -356,8 +309,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
           const float2 bb = ffma2(make_float2(__uint_as_float(rs[k4 * 4 + 2]), __uint_as_float(rs[k4 * 4 + 3])), c2, nm2);
           pt[cch * 32 + k4 * 4 + 0] = fb_ex2(a.x);
           pt[cch * 32 + k4 * 4 + 1] = fb_ex2(a.y);
-          pt[cch * 32 + k4 * 4 + 2] = fb_ex2(bb.x);
-          pt[cch * 32 + k4 * 4 + 3] = fb_ex2(bb.y);
+          if (FB_EMU == 2 || (FB_EMU == 1 && (k4 & 1))) {  // this pair on the FMA pipe instead of the SFU
+            const float2 e = ex2_poly2(bb);
+            pt[cch * 32 + k4 * 4 + 2] = e.x;
+            pt[cch * 32 + k4 * 4 + 3] = e.y;
+          } else {
+            pt[cch * 32 + k4 * 4 + 2] = fb_ex2(bb.x);
+            pt[cch * 32 + k4 * 4 + 3] = fb_ex2(bb.y);
+          }
         }
         uint32_t pk[16];
 #pragma unroll
@@ -367,20 +326,27 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(my_pt_full);
+      if (lane == 0) mbar_arrive(pt_full);
       if (trw) FB_TRACE(1 + grp, 2, i);
       // ---- phase 2: dS^T = P~^T o (dP~^T - D~[q])   (1/sqrt(d) is applied to the dK / dQ results on the way out)
-      mbar_wait(my_dp_full, i & 1);
+      if (i > 0) drain_load(i - 1);  // also: dQ_{i-1} has consumed the dS^T smem tile
+      if (trw) FB_TRACE(1 + grp, 3, i);
+      mbar_wait(dp_full, i & 1);
       tc_fence_after();
       if (trw) FB_TRACE(1 + grp, 4, i);
-      if (i > 1) mbar_wait(&ds_free[i & 1], ((i - 2) >> 1) & 1);  // dQ_{i-2} has read dS^T smem buffer i & 1
-      const uint32_t ds_dst = ds_row + (i & 1) * 2 * FT;
+      uint32_t rpb[2][32];
+      __syncwarp();
+      tmem_ld32(tDP, rpb[0]);
+      tmem_wait_ld();
 #pragma unroll
       for (int cch = 0; cch < 2; ++cch) {
-        uint32_t rp[32];
-        __syncwarp();
-        tmem_ld32(tDP + cch * 32, rp);
-        tmem_wait_ld();
+        const uint32_t(&rp)[32] = rpb[cch];
+        if (cch == 0) {
+          __syncwarp();
+          tmem_ld32(tDP + 32, rpb[1]);
+        } else {
+          tmem_wait_ld();
+        }
         const float4* d4 = reinterpret_cast<const float4*>(st + 128 + cch * 32);
         uint32_t pk[16];
 #pragma unroll
@@ -398,7 +364,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
         tmem_st16(tDP + cch * 16, pk);  // TMEM copy: A operand of dK += dS^T Q_i
 #pragma unroll
         for (int u4 = 0; u4 < 4; ++u4)  // smem copy (row = kv, 64 q contiguous): MN-major A operand of dQ_i = dS_i K
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_dst + (((cch * 4 + u4) ^ sw) << 4)),
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + (((cch * 4 + u4) ^ sw) << 4)),
                        "r"(pk[4 * u4]), "r"(pk[4 * u4 + 1]), "r"(pk[4 * u4 + 2]), "r"(pk[4 * u4 + 3])
                        : "memory");
       }
@@ -406,12 +372,17 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(my_ds_full);
+      if (lane == 0) mbar_arrive(ds_full);
       if (trw) FB_TRACE(1 + grp, 5, i);
+      if (i > 0) drain_issue(qprev);
+      qprev = qt;
+      qt = qn;
       m_cur = m_next;
-      if (++qt == n_q) qt = 0;
-      if (++stq == FB_QST) stq = 0;
     }
+    drain_load(n_q - 1);
+    fence_proxy_async_smem();
+    __syncwarp();
+    drain_issue(qprev);
     // ---- epilogue: group 0 writes dK (x scale), group 1 writes dV
     mbar_wait(acc_done, 0);
     tc_fence_after();
@@ -437,50 +408,6 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       }
     }
     tc_fence_before();
-  } else {
-    // ================================================================== dQ drain (warp = 32 q rows x 64 d columns)
-    // TMEM -> registers -> swizzled smem staging -> TMA reduce-add into the fp32 dQ accumulator, as soon as dQ_j is
-    // complete: the next dQ can be issued a few hundred cycles later, independently of the softmax warps
-    const int quad = warp & 3;
-    const uint32_t tDQ = tmem_base + 384 + (static_cast<uint32_t>(quad * 32) << 16);
-    uint8_t* stg = sStg + (warp - 10) * 8192;
-    uint32_t n_st = 0;
-    int qt = i0;
-    for (int j = 0; j < n_q; ++j) {
-      mbar_wait(dq_full, j & 1);
-      tc_fence_after();
-      uint32_t r0[32], r1[32];
-      __syncwarp();
-      tmem_ld32(tDQ, r0);
-      tmem_ld32(tDQ + 32, r1);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dq_empty);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint8_t* buf = stg + (n_st & 1) * 4096;
-        if (n_st >= 2) {
-          if (lane == 0) tma_store_wait_read<1>();  // the reduce-add that used this buffer two stores ago has read it
-          __syncwarp();
-        }
-        const uint32_t rowb = smem_u32(buf) + lane * 128;
-        const uint32_t* w = half == 0 ? r0 : r1;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((u ^ (lane & 7)) << 4)), "r"(w[4 * u]),
-                       "r"(w[4 * u + 1]), "r"(w[4 * u + 2]), "r"(w[4 * u + 3])
-                       : "memory");
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_reduce_add_3d(&p.tma_dq, buf, h * 64 + half * 32, qt * 128 + quad * 32, b);
-          tma_store_commit();
-        }
-        ++n_st;
-      }
-      if (++qt == n_q) qt = 0;
-    }
     if (lane == 0) tma_store_wait<0>();
     __syncwarp();
   }

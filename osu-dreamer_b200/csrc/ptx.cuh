@@ -289,6 +289,24 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return upk2(rd);
 }
 
+// 2^x for a pair on the FMA / ALU pipes (no SFU): Cody-Waite split x = n + f with the 1.5*2^23 trick, degree-3
+// minimax polynomial of 2^f on [-0.5, 0.5] (max relative error 7.5e-5 -- the results are rounded to bf16 afterwards),
+// exponent patched in with an integer add.  x is clamped to >= -126 (result ~1e-38 instead of a wrapped exponent).
+// Lets the attention kernels split their exponentials between the SFU (16 / clk / SM) and the FMA pipe.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 t = fadd2(x, magic);                                          // low mantissa bits = round(x)
+  const float2 r = fadd2(t, make_float2(-12582912.f, -12582912.f));          // round(x) as a float
+  const float2 f = ffma2(r, make_float2(-1.f, -1.f), x);                     // x - round(x)
+  float2 p = ffma2(f, make_float2(0.055171650f, 0.055171650f), make_float2(0.24261113f, 0.24261113f));
+  p = ffma2(p, f, make_float2(0.69326097f, 0.69326097f));
+  p = ffma2(p, f, make_float2(0.99992806f, 0.99992806f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
 // ----------------------------------------------------------------------------- small math helpers
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
