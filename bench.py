@@ -290,13 +290,23 @@ def run_cuda(args):
                     'attn_bwd_fused': {'ms': ms_b, 'tflops': 2 * fl_f / ms_b / 1e9}}
             dom = 'attn_bwd_fused' if 8 * ms_b > 8 * ms_f else 'attn_fwd'
             ach = kern[dom]['tflops']
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact shape (B=16, L=8192), from the
+            # committed ncu --set full capture profiles/r01h_ncu_attention_summary.json
+            ncu_traffic = {'attn_bwd_fused': 1.622335e9 + 1.030786e9, 'attn_fwd': 0.805537e9 + 0.259025e9}
+            alg_bytes = {'attn_bwd_fused': Ba * L * (3072 * 2 + 1024 * 2 + 2048 * 2 + 1024 * 4),  # q,k,v + dO~ in; dk,dv + fp32 dq out
+                         'attn_fwd': Ba * L * (3072 * 2 + 1024 * 2)}
             line['roofline'] = {'bound': 'tensor', 'kernel': dom, 'achieved': ach, 'peak': peaks['tf_burst'],
-                                'unit': 'TFLOP/s', 'frac': ach / peaks['tf_burst'], 'traffic': None,
+                                'unit': 'TFLOP/s', 'frac': ach / peaks['tf_burst'],
+                                'traffic': ncu_traffic[dom] if (Ba, L) == (16, 8192) else None,
                                 'peak_source': peaks['source'] + ', burst (kernel timed alone)',
-                                'traffic_note': 'ncu --set full at B=4, L=4096 (profiles/r01_ncu_attention_summary.json): dq kernel '
-                                                'dram read+write 156 MB vs 168 MB algorithmic (q,k,v,dO read + dq write) -> no re-read waste',
-                                'sfu_note': 'd=64 attention is SFU-bound before it is tensor-bound: 16384 ex2 per 128x128 tile = 1024 clk/SM '
-                                            'vs 512 clk of tcgen05 time -> kernel ceiling ~1.15 PFLOP/s (DESIGN.md 5)',
+                                'traffic_note': 'DRAM bytes per launch from ncu (profiles/r01h_ncu_attention_summary.json) vs '
+                                                f'{alg_bytes[dom] / 1e9:.2f} GB algorithmic: the fp32 dQ accumulator is partly evicted and '
+                                                're-read between its TMA reduce-adds (1.2x); K/V/Q/dO re-reads are served by L2',
+                                'flop_convention': 'algorithmic = 2 x forward (SURVEY 8(d)); the single-pass kernel executes 2.5 x forward '
+                                                   '(5 GEMMs: S, dP, dV, dK, dQ), so its tensor pipe runs at 1.25 x the quoted rate',
+                                'limits_note': 'd=64 attention: per 128x128 score tile 16384 exponentials = 1024 clk of SFU against 1408 clk of '
+                                               'tcgen05 time (backward) / 512 clk (forward); under load the B200 sits at its 1000 W power cap '
+                                               '(sm clock 1.6-1.8 GHz of 1.965), see DESIGN.md 5',
                                 'algorithmic_flops_per_launch': (2 * fl_f if dom != 'attn_fwd' else fl_f),
                                 'kernels': kern,
                                 'share_of_step': {k: 8 * v['ms'] / (sec / args.steps * 1e3) for k, v in kern.items()}}

@@ -11,6 +11,11 @@
 
 namespace osd {
 
+#ifndef OSD_DB_EMU
+#define OSD_DB_EMU 0
+#endif
+static constexpr bool DB_EMU = OSD_DB_EMU != 0;
+
 static constexpr int DB_THREADS = 192;
 static constexpr int DB_T128 = 128 * 128;
 static constexpr int DB_T64 = 64 * 128;
@@ -186,7 +191,8 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
           const float2 a = ffma2(make_float2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])), c2, n2);
           const float2 bb = ffma2(make_float2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])), c2, n2);
           const float2 ea = make_float2(db_ex2(a.x), db_ex2(a.y));
-          const float2 eb = make_float2(db_ex2(bb.x), db_ex2(bb.y));
+          // half of the exponentials on the FMA pipe (ex2_poly2): the SFU (16 ex2 / clk / SM) is the binding unit at d = 64
+          const float2 eb = DB_EMU ? ex2_poly2(bb) : make_float2(db_ex2(bb.x), db_ex2(bb.y));
           s01 = fadd2(s01, ea);
           s23 = fadd2(s23, eb);
           pk[i >> 1] = pack_bf16(ea.x, ea.y);

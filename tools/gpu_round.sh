@@ -9,6 +9,6 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_ou
 cat gpurun_out/${TAG}_bench.json | cut -c1-1500
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-sampling --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_ --launch-skip 4 -c 4 -f -o gpurun_out/${TAG}_attn \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_ --launch-skip 7 -c 7 -f -o gpurun_out/${TAG}_attn \
     python tools/prof_attn.py 16 8192 > gpurun_out/${TAG}_ncu_attn.log 2>&1
 ls -la gpurun_out
