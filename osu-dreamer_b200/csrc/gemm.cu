@@ -7,10 +7,12 @@
 #include "gemm.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace osd {
 
 static constexpr int BM = 128;
-static constexpr int GEMM_THREADS = 192;
+// threads = 64 (producer + issuer warps) + 32 per epilogue warp (EW = 4 or 8)
 static constexpr int ROW_BYTES = 128;  // one swizzle row: 64 bf16 or 32 tf32
 
 struct GemmParams {
@@ -40,24 +42,28 @@ struct GemmParams {
   void* raw_out;
 };
 
-template <int BN, int ELEM>
+// EW = epilogue warps.  With 4 (one per SM sub-partition) the epilogue is a single latency-bound instruction stream per
+// sub-partition; short-K GEMMs (K <= 1024: qkv, vg, the dgrads) are epilogue-bound that way, so they run with 8 (two
+// warps per lane quadrant, alternating column chunks) and pay for the extra staging with one pipeline stage.
+template <int BN, int ELEM, int EW>
 struct Cfg {
+  static constexpr int THREADS = 64 + 32 * EW;
   static constexpr int EPR = (ELEM == ELEM_BF16) ? 64 : 32;  // elements per 128-byte row
   static constexpr int BK = EPR;                             // k-extent of one stage (elements)
   static constexpr int UMMA_K = EPR / 4;                     // 32 bytes of K per instruction
   static constexpr int A_BYTES = BM * ROW_BYTES;             // 16 KB
   static constexpr int B_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? (EW == 8 ? 3 : 4) : (EW == 8 ? 5 : 6);
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulators (power of two: 256 or 512)
-  static constexpr int STG_BYTES = 4 * 2 * 4096;  // epilogue staging: 4 warps x 2 buffers x [32 rows x 128 B]
+  static constexpr int STG_BYTES = EW * 2 * 4096;  // epilogue staging: EW warps x 2 buffers x [32 rows x 128 B]
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // ---------------------------------------------------------------------------------------------------
-template <int BN, int ELEM, bool QKV>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN, ELEM>;
+template <int BN, int ELEM, bool QKV, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<BN, ELEM, EW>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -82,7 +88,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], EW);
     }
     fence_barrier_init();
   }
@@ -194,6 +200,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     // M and columns past N are clipped by the tensor map.
     const int quad = warp & 3;
     uint8_t* stg = stg_base + (warp - 2) * 8192;
+    constexpr int NSUB = EW / 4;         // warps per lane quadrant
+    const int sub = (warp - 2) >> 2;     // this warp takes the column chunks c with c % NSUB == sub
     uint32_t n_st = 0;  // stores issued by this warp (staging buffer = n_st & 1)
     auto stage_out = [&](const CUtensorMap* map, const uint32_t (&w)[32], int c0, int r0, bool reduce) {
       uint8_t* buf = stg + (n_st & 1) * 4096;
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         const float eps = 1.1920929e-07f;  // torch.finfo(float32).eps: nn.RMSNorm(eps=None)
         const int pos = (m < p.M) ? (m % p.L) : 0;
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = sub; c < BN / 64; c += NSUB) {
           const int n0 = tn * BN + c * 64;
           uint32_t r0v[32], r1v[32];
           __syncwarp();
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       } else if (p.c_fp32) {
         // fp32 output (or fp32 reduce-add): 32 columns = 128 bytes per row segment
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = sub; c < BN / 32; c += NSUB) {
           const int n0 = tn * BN + c * 32;
           uint32_t r[32];
           __syncwarp();
@@ -328,7 +336,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       } else {
         // bf16 output: 64 columns = 128 bytes per row segment
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = sub; c < BN / 64; c += NSUB) {
           const int n0 = tn * BN + c * 64;
           uint32_t ra[32], rb[32];
           __syncwarp();
@@ -386,9 +394,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int BN, int ELEM, bool QKV>
+template <int BN, int ELEM, bool QKV, int EW>
 static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
-  using C = Cfg<BN, ELEM>;
+  using C = Cfg<BN, ELEM, EW>;
   GemmParams p;
   const int eb = (ELEM == ELEM_BF16) ? 2 : 4;
   // A operand
@@ -437,7 +445,7 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   p.dh = a.dh;
   p.raw_out = a.raw_out;
 
-  auto kern = gemm_kernel<BN, ELEM, QKV>;
+  auto kern = gemm_kernel<BN, ELEM, QKV, EW>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     OSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -445,7 +453,7 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   }
   const int total = p.tiles_m * p.tiles_n * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(p);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
   return 0;
 }
@@ -466,18 +474,26 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     OSD_CHECK(a.elem == ELEM_BF16 || a.elem == ELEM_TF32, "gemm: bad elem");
     OSD_CHECK(a.N % 64 == 0 && a.dh % 64 == 0 && a.bias && a.qnorm_w && a.knorm_w && a.rope && a.L > 0 && !a.c_fp32,
               "gemm: EPI_QKV arguments incomplete");
-    if (a.elem == ELEM_BF16) return launch_cfg<256, ELEM_BF16, true>(a, stream);
-    return launch_cfg<256, ELEM_TF32, true>(a, stream);
+    if (a.elem == ELEM_BF16) return launch_cfg<256, ELEM_BF16, true, 8>(a, stream);
+    return launch_cfg<256, ELEM_TF32, true, 4>(a, stream);
   }
   // narrow tiles when the wide ones cannot fill the machine or N is not a multiple of 256
   const int wide_items = ceil_div(a.M, BM) * ceil_div(a.N, 256) * (a.split_k < 1 ? 1 : a.split_k);
   const bool narrow = (a.N % 256 != 0) || wide_items < num_sms();
+  // k-blocks per work item: short main loops cannot hide a 4-warp epilogue (OSD_GEMM_EW=4 forces the old layout)
+  const int kphys = (a.split3 ? 3 : 1) * ceil_div(a.K, 64);
+  const int kb_item = ceil_div(kphys, a.split_k < 1 ? 1 : a.split_k);
+  static const bool ew4_only = [] {
+    const char* e = getenv("OSD_GEMM_EW");
+    return e != nullptr && e[0] == '4';
+  }();
+  const bool wide_epi = kb_item <= 24 && !ew4_only;
   if (a.elem == ELEM_BF16) {
-    if (narrow) return launch_cfg<128, ELEM_BF16, false>(a, stream);
-    return launch_cfg<256, ELEM_BF16, false>(a, stream);
+    if (narrow) return wide_epi ? launch_cfg<128, ELEM_BF16, false, 8>(a, stream) : launch_cfg<128, ELEM_BF16, false, 4>(a, stream);
+    return wide_epi ? launch_cfg<256, ELEM_BF16, false, 8>(a, stream) : launch_cfg<256, ELEM_BF16, false, 4>(a, stream);
   } else {
-    if (narrow) return launch_cfg<128, ELEM_TF32, false>(a, stream);
-    return launch_cfg<256, ELEM_TF32, false>(a, stream);
+    if (narrow) return launch_cfg<128, ELEM_TF32, false, 4>(a, stream);
+    return launch_cfg<256, ELEM_TF32, false, 4>(a, stream);
   }
 }
 
