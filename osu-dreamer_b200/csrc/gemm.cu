@@ -487,7 +487,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     const char* e = getenv("OSD_GEMM_EW");
     return e != nullptr && e[0] == '4';
   }();
-  const bool wide_epi = kb_item <= 24 && !ew4_only;
+  const bool wide_epi = kb_item <= 8 && !ew4_only;  // K <= 512: measured faster with 8 (tools/gemm_ab.py); K >= 1024 slower
   if (a.elem == ELEM_BF16) {
     if (narrow) return wide_epi ? launch_cfg<128, ELEM_BF16, false, 8>(a, stream) : launch_cfg<128, ELEM_BF16, false, 4>(a, stream);
     return wide_epi ? launch_cfg<256, ELEM_BF16, false, 8>(a, stream) : launch_cfg<256, ELEM_BF16, false, 4>(a, stream);
