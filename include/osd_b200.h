@@ -149,6 +149,8 @@ OSD_API int osd_attn_bwd_fused(const void* qkv, const void* y, const void* dy, c
 /* Debugging aid (tools/trace_attn_bwd.py): record the event timeline of CTA `cta` of the single-pass attention
  * backward into buf (DEVICE memory, 3 x 1024 u64 records: (event << 48) | (tile << 32) | SM clock); null = off. */
 OSD_API void osd_debug_attn_bwd_trace(unsigned long long* buf, int cta);
+/* same for the forward kernel variant 5 (2 x 1024 records) */
+OSD_API void osd_debug_attn_fwd_trace(unsigned long long* buf, int cta);
 
 /* Gradient of DiffusionModel.forward (what autograd computes for the reference at train.py:84 + Lightning's
  * backward): given du [B] and dv [B,6,L], ACCUMULATES the parameter gradients into grads[164] (HOST array of

@@ -1,30 +1,33 @@
-// Flash attention forward, variant "db": two S accumulators in TMEM ping-pong, so the QK^T MMA of tile j+1 (and
-// j+2) runs while the softmax warps are still working on tile j -- the softmax never waits for the tensor pipe
-// and the SFU (the binding unit at head_dim 64) stays busy.  Profile that motivated it (ncu, variant 2):
-// 20 % of all warp samples sat on the s_full wait because the co-resident CTAs fall into lockstep.
-//   CTA = 128 q rows of one (b,h); 64-row kv tiles, 3-stage K/V ring; 2 CTAs/SM (192 of 256 TMEM columns)
-//   TMEM: S0 cols [0,64) | S1 [64,128) | O [128,192); bf16 P_j is written back over the first 32 columns of
-//         S_{j&1} and consumed from there as the A operand of O += P_j V_j; S_{j+2} is issued right after that MMA
-//         (in-order tensor pipe), so the aliasing is safe.
+// Flash attention forward, variant "w8" (fixed-bound softmax only): the "db" layout (attn_fwd_db.cu: two S
+// accumulators in TMEM ping-pong, 64-row kv tiles, 3-stage K/V ring, 2 CTAs/SM) with EIGHT softmax warps per CTA --
+// two per TMEM lane quadrant, each owning 32 of the 64 score columns of a tile.  With four warps the per-tile
+// instruction stream of a softmax warp (~400 dependent instructions) is the critical path and moving exponentials to
+// the FMA pipe only lengthens it; with eight, four warps per SM sub-partition hide each other's latencies, and half of
+// the exponentials run on the FMA pipe (ex2_poly2) so the SFU (16 ex2 / clk / SM) is no longer the binding unit.
+//   TMEM: S0 cols [0,64) | S1 [64,128) | O [128,192); the bf16 P of column half hf is written back over columns
+//         [32 hf, 32 hf + 16) of S_{j&1} (inside the range its own warp has consumed) and is the A operand of O += P_j V_j.
+// The running-max ("online") softmax needs a per-step exchange between the two warps of a row; it stays on the db
+// kernel: when the bound is not finite this kernel returns immediately and the gated db launch does the work.
 #include "kernels.cuh"
 #include "ptx.cuh"
 
 namespace osd {
 
-#ifndef OSD_DB_EMU
-#define OSD_DB_EMU 0
+// of every 8 score pairs of a thread, W8_EMU (0..4) have their exponentials computed on the FMA pipe
+#ifndef OSD_W8_EMU
+#define OSD_W8_EMU 4
 #endif
-static constexpr bool DB_EMU = OSD_DB_EMU != 0;
+static constexpr int W8_EMU = OSD_W8_EMU;
 
-static constexpr int DB_THREADS = 192;
+static constexpr int DB_THREADS = 320;
 static constexpr int DB_T128 = 128 * 128;
 static constexpr int DB_T64 = 64 * 128;
 static constexpr int DB_STAGES = 3;
 static constexpr int DB_SMEM_TILES = DB_T128 + 2 * DB_STAGES * DB_T64;
-static constexpr int DB_SMEM_BYTES = DB_SMEM_TILES + 256;
+static constexpr int DB_SMEM_BYTES = DB_SMEM_TILES + 256 + 1024 + 1024;  // barriers, row-sum exchange [2][128] fp32, alignment slack
 static constexpr uint32_t DB_TMEM_COLS = 256;
 
-struct AttnDbParams {
+struct AttnW8Params {
   CUtensorMap tma_q;   // dims (3*dh, L, B), box (64, 128, 1)
   CUtensorMap tma_kv;  // box (64, 64, 1)
   const float* bound_log2;
@@ -32,25 +35,33 @@ struct AttnDbParams {
   float* lse;
   int B, H, L, dh;
   float scale_log2, scale;
-  int only_if_online;  // 1: return immediately when the bound is finite (the w8 kernel has done the work)
+  unsigned long long* trace;  // nullable debugging aid (osd_debug_attn_fwd_trace): 2 writers x 1024 records
+  int trace_cta;
 };
 
-__device__ __forceinline__ float db_ex2(float x) {
+#define W8_TRACE(slot, ev, tile)                                                                                     \
+  do {                                                                                                               \
+    if (tr != nullptr && tr_n < 1024)                                                                                \
+      tr[(slot) * 1024 + tr_n++] = ((unsigned long long)(ev) << 48) | ((unsigned long long)(tile) << 32) |           \
+                                   (unsigned long long)(clock64() & 0xffffffffll);                                   \
+  } while (0)
+
+__device__ __forceinline__ float w8_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-__global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid_constant__ AttnDbParams p) {
+__global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_w8_kernel(const __grid_constant__ AttnW8Params p) {
   extern __shared__ uint8_t smem_raw[];
-  if (p.only_if_online && p.bound_log2 != nullptr && *p.bound_log2 < 3.0e38f) return;
+  if (!(p.bound_log2 != nullptr && *p.bound_log2 < 3.0e38f)) return;  // online softmax: the gated db launch runs instead
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   {
     uint32_t dyn;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    if (pad + DB_SMEM_TILES + 160 > dyn) __trap();
+    if (pad + DB_SMEM_TILES + 256 + 1024 > dyn) __trap();
   }
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + DB_T128;
@@ -65,6 +76,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
   uint64_t* p_full = bars + 15;
   uint64_t* o_ready = bars + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  float* sL = reinterpret_cast<float*>(bars + 32);  // [2 halves][128 rows] partial row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = (p.L + 127) / 128;
@@ -73,6 +85,8 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
   const int h = bh % p.H, b = bh / p.H;
   const int q0 = qt * 128;
   const int n_kv = (p.L + 63) / 64;
+  unsigned long long* tr = (p.trace != nullptr && (int)blockIdx.x == p.trace_cta && (threadIdx.x & 31) == 0) ? p.trace : nullptr;
+  int tr_n = 0;
 
   if (warp == 0 && lane == 0) {
     mbar_init(q_full, 1);
@@ -84,7 +98,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
     }
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(o_ready, 1);
     fence_barrier_init();
   }
@@ -140,121 +154,97 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % DB_STAGES;
         mbar_wait(p_full, j & 1);
+        W8_TRACE(0, 10, j);
         mbar_wait(&v_full[st], (j / DB_STAGES) & 1);
         tc_fence_after();
+        W8_TRACE(0, 11, j);
         const uint32_t aV = smem_u32(sV + st * DB_T64);
         const uint32_t tP = tmem_base + (j & 1) * 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16_ts(tO, tP + k * 8, make_smem_desc(aV + k * 16 * 128, 0, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          umma_f16_ts(tO, tP + (k >> 1) * 32 + (k & 1) * 8, make_smem_desc(aV + k * 16 * 128, 0, 1024), idesc_o,
+                      (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&v_empty[st]);
         umma_commit(o_ready);
         if (j + 2 < n_kv) issue_s(j + 2);  // reuses S_{j&1}: issued after the MMA that read P_j from it
+        W8_TRACE(0, 12, j);
       }
     }
   } else {
     const int quad = warp & 3;
+    const int hf = (warp - 2) >> 2;  // score-column half of this warp: columns [32 hf, 32 hf + 32)
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tO = tmem_base + 128 + lane_off;
     const float c = p.scale_log2;
-    float bound = INFINITY;
-    if (p.bound_log2 != nullptr) bound = __ldg(p.bound_log2);
-    const bool fixed = bound < 3.0e38f;
-    float m = fixed ? bound / c : -INFINITY, l = 0.f;
+    const float bound = __ldg(p.bound_log2);  // |s| c <= bound: exp2(s c - bound) <= 1, no running max, no O rescale
+    const float2 c2 = make_float2(c, c), n2 = make_float2(-bound, -bound);
+    float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
     for (int j = 0; j < n_kv; ++j) {
-      const uint32_t tS = tmem_base + (j & 1) * 64 + lane_off;
+      const uint32_t tS = tmem_base + (j & 1) * 64 + lane_off + hf * 32;
+      if (warp == 2) W8_TRACE(1, 0, j);
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      const int valid = p.L - j * 64;
-      uint32_t r0[32], r1[32];
+      if (warp == 2) W8_TRACE(1, 1, j);
+      const int valid = p.L - j * 64 - hf * 32;  // valid columns of this warp's half
+      uint32_t r[32];
       __syncwarp();
-      tmem_ld32(tS, r0);
-      tmem_ld32(tS + 32, r1);
+      tmem_ld32(tS, r);
       tmem_wait_ld();
-      float m_new = m, alpha = 1.0f;
-      if (!fixed) {
-        float mx = -INFINITY;
+      uint32_t pk[16];
+      if (valid >= 32) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < valid) mx = fmaxf(mx, __uint_as_float(r0[i]));
-          if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(r1[i]));
-        }
-        m_new = fmaxf(m, mx);
-        alpha = db_ex2((m - m_new) * c);
-      }
-      const float neg_mc = -m_new * c;
-      const float2 c2 = make_float2(c, c), n2 = make_float2(neg_mc, neg_mc);
-      uint32_t pk[32];
-      float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
-      if (valid >= 64) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float2 a = ffma2(make_float2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])), c2, n2);
-          const float2 bb = ffma2(make_float2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])), c2, n2);
-          const float2 ea = make_float2(db_ex2(a.x), db_ex2(a.y));
-          // half of the exponentials on the FMA pipe (ex2_poly2): the SFU (16 ex2 / clk / SM) is the binding unit at d = 64
-          const float2 eb = DB_EMU ? ex2_poly2(bb) : make_float2(db_ex2(bb.x), db_ex2(bb.y));
+        for (int i = 0; i < 32; i += 4) {
+          const float2 a = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, n2);
+          const float2 bb = ffma2(make_float2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), c2, n2);
+          const float2 ea = make_float2(w8_ex2(a.x), w8_ex2(a.y));
+          const float2 eb = (((i >> 2) & 3) < W8_EMU) ? ex2_poly2(bb) : make_float2(w8_ex2(bb.x), w8_ex2(bb.y));
           s01 = fadd2(s01, ea);
           s23 = fadd2(s23, eb);
           pk[i >> 1] = pack_bf16(ea.x, ea.y);
-          pk[16 + (i >> 1)] = pack_bf16(eb.x, eb.y);
+          pk[(i >> 1) + 1] = pack_bf16(eb.x, eb.y);
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float a0 = (i < valid) ? db_ex2(fmaf(__uint_as_float(r0[i]), c, neg_mc)) : 0.f;
-          const float a1 = (i + 1 < valid) ? db_ex2(fmaf(__uint_as_float(r0[i + 1]), c, neg_mc)) : 0.f;
-          const float b0 = (32 + i < valid) ? db_ex2(fmaf(__uint_as_float(r1[i]), c, neg_mc)) : 0.f;
-          const float b1 = (33 + i < valid) ? db_ex2(fmaf(__uint_as_float(r1[i + 1]), c, neg_mc)) : 0.f;
+          const float a0 = (i < valid) ? w8_ex2(fmaf(__uint_as_float(r[i]), c, -bound)) : 0.f;
+          const float a1 = (i + 1 < valid) ? w8_ex2(fmaf(__uint_as_float(r[i + 1]), c, -bound)) : 0.f;
           s01 = fadd2(s01, make_float2(a0, a1));
-          s23 = fadd2(s23, make_float2(b0, b1));
           pk[i >> 1] = pack_bf16(a0, a1);
-          pk[16 + (i >> 1)] = pack_bf16(b0, b1);
         }
       }
-      const float sum = (s01.x + s01.y) + (s23.x + s23.y);
-      // O_{j-1} must be complete before (a) it is rescaled (online mode) and (b) this warp runs further ahead of the
-      // o_ready phase counter; by now that MMA has long retired, so this wait is free in steady state.
+      // keeps this warp within one phase of the o_ready barrier (O_{j-1} has long retired: free in steady state)
+      if (warp == 2) W8_TRACE(1, 2, j);
       if (j > 0) {
         mbar_wait(o_ready, (j - 1) & 1);
         tc_fence_after();
-        if (!fixed && __any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-          for (int cch = 0; cch < 2; ++cch) {
-            uint32_t ro[32];
-            __syncwarp();
-            tmem_ld32(tO + cch * 32, ro);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-            tmem_st32(tO + cch * 32, ro);
-          }
-          tmem_wait_st();
-        }
       }
+      if (warp == 2) W8_TRACE(1, 3, j);
       __syncwarp();
-      tmem_st32(tS, pk);  // P_j (64 bf16 = 32 columns) over the consumed S_j
+      tmem_st16(tS, pk);  // P_j of this half (32 bf16 = 16 columns) over the S columns this warp has consumed
       tmem_wait_st();
-      l = l * alpha + sum;
-      m = m_new;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (warp == 2) W8_TRACE(1, 4, j);
     }
+    // row sum = both halves
+    const float lpart = (s01.x + s01.y) + (s23.x + s23.y);
+    sL[hf * 128 + row] = lpart;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l = sL[row] + sL[128 + row];
     mbar_wait(o_ready, (n_kv - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const int q = q0 + row;
     const bool ok = q < p.L;
-#pragma unroll 1
-    for (int cch = 0; cch < 2; ++cch) {
+    {
       uint32_t r[32];
       __syncwarp();
-      tmem_ld32(tO + cch * 32, r);
+      tmem_ld32(tO + hf * 32, r);
       tmem_wait_ld();
       if (ok) {
-        uint4* dst = reinterpret_cast<uint4*>(p.y + ((size_t)b * p.L + q) * p.dh + h * 64 + cch * 32);
+        uint4* dst = reinterpret_cast<uint4*>(p.y + ((size_t)b * p.L + q) * p.dh + h * 64 + hf * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           dst[i] = make_uint4(pack_bf16(__uint_as_float(r[8 * i]) * inv_l, __uint_as_float(r[8 * i + 1]) * inv_l),
@@ -263,7 +253,9 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
                               pack_bf16(__uint_as_float(r[8 * i + 6]) * inv_l, __uint_as_float(r[8 * i + 7]) * inv_l));
       }
     }
-    if (ok && p.lse != nullptr) p.lse[((size_t)b * p.H + h) * p.L + q] = m * p.scale + __logf(l);
+    // lse = m * scale + log(l) with m = bound / c  ->  bound / log2(e) + log(l)
+    if (ok && hf == 0 && p.lse != nullptr)
+      p.lse[((size_t)b * p.H + h) * p.L + q] = bound * 0.6931471805599453f + __logf(l);
     tc_fence_before();
   }
   __syncthreads();
@@ -276,14 +268,19 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
 
 int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                              int only_if_online, cudaStream_t stream);
-int launch_attn_fwd_db(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
-                       cudaStream_t stream) {
-  return launch_attn_fwd_db_gated(qkv, y, lse, bound_log2, B, L, H, 0, stream);
+
+static unsigned long long* g_w8_trace = nullptr;
+static int g_w8_trace_cta = 0;
+void attn_fwd_w8_set_trace(unsigned long long* buf, int cta) {
+  g_w8_trace = buf;
+  g_w8_trace_cta = cta;
 }
-int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
-                             int only_if_online, cudaStream_t stream) {
-  OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd_db: bad arguments");
-  AttnDbParams p;
+
+int launch_attn_fwd_w8(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                       cudaStream_t stream) {
+  OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd_w8: bad arguments");
+  if (bound_log2 == nullptr) return launch_attn_fwd_db_gated(qkv, y, lse, bound_log2, B, L, H, 0, stream);
+  AttnW8Params p;
   const int dh = H * 64;
   uint64_t dims[3] = {(uint64_t)3 * dh, (uint64_t)L, (uint64_t)B};
   uint64_t strides[2] = {(uint64_t)3 * dh * 2, (uint64_t)L * 3 * dh * 2};
@@ -291,22 +288,24 @@ int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* 
   OSD_TRY(make_tmap(&p.tma_q, qkv, 2, 3, dims, strides, box_q));
   OSD_TRY(make_tmap(&p.tma_kv, qkv, 2, 3, dims, strides, box_kv));
   p.bound_log2 = bound_log2;
-  p.only_if_online = only_if_online;
   p.y = static_cast<__nv_bfloat16*>(y);
   p.lse = lse;
   p.B = B; p.H = H; p.L = L; p.dh = dh;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.trace = g_w8_trace;
+  p.trace_cta = g_w8_trace_cta;
   static bool attr_set = false;
   if (!attr_set) {
-    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES));
+    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_w8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES));
     attr_set = true;
   }
   const long long grid = (long long)ceil_div(L, 128) * H * B;
-  OSD_CHECK(grid < (1ll << 31), "attn_fwd_db: grid too large");
-  attn_fwd_db_kernel<<<(unsigned)grid, DB_THREADS, DB_SMEM_BYTES, stream>>>(p);
+  OSD_CHECK(grid < (1ll << 31), "attn_fwd_w8: grid too large");
+  attn_fwd_w8_kernel<<<(unsigned)grid, DB_THREADS, DB_SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
-  return 0;
+  // bound not finite (decided on the device): the db kernel with the running-max softmax does the work instead
+  return launch_attn_fwd_db_gated(qkv, y, lse, bound_log2, B, L, H, 1, stream);
 }
 
 }  // namespace osd

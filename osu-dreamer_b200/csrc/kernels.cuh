@@ -74,11 +74,14 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
 // single-pass backward (attn_bwd_fused.cu): dq_acc fp32 [B*L, H*64] is scratch (zeroed and reduced into here),
 // stats fp32 [attn_bwd_fused_stats_floats()] and dy_scaled bf16 [B*L, H*64] are scratch
 size_t attn_bwd_fused_stats_floats(int B, int L, int H);
+void attn_fwd_w8_set_trace(unsigned long long* buf, int cta);  // debugging aid, see osd_debug_attn_fwd_trace
 void attn_bwd_fused_set_trace(unsigned long long* buf, int cta);  // debugging aid, see osd_debug_attn_bwd_trace
 int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* stats, float* dq_acc,
                           void* dy_scaled, void* dqkv, int B, int L, int H, cudaStream_t stream);
 int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int variant,
                     cudaStream_t stream);
+int launch_attn_fwd_w8(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                       cudaStream_t stream);
 int launch_attn_fwd_db(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                        cudaStream_t stream);
 int launch_attn_fwd_x3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,

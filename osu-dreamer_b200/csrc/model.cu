@@ -555,6 +555,7 @@ int osd_attn_bwd(const void* qkv, const void* y, const void* dy, const float* ls
 // debugging aid (tools/trace_attn_bwd.py): event timeline of one CTA of the single-pass kernel; buf = device
 // buffer of 3 x 1024 u64 records, or null to switch tracing off
 void osd_debug_attn_bwd_trace(unsigned long long* buf, int cta) { attn_bwd_fused_set_trace(buf, cta); }
+void osd_debug_attn_fwd_trace(unsigned long long* buf, int cta) { attn_fwd_w8_set_trace(buf, cta); }
 
 size_t osd_attn_bwd_fused_stats_floats(int B, int L, int H) { return attn_bwd_fused_stats_floats(B, L, H); }
 

@@ -293,9 +293,12 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
 // minimax polynomial of 2^f on [-0.5, 0.5] (max relative error 7.5e-5 -- the results are rounded to bf16 afterwards),
 // exponent patched in with an integer add.  x is clamped to >= -126 (result ~1e-38 instead of a wrapped exponent).
 // Lets the attention kernels split their exponentials between the SFU (16 / clk / SM) and the FMA pipe.
+template <bool CLAMP = true>
 __device__ __forceinline__ float2 ex2_poly2(float2 x) {
-  x.x = fmaxf(x.x, -126.f);
-  x.y = fmaxf(x.y, -126.f);
+  if (CLAMP) {  // callers that can prove x >= -126 skip the two FMNMX
+    x.x = fmaxf(x.x, -126.f);
+    x.y = fmaxf(x.y, -126.f);
+  }
   const float2 magic = make_float2(12582912.f, 12582912.f);
   const float2 t = fadd2(x, magic);                                          // low mantissa bits = round(x)
   const float2 r = fadd2(t, make_float2(-12582912.f, -12582912.f));          // round(x) as a float

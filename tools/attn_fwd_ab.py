@@ -23,7 +23,7 @@ B, L = 2, 1000
 g = torch.Generator().manual_seed(1)
 qkv = torch.randn(B * L, 3072, generator=g).cuda().to(torch.bfloat16)
 bound = torch.tensor([14.0], device='cuda')
-for variant, bl in ((4, bound), (4, None)):
+for variant, bl in ((4, bound), (4, None), (5, bound), (5, None), (5, torch.tensor([float('inf')], device='cuda'))):
     y, lse = lib.attn_fwd(qkv, B, L, bound_log2=bl, variant=variant)
     q, k, v = qkv.float().view(B, L, 3, 16, 64).permute(2, 0, 3, 1, 4)
     s = (q @ k.transpose(-1, -2)) / 8
@@ -34,5 +34,6 @@ for variant, bl in ((4, bound), (4, None)):
 for B, L in ((16, 8192), (32, 8192)):
     qkv = torch.randn(B * L, 3072, device='cuda').to(torch.bfloat16)
     fl = 4.0 * B * 16 * L * L * 64
-    t = timeit(lambda: lib.attn_fwd(qkv, B, L, bound_log2=bound, variant=4))
-    print(f'B={B} L={L}: fwd {t:.3f} ms ({fl / t / 1e9:.0f} TF/s)', flush=True)
+    for variant in (4, 5):
+        t = timeit(lambda: lib.attn_fwd(qkv, B, L, bound_log2=bound, variant=variant))
+        print(f'B={B} L={L} variant {variant}: fwd {t:.3f} ms ({fl / t / 1e9:.0f} TF/s)', flush=True)
