@@ -525,8 +525,13 @@ size_t attn_bwd_fused_stats_floats(int B, int L, int H) {
   return (size_t)B * H * (n_t * 128 + L + n_t) + 64;
 }
 
+const int* attn_bwd_fused_flag(const float* stats, int B, int L, int H) {
+  const size_t n_t = (L + 127) / 128;
+  return reinterpret_cast<const int*>(stats + (size_t)B * H * (n_t * 128 + L + n_t));
+}
+
 int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* stats, float* dq_acc,
-                          void* dy_scaled, void* dqkv, int B, int L, int H, cudaStream_t stream) {
+                          void* dy_scaled, void* dqkv, int B, int L, int H, int convert_dq, cudaStream_t stream) {
   OSD_CHECK(qkv && y && dy && lse && stats && dq_acc && dy_scaled && dqkv && B > 0 && L > 0 && H == 16,
             "attn_bwd_fused: bad arguments");
   const int dh = H * 64;
@@ -580,9 +585,11 @@ int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const 
   OSD_CHECK(grid < (1ll << 31), "attn_bwd_fused: grid too large");
   attn_bwd_fused_kernel<<<(unsigned)grid, FB_THREADS, FB_SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
-  const size_t n8 = (size_t)B * L * dh / 8;
-  attn_bwd_dq_convert_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(dq_acc, p.dqkv, n8, dh, p.scale, fallback);
-  OSD_LAUNCHED();
+  if (convert_dq) {
+    const size_t n8 = (size_t)B * L * dh / 8;
+    attn_bwd_dq_convert_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(dq_acc, p.dqkv, n8, dh, p.scale, fallback);
+    OSD_LAUNCHED();
+  }
   // fallback (statistics of a q tile too spread out for the w-scaling): the two-kernel path, gated on the same flag
   return launch_attn_bwd_gated(qkv, dy, lse, dsum, dqkv, B, L, H, fallback, stream);
 }

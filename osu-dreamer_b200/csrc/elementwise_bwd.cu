@@ -377,198 +377,250 @@ int launch_dwconv_prenorm_bwd(const void* dz2, const void* hmod, const float* x1
 }
 
 // ------------------------------------------------------------------------------------------------
-// SwiGLU + RMSNorm(1365) backward: dvg from dhn; dbvg (padded layout) = colsum(dvg).
+// SwiGLU + RMSNorm(1365) backward: dvg from dhn; dbvg (padded layout) = column sums of dvg (fused: the bf16
+// values the GEMMs read are summed here, no second pass over dvg).
+// Column-parallel: a block of 11 warps owns SWB_ROWS consecutive tokens and all 2 x 1408 columns; each lane keeps
+// the same 4 v and 4 g columns for every row, so the column sums stay in registers.  Rows go through in batches of
+// SWB_R: all loads of a batch are issued up front (12 x 8 bytes per lane in flight), the row statistic
+// mean(dhn * hn) is a warp sum + an 11-entry exchange through shared memory (double-buffered: one barrier per
+// batch), and the outputs are produced from the registers of the same single read.
 static constexpr int HID = 1365, HIDP = 1408;
-__global__ void __launch_bounds__(256) swiglu_norm_bwd_kernel(const __nv_bfloat16* __restrict__ vg,
-                                                              const __nv_bfloat16* __restrict__ dhn,
-                                                              const float* __restrict__ rinv,
-                                                              __nv_bfloat16* __restrict__ dvg, float* __restrict__ dbvg,
-                                                              int T) {
+static constexpr int SWB_ROWS = 128, SWB_R = 4, SWB_WARPS = HIDP / 128;
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__global__ void __launch_bounds__(SWB_WARPS * 32, 2) swiglu_norm_bwd_kernel(const __nv_bfloat16* __restrict__ vg,
+                                                                         const __nv_bfloat16* __restrict__ dhn,
+                                                                         const float* __restrict__ rinv,
+                                                                         __nv_bfloat16* __restrict__ dvg,
+                                                                         float* __restrict__ dbvg, int T) {
+  __shared__ float sdot[2][SWB_R][SWB_WARPS + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t0 = blockIdx.x * TOKB;
-  for (int rr = warp; rr < TOKB; rr += 8) {
-    const int t = t0 + rr;
-    if (t >= T) break;
-    const __nv_bfloat16* row = vg + (size_t)t * 2 * HIDP;
-    const __nv_bfloat16* drow = dhn + (size_t)t * HIDP;
-    const float r = rinv[t];
-    // two passes over the row (the second one hits L1/L2): keeps the kernel at ~50 registers so that enough
-    // warps are resident to cover HBM latency
-    float dot = 0.f;
-#pragma unroll 1
-    for (int i = 0; i < 11; ++i) {
-      const int c0 = i * 128 + lane * 4;
-      const uint2 va = *reinterpret_cast<const uint2*>(row + c0);
-      const uint2 ga = *reinterpret_cast<const uint2*>(row + HIDP + c0);
-      const uint2 da = *reinterpret_cast<const uint2*>(drow + c0);
-      const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&va);
-      const __nv_bfloat162* bp = reinterpret_cast<const __nv_bfloat162*>(&ga);
-      const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&da);
+  const int c0 = warp * 128 + lane * 4;
+  const int t0 = blockIdx.x * SWB_ROWS;
+  const int t1 = min(T, t0 + SWB_ROWS);
+  float csv[4] = {0.f, 0.f, 0.f, 0.f}, csg[4] = {0.f, 0.f, 0.f, 0.f};
+  int it = 0;
+  for (int tb = t0; tb < t1; tb += SWB_R, ++it) {
+    uint2 va[SWB_R], ga[SWB_R], da[SWB_R];
+    float rr[SWB_R];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float2 v2 = __bfloat1622float2(ap[h]), g2 = __bfloat1622float2(bp[h]), d2 = __bfloat1622float2(dp[h]);
-        dot = fmaf(d2.x, v2.x * silu_f(g2.x), dot);
-        dot = fmaf(d2.y, v2.y * silu_f(g2.y), dot);
-      }
+    for (int r = 0; r < SWB_R; ++r) {
+      const int t = min(tb + r, t1 - 1);  // tail rows re-read the last row (their results are discarded)
+      const __nv_bfloat16* row = vg + (size_t)t * 2 * HIDP;
+      va[r] = *reinterpret_cast<const uint2*>(row + c0);
+      ga[r] = *reinterpret_cast<const uint2*>(row + HIDP + c0);
+      da[r] = *reinterpret_cast<const uint2*>(dhn + (size_t)t * HIDP + c0);
+      rr[r] = rinv[t];
     }
-    dot = warp_sum(dot) * r * (1.0f / HID);  // mean(dhn * hn), hn = hs * r
-#pragma unroll 1
-    for (int i = 0; i < 11; ++i) {
-      const int c0 = i * 128 + lane * 4;
-      const uint2 va = *reinterpret_cast<const uint2*>(row + c0);
-      const uint2 ga = *reinterpret_cast<const uint2*>(row + HIDP + c0);
-      const uint2 da = *reinterpret_cast<const uint2*>(drow + c0);
-      const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&va);
-      const __nv_bfloat162* bp = reinterpret_cast<const __nv_bfloat162*>(&ga);
-      const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&da);
+    float part[SWB_R];
+#pragma unroll
+    for (int r = 0; r < SWB_R; ++r) {
+      float v[4], g[4], d[4];
+      unpack_bf16x4(va[r], v);
+      unpack_bf16x4(ga[r], g);
+      unpack_bf16x4(da[r], d);
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc = fmaf(d[e], v[e] * g[e] * sigmoid_fast(g[e]), acc);
+      part[r] = acc;
+    }
+#pragma unroll
+    for (int r = 0; r < SWB_R; ++r) part[r] = warp_sum(part[r]);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < SWB_R; ++r) sdot[it & 1][r][warp] = part[r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SWB_R; ++r) {
+      const int t = tb + r;
+      if (t >= t1) break;  // block-uniform
+      float dot = 0.f;
+#pragma unroll
+      for (int w = 0; w < SWB_WARPS; ++w) dot += sdot[it & 1][r][w];
+      const float rinv_t = rr[r];
+      dot = dot * rinv_t * (1.0f / HID);  // mean(dhn * hn), hn = hs * r
+      float v[4], g[4], d[4];
+      unpack_bf16x4(va[r], v);
+      unpack_bf16x4(ga[r], g);
+      unpack_bf16x4(da[r], d);
       float ov[4], og[4];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float2 v2 = __bfloat1622float2(ap[h]), g2 = __bfloat1622float2(bp[h]), d2 = __bfloat1622float2(dp[h]);
-        const float vv[2] = {v2.x, v2.y}, gg[2] = {g2.x, g2.y}, dd[2] = {d2.x, d2.y};
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float sg = 1.0f / (1.0f + __expf(-gg[e]));
-          const float sil = gg[e] * sg;
-          const float dhs = r * (dd[e] - vv[e] * sil * r * dot);
-          ov[2 * h + e] = dhs * sil;
-          og[2 * h + e] = dhs * vv[e] * (sg * (1.0f + gg[e] * (1.0f - sg)));
-        }
+      for (int e = 0; e < 4; ++e) {
+        const float sg = sigmoid_fast(g[e]);
+        const float sil = g[e] * sg;
+        const float dhs = rinv_t * (d[e] - v[e] * sil * rinv_t * dot);
+        ov[e] = dhs * sil;
+        og[e] = dhs * v[e] * (sg * (1.0f + g[e] * (1.0f - sg)));
       }
-      *reinterpret_cast<uint2*>(dvg + (size_t)t * 2 * HIDP + c0) = make_uint2(pack_bf16(ov[0], ov[1]), pack_bf16(ov[2], ov[3]));
-      *reinterpret_cast<uint2*>(dvg + (size_t)t * 2 * HIDP + HIDP + c0) =
-          make_uint2(pack_bf16(og[0], og[1]), pack_bf16(og[2], og[3]));
+      const uint2 pv = make_uint2(pack_bf16(ov[0], ov[1]), pack_bf16(ov[2], ov[3]));
+      const uint2 pg = make_uint2(pack_bf16(og[0], og[1]), pack_bf16(og[2], og[3]));
+      *reinterpret_cast<uint2*>(dvg + (size_t)t * 2 * HIDP + c0) = pv;
+      *reinterpret_cast<uint2*>(dvg + (size_t)t * 2 * HIDP + HIDP + c0) = pg;
+      float rv[4], rg[4];
+      unpack_bf16x4(pv, rv);
+      unpack_bf16x4(pg, rg);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) csv[e] += rv[e], csg[e] += rg[e];
     }
   }
-}
-// column sums of a bf16 [T, N] matrix (N % 8 == 0) accumulated into out[N] (fp32 atomics, one per column per block)
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ m, float* __restrict__ out,
-                                                          int T, int N) {
-  const int t0 = blockIdx.x * 128;
-  const int t1 = min(T, t0 + 128);
-  for (int v = threadIdx.x; v < N / 8; v += 256) {
-    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = t0; t < t1; ++t) {
-      const uint4 q = *reinterpret_cast<const uint4*>(m + (size_t)t * N + v * 8);
-      const __nv_bfloat162* qp = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) a[2 * k] += __low2float(qp[k]), a[2 * k + 1] += __high2float(qp[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(out + v * 8 + k, a[k]);
+  for (int e = 0; e < 4; ++e) {
+    atomicAdd(dbvg + c0 + e, csv[e]);
+    atomicAdd(dbvg + HIDP + c0 + e, csg[e]);
   }
-}
-int launch_colsum_bf16(const void* m, float* out, int T, int N, cudaStream_t s) {
-  OSD_CHECK(N % 8 == 0, "colsum: N must be a multiple of 8");
-  colsum_bf16_kernel<<<ceil_div(T, 128), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(m), out, T, N);
-  OSD_LAUNCHED();
-  return 0;
 }
 int launch_swiglu_norm_bwd(const void* vg, const void* dhn, const float* rinv, void* dvg, float* dbvg, int T,
                            cudaStream_t s) {
-  swiglu_norm_bwd_kernel<<<ceil_div(T, TOKB), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(vg),
-                                                           static_cast<const __nv_bfloat16*>(dhn), rinv,
-                                                           static_cast<__nv_bfloat16*>(dvg), dbvg, T);
+  swiglu_norm_bwd_kernel<<<ceil_div(T, SWB_ROWS), SWB_WARPS * 32, 0, s>>>(static_cast<const __nv_bfloat16*>(vg),
+                                                                        static_cast<const __nv_bfloat16*>(dhn), rinv,
+                                                                        static_cast<__nv_bfloat16*>(dvg), dbvg, T);
   OSD_LAUNCHED();
-  return launch_colsum_bf16(dvg, dbvg, T, 2 * HIDP, s);
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // q/k RMSNorm(64)*w + RoPE backward, in place on dqkv [T,3072] (dq | dk | dv) -> gradients of the raw
-// projections; dqn_w / dkn_w [64]; dbqkv [3072] = colsum of the result.  16 lanes per 64-wide head chunk:
-// lane j of the half-warp holds elements (2j, 2j+1) and (2j+32, 2j+33) -- the rope partner pairs.
+// projections; dqn_w / dkn_w [64]; dbqkv [3072] = column sums of the result (fused: no second pass over dqkv).
+// Column-parallel: a block owns QKB consecutive tokens of one sample and ALL 3072 columns; warp w owns the four
+// 64-wide heads 4w..4w+3 of q (w < 4) or k (w >= 4) plus 128 of the v columns, for every row of the block, so the
+// column sums (and the norm-weight gradients) stay in registers until the end.  8 lanes per head: lane j holds
+// elements 4j..4j+3 and 32+4j..32+4j+3 -- the rope partner pairs -- and the two 64-wide row statistics are
+// 3-step shuffles.  dq can be taken straight from the fp32 accumulator of the single-pass attention backward
+// (dq_acc, scaled by dq_scale) when its fallback flag is clear, which replaces that path's convert pass.
+static constexpr int QKB = 128;
 __global__ void __launch_bounds__(256) qknorm_rope_bwd_kernel(__nv_bfloat16* __restrict__ dqkv,
                                                               const __nv_bfloat16* __restrict__ raw,
                                                               const float* __restrict__ rope,
                                                               const float* __restrict__ qw, const float* __restrict__ kw,
                                                               float* __restrict__ dqw, float* __restrict__ dkw,
-                                                              int L) {
+                                                              float* __restrict__ dbias,
+                                                              const float* __restrict__ dq_acc,
+                                                              const int* __restrict__ dq_flag, float dq_scale, int L) {
   __shared__ float sW[2][64];
   if (threadIdx.x < 128) sW[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
   __syncthreads();
-  const int b = blockIdx.y, l0 = blockIdx.x * TOKB;
+  const int b = blockIdx.y, l0 = blockIdx.x * QKB;
+  const int l1 = min(L, l0 + QKB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = lane >> 4, j = lane & 15;
+  const int sub = lane >> 3, j = lane & 7;
+  const int isk = warp >> 2;                        // warp-uniform
+  const int col = (warp * 4 + sub) * 64 + 4 * j;    // first of this lane's 4 + 4 q/k columns (second group at +32)
+  const int vcol = 2048 + warp * 128 + lane * 4;    // this lane's 4 v columns
+  const bool from_acc = (isk == 0) && dq_acc != nullptr && (dq_flag == nullptr || *dq_flag == 0);
   const float eps = 1.1920929e-07f;
-  // weights for this lane's 4 elements, q and k
-  float wq[4], wkk[4];
-  wq[0] = qw[2 * j], wq[1] = qw[2 * j + 1], wq[2] = qw[2 * j + 32], wq[3] = qw[2 * j + 33];
-  wkk[0] = kw[2 * j], wkk[1] = kw[2 * j + 1], wkk[2] = kw[2 * j + 32], wkk[3] = kw[2 * j + 33];
-  float adw[2][4];
+  const float* wsrc = isk ? kw : qw;
+  const float4 w0 = *reinterpret_cast<const float4*>(wsrc + 4 * j);
+  const float4 w1 = *reinterpret_cast<const float4*>(wsrc + 32 + 4 * j);
+  const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+  float adw[8], cs[8], csv[4];
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int e = 0; e < 8; ++e) adw[e] = 0.f, cs[e] = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) adw[a][e] = 0.f;
+  for (int e = 0; e < 4; ++e) csv[e] = 0.f;
 
-  for (int rr = warp; rr < TOKB; rr += 8) {
-    const int l = l0 + rr;
-    if (l >= L) break;
+#pragma unroll 2
+  for (int l = l0; l < l1; ++l) {
     const size_t t = (size_t)b * L + l;
     __nv_bfloat16* drow = dqkv + t * 3072;
     const __nv_bfloat16* xrow = raw + t * 3072;
-    const float2 c01 = *reinterpret_cast<const float2*>(rope + (size_t)l * 64 + 2 * j);
-    const float2 s01 = *reinterpret_cast<const float2*>(rope + (size_t)l * 64 + 32 + 2 * j);
-#pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const int chunk = it * 2 + half;  // 0..31: 16 q heads then 16 k heads
-      const int col = chunk * 64;
-      const int isk = chunk >= 16;
-      const __nv_bfloat162 g1 = *reinterpret_cast<const __nv_bfloat162*>(drow + col + 2 * j);
-      const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(drow + col + 32 + 2 * j);
-      const __nv_bfloat162 x1 = *reinterpret_cast<const __nv_bfloat162*>(xrow + col + 2 * j);
-      const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(xrow + col + 32 + 2 * j);
-      const float gy[4] = {__low2float(g1), __high2float(g1), __low2float(g2), __high2float(g2)};
-      const float xx[4] = {__low2float(x1), __high2float(x1), __low2float(x2), __high2float(x2)};
-      // inverse rotation: da = g1*c + g2*s ; db = -g1*s + g2*c
-      float da[4];
-      da[0] = gy[0] * c01.x + gy[2] * s01.x;
-      da[1] = gy[1] * c01.y + gy[3] * s01.y;
-      da[2] = -gy[0] * s01.x + gy[2] * c01.x;
-      da[3] = -gy[1] * s01.y + gy[3] * c01.y;
-      float ss = xx[0] * xx[0] + xx[1] * xx[1] + xx[2] * xx[2] + xx[3] * xx[3];
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const float r = rsqrtf(ss * (1.0f / 64.0f) + eps);
-      float n[4], dn[4];
-      float dot = 0.f;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        n[e] = xx[e] * r;
-        const float w = isk ? wkk[e] : wq[e];
-        dn[e] = da[e] * w;
-        adw[isk][e] = fmaf(da[e], n[e], adw[isk][e]);
-        dot = fmaf(dn[e], n[e], dot);
-      }
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-      dot *= (1.0f / 64.0f);
-      float dxr[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        dxr[e] = r * (dn[e] - n[e] * dot);
-      }
-      *reinterpret_cast<__nv_bfloat162*>(drow + col + 2 * j) = __floats2bfloat162_rn(dxr[0], dxr[1]);
-      *reinterpret_cast<__nv_bfloat162*>(drow + col + 32 + 2 * j) = __floats2bfloat162_rn(dxr[2], dxr[3]);
+    const uint2 xa = *reinterpret_cast<const uint2*>(xrow + col);
+    const uint2 xb = *reinterpret_cast<const uint2*>(xrow + col + 32);
+    const uint2 gv = *reinterpret_cast<const uint2*>(drow + vcol);
+    const float4 cc = *reinterpret_cast<const float4*>(rope + (size_t)l * 64 + 4 * j);
+    const float4 sn = *reinterpret_cast<const float4*>(rope + (size_t)l * 64 + 32 + 4 * j);
+    float gy[8];
+    if (from_acc) {
+      const float* arow = dq_acc + t * 1024 + (col);
+      const float4 a0 = *reinterpret_cast<const float4*>(arow);
+      const float4 a1 = *reinterpret_cast<const float4*>(arow + 32);
+      gy[0] = a0.x * dq_scale, gy[1] = a0.y * dq_scale, gy[2] = a0.z * dq_scale, gy[3] = a0.w * dq_scale;
+      gy[4] = a1.x * dq_scale, gy[5] = a1.y * dq_scale, gy[6] = a1.z * dq_scale, gy[7] = a1.w * dq_scale;
+    } else {
+      const uint2 ga = *reinterpret_cast<const uint2*>(drow + col);
+      const uint2 gb = *reinterpret_cast<const uint2*>(drow + col + 32);
+      unpack_bf16x4(ga, gy);
+      unpack_bf16x4(gb, gy + 4);
     }
-  }
+    float xx[8], vv[4];
+    unpack_bf16x4(xa, xx);
+    unpack_bf16x4(xb, xx + 4);
+    unpack_bf16x4(gv, vv);
 #pragma unroll
-  for (int a = 0; a < 2; ++a) {
-    atomicAdd(&sW[a][2 * j], adw[a][0]);
-    atomicAdd(&sW[a][2 * j + 1], adw[a][1]);
-    atomicAdd(&sW[a][2 * j + 32], adw[a][2]);
-    atomicAdd(&sW[a][2 * j + 33], adw[a][3]);
+    for (int e = 0; e < 4; ++e) csv[e] += vv[e];
+    const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
+    const float sv[4] = {sn.x, sn.y, sn.z, sn.w};
+    // inverse rotation: da = g1*c + g2*s ; db = -g1*s + g2*c
+    float da[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      da[e] = gy[e] * cv[e] + gy[4 + e] * sv[e];
+      da[4 + e] = gy[4 + e] * cv[e] - gy[e] * sv[e];
+      ss = fmaf(xx[e], xx[e], ss);
+      ss = fmaf(xx[4 + e], xx[4 + e], ss);
+    }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    const float r = rsqrtf(ss * (1.0f / 64.0f) + eps);
+    float n[8], dn[8];
+    float dot = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      n[e] = xx[e] * r;
+      dn[e] = da[e] * wv[e];
+      adw[e] = fmaf(da[e], n[e], adw[e]);
+      dot = fmaf(dn[e], n[e], dot);
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot *= (1.0f / 64.0f);
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float d0 = r * (dn[2 * e] - n[2 * e] * dot), d1 = r * (dn[2 * e + 1] - n[2 * e + 1] * dot);
+      o[e] = pack_bf16(d0, d1);
+      // the bias gradient is the column sum of what the GEMMs will read, i.e. of the bf16-rounded values
+      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&o[e]);
+      cs[2 * e] += __low2float(h2);
+      cs[2 * e + 1] += __high2float(h2);
+    }
+    *reinterpret_cast<uint2*>(drow + col) = make_uint2(o[0], o[1]);
+    *reinterpret_cast<uint2*>(drow + col + 32) = make_uint2(o[2], o[3]);
+  }
+  // ---- column sums: one global atomic per column per block
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    atomicAdd(dbias + col + e, cs[e]);
+    atomicAdd(dbias + col + 32 + e, cs[4 + e]);
+    atomicAdd(dbias + vcol + e, csv[e]);
+  }
+  // ---- norm-weight gradients: sum over the warp's four heads (lanes with equal j), then over warps
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    adw[e] += __shfl_xor_sync(0xffffffffu, adw[e], 8);
+    adw[e] += __shfl_xor_sync(0xffffffffu, adw[e], 16);
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      atomicAdd(&sW[isk][4 * j + e], adw[e]);
+      atomicAdd(&sW[isk][32 + 4 * j + e], adw[4 + e]);
+    }
   }
   __syncthreads();
   if (threadIdx.x < 64) atomicAdd(dqw + threadIdx.x, sW[0][threadIdx.x]);
   else if (threadIdx.x < 128) atomicAdd(dkw + threadIdx.x - 64, sW[1][threadIdx.x - 64]);
 }
 int launch_qknorm_rope_bwd(void* dqkv, const void* raw, const float* rope, const float* qw, const float* kw,
-                           float* dqw, float* dkw, float* dbias, int B, int L, cudaStream_t s) {
-  dim3 grid(ceil_div(L, TOKB), B);
+                           float* dqw, float* dkw, float* dbias, const float* dq_acc, const int* dq_flag,
+                           float dq_scale, int B, int L, cudaStream_t s) {
+  dim3 grid(ceil_div(L, QKB), B);
   qknorm_rope_bwd_kernel<<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(raw),
-                                              rope, qw, kw, dqw, dkw, L);
+                                              rope, qw, kw, dqw, dkw, dbias, dq_acc, dq_flag, dq_scale, L);
   OSD_LAUNCHED();
-  return launch_colsum_bf16(dqkv, dbias, B * L, 3072, s);  // dbqkv = column sums of the raw-projection gradients
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -43,9 +43,9 @@ int launch_dwconv_prenorm_bwd(const void* dz2, const void* hmod, const float* x1
                               float* dx, float* dmod, float* dw, float* db, int B, int L, cudaStream_t s);
 int launch_swiglu_norm_bwd(const void* vg, const void* dhn, const float* rinv, void* dvg, float* dbvg, int T,
                            cudaStream_t s);
-int launch_colsum_bf16(const void* m, float* out, int T, int N, cudaStream_t s);
 int launch_qknorm_rope_bwd(void* dqkv, const void* raw, const float* rope, const float* qw, const float* kw,
-                           float* dqw, float* dkw, float* dbias, int B, int L, cudaStream_t s);
+                           float* dqw, float* dkw, float* dbias, const float* dq_acc, const int* dq_flag,
+                           float dq_scale, int B, int L, cudaStream_t s);
 int launch_proj_in_bwd(const float* dx, const float* xt, float* dW, float* db, int B, int L, cudaStream_t s);
 int launch_silu_bwd(const float* da, const float* pre, void* dpre, float* db, int T, cudaStream_t s);
 int launch_linear_small_bwd(const float* dout, const float* pre_or_null, const float* in, const float* W, float* dW,
@@ -76,8 +76,12 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
 size_t attn_bwd_fused_stats_floats(int B, int L, int H);
 void attn_fwd_w8_set_trace(unsigned long long* buf, int cta);  // debugging aid, see osd_debug_attn_fwd_trace
 void attn_bwd_fused_set_trace(unsigned long long* buf, int cta);  // debugging aid, see osd_debug_attn_bwd_trace
+// convert_dq = 0 leaves dq in dq_acc (fp32, unscaled; multiply by attn_bwd_fused_dq_scale()) unless the fallback flag
+// (*attn_bwd_fused_flag(...) != 0) says the two-kernel path wrote dq into dqkv: launch_qknorm_rope_bwd consumes that.
 int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* stats, float* dq_acc,
-                          void* dy_scaled, void* dqkv, int B, int L, int H, cudaStream_t stream);
+                          void* dy_scaled, void* dqkv, int B, int L, int H, int convert_dq, cudaStream_t stream);
+const int* attn_bwd_fused_flag(const float* stats, int B, int L, int H);
+static inline float attn_bwd_fused_dq_scale() { return 0.125f; }
 int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int variant,
                     cudaStream_t stream);
 int launch_attn_fwd_w8(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,

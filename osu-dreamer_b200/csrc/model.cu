@@ -376,15 +376,21 @@ static int pred_backward(const FwdCtx& c, const float* audio, const float* style
                                      G[lp(l, L_OUT_B)], B, L, s));
     OSD_TRY(gemm_dgrad(dh, 512, c.W.out(l), 1024, bw + bp.dy, 1024, 0, 0, T, 1024, 512, s));
     OSD_TRY(gemm_wgrad(dh, 512, lb + pl.y, 1024, G[lp(l, L_OUT_W)], 1024, 512, 1024, T, s));
-    if (attn_bwd_two_pass())
+    const float* dq_acc = nullptr;  // single-pass path: dq stays in its fp32 accumulator, consumed by qknorm_rope_bwd
+    const int* dq_flag = nullptr;
+    if (attn_bwd_two_pass()) {
       OSD_TRY(launch_attn_bwd(lb + pl.qkv, lb + pl.y, bw + bp.dy, reinterpret_cast<float*>(lb + pl.lse),
                               reinterpret_cast<float*>(bw + bp.dsum), bw + bp.dqkv, B, L, 16, s));
-    else
+    } else {
       OSD_TRY(launch_attn_bwd_fused(lb + pl.qkv, lb + pl.y, bw + bp.dy, reinterpret_cast<float*>(lb + pl.lse),
                                     reinterpret_cast<float*>(bw + bp.dsum), reinterpret_cast<float*>(bw + bp.dq_acc),
-                                    bw + bp.dys, bw + bp.dqkv, B, L, 16, s));
+                                    bw + bp.dys, bw + bp.dqkv, B, L, 16, /*convert_dq=*/0, s));
+      dq_acc = reinterpret_cast<const float*>(bw + bp.dq_acc);
+      dq_flag = attn_bwd_fused_flag(reinterpret_cast<const float*>(bw + bp.dsum), B, L, 16);
+    }
     OSD_TRY(launch_qknorm_rope_bwd(bw + bp.dqkv, lb + pl.qkv_raw, c.rope, c.P[lp(l, L_QN_W)], c.P[lp(l, L_KN_W)],
-                                   G[lp(l, L_QN_W)], G[lp(l, L_KN_W)], G[lp(l, L_QKV_B)], B, L, s));
+                                   G[lp(l, L_QN_W)], G[lp(l, L_KN_W)], G[lp(l, L_QKV_B)], dq_acc, dq_flag,
+                                   attn_bwd_fused_dq_scale(), B, L, s));
     OSD_TRY(gemm_dgrad(bw + bp.dqkv, 3072, c.W.qkv(l), 512, bw + bp.dz, 512, 0, 0, T, 512, 3072, s));
     OSD_TRY(gemm_wgrad(bw + bp.dqkv, 3072, lb + pl.z, 512, G[lp(l, L_QKV_W)], 512, 3072, 512, T, s));
     OSD_TRY(launch_prenorm_mod_bwd(bw + bp.dz, x0, c.cond.mod1(l), dx, dm1, G[lp(l, L_CL_B)], B, L, s));
@@ -561,7 +567,7 @@ size_t osd_attn_bwd_fused_stats_floats(int B, int L, int H) { return attn_bwd_fu
 
 int osd_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const float* lse, float* stats, float* dq_acc,
                        void* dy_scaled, void* dqkv, int B, int L, int H, void* stream) {
-  return launch_attn_bwd_fused(qkv, y, dy, lse, stats, dq_acc, dy_scaled, dqkv, B, L, H,
+  return launch_attn_bwd_fused(qkv, y, dy, lse, stats, dq_acc, dy_scaled, dqkv, B, L, H, /*convert_dq=*/1,
                                static_cast<cudaStream_t>(stream));
 }
 

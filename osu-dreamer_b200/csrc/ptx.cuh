@@ -315,6 +315,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// 4 bf16 (8 bytes) -> 4 floats: a bf16 is the upper half of the fp32 with the same value
+__device__ __forceinline__ void unpack_bf16x4(uint2 q, float* f) {
+  f[0] = __uint_as_float(q.x << 16), f[1] = __uint_as_float(q.x & 0xffff0000u);
+  f[2] = __uint_as_float(q.y << 16), f[3] = __uint_as_float(q.y & 0xffff0000u);
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
