@@ -41,6 +41,15 @@ __device__ __forceinline__ float db_ex2(float x) {
   return y;
 }
 
+// PF (variant 6): in fixed-bound mode the softmax warps (a) probe the barriers a step needs (o_ready of the previous
+// PV, s_full of the next S) with non-blocking test_waits BEFORE the exponentials, so the probe latency hides behind
+// the math, and (b) issue the TMEM load of S_{j+1} before storing / publishing P_j, so the load latency hides behind
+// the store + fence + arrive tail.  ncu source view of the non-PF kernel: 10 % of the softmax warps' samples sit on
+// the s_full probe, 5 % on the o_ready probe, 7 % on the TMEM load and 9 % on the store tail.
+// QT (variant 7): the Q tile is copied into TMEM once (columns [192, 224)) and is the A operand of S = Q K^T from
+// there (tcgen05.mma .ts), which halves the shared-memory operand reads of the kernel (Q 16 KB + K 8 KB + V 8 KB per
+// kv step -> 16 KB).
+template <bool PF, bool QT>
 __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid_constant__ AttnDbParams p) {
   extern __shared__ uint8_t smem_raw[];
   if (p.only_if_online && p.bound_log2 != nullptr && *p.bound_log2 < 3.0e38f) return;
@@ -65,6 +74,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
   uint64_t* p_full = bars + 15;
   uint64_t* o_ready = bars + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* qt_ready = bars + 18;  // QT: Q copied into TMEM by the softmax warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = (p.L + 127) / 128;
@@ -86,6 +96,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
     mbar_init(&s_full[1], 1);
     mbar_init(p_full, 4);
     mbar_init(o_ready, 1);
+    mbar_init(qt_ready, 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -129,12 +140,21 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
         const uint32_t aK = smem_u32(sK + st * DB_T64);
         const uint32_t tS = tmem_base + (j & 1) * 64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tS, make_smem_desc(aQ + k * 32, 0, 1024), make_smem_desc(aK + k * 32, 0, 1024), idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) {
+          if (QT)
+            umma_f16_ts(tS, tmem_base + 192 + k * 8, make_smem_desc(aK + k * 32, 0, 1024), idesc_s, k > 0);
+          else
+            umma_f16_ss(tS, make_smem_desc(aQ + k * 32, 0, 1024), make_smem_desc(aK + k * 32, 0, 1024), idesc_s, k > 0);
+        }
         umma_commit(&k_empty[st]);
         umma_commit(&s_full[j & 1]);
       };
-      mbar_wait(q_full, 0);
+      if (QT) {
+        mbar_wait(qt_ready, 0);
+        tc_fence_after();
+      } else {
+        mbar_wait(q_full, 0);
+      }
       issue_s(0);
       if (n_kv > 1) issue_s(1);
       for (int j = 0; j < n_kv; ++j) {
@@ -157,20 +177,45 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tO = tmem_base + 128 + lane_off;
+    if (QT) {  // one-time copy of this thread's Q row (128 B, SW128 smem) into TMEM
+      mbar_wait(q_full, 0);
+      const uint32_t base = smem_u32(sQ) + row * 128;
+      uint32_t rq[32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(rq[4 * u]), "=r"(rq[4 * u + 1]), "=r"(rq[4 * u + 2]), "=r"(rq[4 * u + 3])
+                     : "r"(base + ((u ^ (row & 7)) << 4)));
+      __syncwarp();
+      tmem_st32(tmem_base + 192 + lane_off, rq);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qt_ready);
+    }
     const float c = p.scale_log2;
     float bound = INFINITY;
     if (p.bound_log2 != nullptr) bound = __ldg(p.bound_log2);
     const bool fixed = bound < 3.0e38f;
     float m = fixed ? bound / c : -INFINITY, l = 0.f;
+    const bool pf = PF && fixed;
+    uint32_t r0[32], r1[32];
+    bool have = false;  // r0 / r1 already hold (or are receiving) S_j
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t tS = tmem_base + (j & 1) * 64 + lane_off;
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
+      if (!have) {
+        mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        __syncwarp();
+        tmem_ld32(tS, r0);
+        tmem_ld32(tS + 32, r1);
+      }
+      bool o_ok = false, s_ok = false;
+      if (pf) {
+        if (j > 0) o_ok = mbar_test(o_ready, (j - 1) & 1);
+        if (j + 1 < n_kv) s_ok = mbar_test(&s_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+      }
       const int valid = p.L - j * 64;
-      uint32_t r0[32], r1[32];
-      __syncwarp();
-      tmem_ld32(tS, r0);
-      tmem_ld32(tS + 32, r1);
       tmem_wait_ld();
       float m_new = m, alpha = 1.0f;
       if (!fixed) {
@@ -217,7 +262,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
       // O_{j-1} must be complete before (a) it is rescaled (online mode) and (b) this warp runs further ahead of the
       // o_ready phase counter; by now that MMA has long retired, so this wait is free in steady state.
       if (j > 0) {
-        mbar_wait(o_ready, (j - 1) & 1);
+        if (!o_ok) mbar_wait(o_ready, (j - 1) & 1);
         tc_fence_after();
         if (!fixed && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
@@ -234,6 +279,16 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
         }
       }
       __syncwarp();
+      have = false;
+      if (pf && j + 1 < n_kv) {
+        // r0 / r1 are dead (pk holds P_j): S_{j+1} streams in from the other accumulator while P_j is stored / published
+        if (!s_ok) mbar_wait(&s_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tSn = tmem_base + ((j + 1) & 1) * 64 + lane_off;
+        tmem_ld32(tSn, r0);
+        tmem_ld32(tSn + 32, r1);
+        have = true;
+      }
       tmem_st32(tS, pk);  // P_j (64 bf16 = 32 columns) over the consumed S_j
       tmem_wait_st();
       l = l * alpha + sum;
@@ -276,12 +331,28 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
 
 int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                              int only_if_online, cudaStream_t stream);
+template <bool PF, bool QT>
+static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                                int only_if_online, cudaStream_t stream);
 int launch_attn_fwd_db(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                        cudaStream_t stream) {
-  return launch_attn_fwd_db_gated(qkv, y, lse, bound_log2, B, L, H, 0, stream);
+  return launch_attn_fwd_db_t<false, false>(qkv, y, lse, bound_log2, B, L, H, 0, stream);
+}
+int launch_attn_fwd_db_qt(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                          cudaStream_t stream) {
+  return launch_attn_fwd_db_t<false, true>(qkv, y, lse, bound_log2, B, L, H, 0, stream);
+}
+int launch_attn_fwd_db_pf(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                          cudaStream_t stream) {
+  return launch_attn_fwd_db_t<true, false>(qkv, y, lse, bound_log2, B, L, H, 0, stream);
 }
 int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                              int only_if_online, cudaStream_t stream) {
+  return launch_attn_fwd_db_t<false, false>(qkv, y, lse, bound_log2, B, L, H, only_if_online, stream);
+}
+template <bool PF, bool QT>
+static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                                int only_if_online, cudaStream_t stream) {
   OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd_db: bad arguments");
   AttnDbParams p;
   const int dh = H * 64;
@@ -299,12 +370,12 @@ int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* 
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES));
+    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<PF, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES));
     attr_set = true;
   }
   const long long grid = (long long)ceil_div(L, 128) * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_fwd_db: grid too large");
-  attn_fwd_db_kernel<<<(unsigned)grid, DB_THREADS, DB_SMEM_BYTES, stream>>>(p);
+  attn_fwd_db_kernel<PF, QT><<<(unsigned)grid, DB_THREADS, DB_SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
   return 0;
 }

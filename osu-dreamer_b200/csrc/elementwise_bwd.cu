@@ -488,7 +488,11 @@ int launch_swiglu_norm_bwd(const void* vg, const void* dhn, const float* rinv, v
 // 3-step shuffles.  dq can be taken straight from the fp32 accumulator of the single-pass attention backward
 // (dq_acc, scaled by dq_scale) when its fallback flag is clear, which replaces that path's convert pass.
 static constexpr int QKB = 128;
+// gin aliases dqkv: every element is read (through gin) by the thread that later overwrites it and by no other
+// thread, so declaring the read side const/restrict is safe and lets the compiler hoist the loads of the next
+// rows above the stores of the current one (several rows in flight per warp; 0.65 -> ms before / after in DESIGN.md).
 __global__ void __launch_bounds__(256) qknorm_rope_bwd_kernel(__nv_bfloat16* __restrict__ dqkv,
+                                                              const __nv_bfloat16* __restrict__ gin,
                                                               const __nv_bfloat16* __restrict__ raw,
                                                               const float* __restrict__ rope,
                                                               const float* __restrict__ qw, const float* __restrict__ kw,
@@ -518,76 +522,95 @@ __global__ void __launch_bounds__(256) qknorm_rope_bwd_kernel(__nv_bfloat16* __r
 #pragma unroll
   for (int e = 0; e < 4; ++e) csv[e] = 0.f;
 
-#pragma unroll 2
-  for (int l = l0; l < l1; ++l) {
-    const size_t t = (size_t)b * L + l;
-    __nv_bfloat16* drow = dqkv + t * 3072;
-    const __nv_bfloat16* xrow = raw + t * 3072;
-    const uint2 xa = *reinterpret_cast<const uint2*>(xrow + col);
-    const uint2 xb = *reinterpret_cast<const uint2*>(xrow + col + 32);
-    const uint2 gv = *reinterpret_cast<const uint2*>(drow + vcol);
-    const float4 cc = *reinterpret_cast<const float4*>(rope + (size_t)l * 64 + 4 * j);
-    const float4 sn = *reinterpret_cast<const float4*>(rope + (size_t)l * 64 + 32 + 4 * j);
-    float gy[8];
-    if (from_acc) {
-      const float* arow = dq_acc + t * 1024 + (col);
-      const float4 a0 = *reinterpret_cast<const float4*>(arow);
-      const float4 a1 = *reinterpret_cast<const float4*>(arow + 32);
-      gy[0] = a0.x * dq_scale, gy[1] = a0.y * dq_scale, gy[2] = a0.z * dq_scale, gy[3] = a0.w * dq_scale;
-      gy[4] = a1.x * dq_scale, gy[5] = a1.y * dq_scale, gy[6] = a1.z * dq_scale, gy[7] = a1.w * dq_scale;
-    } else {
-      const uint2 ga = *reinterpret_cast<const uint2*>(drow + col);
-      const uint2 gb = *reinterpret_cast<const uint2*>(drow + col + 32);
-      unpack_bf16x4(ga, gy);
-      unpack_bf16x4(gb, gy + 4);
-    }
-    float xx[8], vv[4];
-    unpack_bf16x4(xa, xx);
-    unpack_bf16x4(xb, xx + 4);
-    unpack_bf16x4(gv, vv);
+  constexpr int R = 4;  // rows per batch: all loads of a batch are issued before any of its math
+  for (int lb = l0; lb < l1; lb += R) {
+    uint2 xa[R], xb[R], gv[R];
+    uint4 g0[R], g1[R];  // dq / dk: 4 + 4 fp32 (from the accumulator) or 4 + 4 bf16 in .x/.y
 #pragma unroll
-    for (int e = 0; e < 4; ++e) csv[e] += vv[e];
-    const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
-    const float sv[4] = {sn.x, sn.y, sn.z, sn.w};
-    // inverse rotation: da = g1*c + g2*s ; db = -g1*s + g2*c
-    float da[8];
-    float ss = 0.f;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      da[e] = gy[e] * cv[e] + gy[4 + e] * sv[e];
-      da[4 + e] = gy[4 + e] * cv[e] - gy[e] * sv[e];
-      ss = fmaf(xx[e], xx[e], ss);
-      ss = fmaf(xx[4 + e], xx[4 + e], ss);
+    for (int r = 0; r < R; ++r) {
+      const int l = min(lb + r, l1 - 1);  // tail rows re-read the last row (results discarded)
+      const size_t t = (size_t)b * L + l;
+      const __nv_bfloat16* grow = gin + t * 3072;
+      const __nv_bfloat16* xrow = raw + t * 3072;
+      xa[r] = *reinterpret_cast<const uint2*>(xrow + col);
+      xb[r] = *reinterpret_cast<const uint2*>(xrow + col + 32);
+      gv[r] = *reinterpret_cast<const uint2*>(grow + vcol);
+      if (from_acc) {
+        const float* arow = dq_acc + t * 1024 + col;
+        g0[r] = *reinterpret_cast<const uint4*>(arow);
+        g1[r] = *reinterpret_cast<const uint4*>(arow + 32);
+      } else {
+        const uint2 ga = *reinterpret_cast<const uint2*>(grow + col);
+        const uint2 gb = *reinterpret_cast<const uint2*>(grow + col + 32);
+        g0[r] = make_uint4(ga.x, ga.y, 0u, 0u);
+        g1[r] = make_uint4(gb.x, gb.y, 0u, 0u);
+      }
     }
-    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-    const float r = rsqrtf(ss * (1.0f / 64.0f) + eps);
-    float n[8], dn[8];
-    float dot = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      n[e] = xx[e] * r;
-      dn[e] = da[e] * wv[e];
-      adw[e] = fmaf(da[e], n[e], adw[e]);
-      dot = fmaf(dn[e], n[e], dot);
-    }
-    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-    dot *= (1.0f / 64.0f);
-    uint32_t o[4];
+    for (int r = 0; r < R; ++r) {
+      const int l = lb + r;
+      if (l >= l1) break;  // block-uniform
+      const size_t t = (size_t)b * L + l;
+      __nv_bfloat16* drow = dqkv + t * 3072;
+      const float4 cc = *reinterpret_cast<const float4*>(rope + (size_t)l * 64 + 4 * j);
+      const float4 sn = *reinterpret_cast<const float4*>(rope + (size_t)l * 64 + 32 + 4 * j);
+      float gy[8];
+      if (from_acc) {
+        gy[0] = __uint_as_float(g0[r].x) * dq_scale, gy[1] = __uint_as_float(g0[r].y) * dq_scale;
+        gy[2] = __uint_as_float(g0[r].z) * dq_scale, gy[3] = __uint_as_float(g0[r].w) * dq_scale;
+        gy[4] = __uint_as_float(g1[r].x) * dq_scale, gy[5] = __uint_as_float(g1[r].y) * dq_scale;
+        gy[6] = __uint_as_float(g1[r].z) * dq_scale, gy[7] = __uint_as_float(g1[r].w) * dq_scale;
+      } else {
+        unpack_bf16x4(make_uint2(g0[r].x, g0[r].y), gy);
+        unpack_bf16x4(make_uint2(g1[r].x, g1[r].y), gy + 4);
+      }
+      float xx[8], vv[4];
+      unpack_bf16x4(xa[r], xx);
+      unpack_bf16x4(xb[r], xx + 4);
+      unpack_bf16x4(gv[r], vv);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float d0 = r * (dn[2 * e] - n[2 * e] * dot), d1 = r * (dn[2 * e + 1] - n[2 * e + 1] * dot);
-      o[e] = pack_bf16(d0, d1);
-      // the bias gradient is the column sum of what the GEMMs will read, i.e. of the bf16-rounded values
-      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&o[e]);
-      cs[2 * e] += __low2float(h2);
-      cs[2 * e + 1] += __high2float(h2);
+      for (int e = 0; e < 4; ++e) csv[e] += vv[e];
+      const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
+      const float sv[4] = {sn.x, sn.y, sn.z, sn.w};
+      // inverse rotation: da = g1*c + g2*s ; db = -g1*s + g2*c
+      float da[8];
+      float ss = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        da[e] = gy[e] * cv[e] + gy[4 + e] * sv[e];
+        da[4 + e] = gy[4 + e] * cv[e] - gy[e] * sv[e];
+        ss = fmaf(xx[e], xx[e], ss);
+        ss = fmaf(xx[4 + e], xx[4 + e], ss);
+      }
+      ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      const float rs = rsqrtf(ss * (1.0f / 64.0f) + eps);
+      float n[8], dn[8];
+      float dot = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        n[e] = xx[e] * rs;
+        dn[e] = da[e] * wv[e];
+        adw[e] = fmaf(da[e], n[e], adw[e]);
+        dot = fmaf(dn[e], n[e], dot);
+      }
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot *= (1.0f / 64.0f);
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d0 = rs * (dn[2 * e] - n[2 * e] * dot), d1 = rs * (dn[2 * e + 1] - n[2 * e + 1] * dot);
+        o[e] = pack_bf16(d0, d1);
+        // the bias gradient is the column sum of what the GEMMs will read, i.e. of the bf16-rounded values
+        cs[2 * e] += __uint_as_float(o[e] << 16);
+        cs[2 * e + 1] += __uint_as_float(o[e] & 0xffff0000u);
+      }
+      *reinterpret_cast<uint2*>(drow + col) = make_uint2(o[0], o[1]);
+      *reinterpret_cast<uint2*>(drow + col + 32) = make_uint2(o[2], o[3]);
     }
-    *reinterpret_cast<uint2*>(drow + col) = make_uint2(o[0], o[1]);
-    *reinterpret_cast<uint2*>(drow + col + 32) = make_uint2(o[2], o[3]);
   }
   // ---- column sums: one global atomic per column per block
 #pragma unroll
@@ -617,7 +640,8 @@ int launch_qknorm_rope_bwd(void* dqkv, const void* raw, const float* rope, const
                            float* dqw, float* dkw, float* dbias, const float* dq_acc, const int* dq_flag,
                            float dq_scale, int B, int L, cudaStream_t s) {
   dim3 grid(ceil_div(L, QKB), B);
-  qknorm_rope_bwd_kernel<<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(raw),
+  qknorm_rope_bwd_kernel<<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(dqkv), static_cast<const __nv_bfloat16*>(dqkv),
+                                              static_cast<const __nv_bfloat16*>(raw),
                                               rope, qw, kw, dqw, dkw, dbias, dq_acc, dq_flag, dq_scale, L);
   OSD_LAUNCHED();
   return 0;

@@ -152,6 +152,16 @@ static int proj_cl(const float* const* P, const PackedW& W, int mode, int l, con
   return launch_gemm(g, s);
 }
 
+// forward attention kernel of the model: variant 7 (double-buffered S, Q tile resident in TMEM); OSD_ATTN_FWD=<n>
+// selects another variant for A/B measurements
+static int attn_fwd_variant() {
+  static const int v = [] {
+    const char* e = getenv("OSD_ATTN_FWD");
+    return (e != nullptr && e[0] >= '0' && e[0] <= '9') ? atoi(e) : 7;
+  }();
+  return v;
+}
+
 struct FwdCtx {
   const float* const* P;
   PackedW W;
@@ -202,7 +212,8 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
     if (X)
       OSD_TRY(launch_attn_fwd_x3(lb + pl.qkv, lb + pl.y, nullptr, c.W.bound(l), B, L, 16, s));
     else
-      OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), c.W.bound(l), B, L, 16, 4,
+      OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), c.W.bound(l), B, L, 16,
+                              attn_fwd_variant(),
                               s));
     GemmArgs o;
     o.A = lb + pl.y; o.B = c.W.out(l); o.lda = 1024 * km; o.ldb = 1024 * km; o.M = T; o.N = 512; o.K = 1024;

@@ -50,6 +50,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (test_wait never suspends): issue it early, consume the predicate after independent work
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded spin: a pipeline bug must surface as a trap (CUDA error on the host), never as a hung GPU.
 #ifndef OSD_WATCHDOG_CYCLES
 #define OSD_WATCHDOG_CYCLES (20ll * 1000 * 1000 * 1000)  // ~10 s at 2 GHz
