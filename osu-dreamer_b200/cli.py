@@ -135,12 +135,31 @@ def fit_denoiser(config: str, ckpt_path: str | None, synthetic: bool, max_steps:
         dist.destroy_process_group()
 
 
+@click.command('predict', context_settings=dict(ignore_unknown_options=True, allow_extra_args=True))
+@click.pass_context
+def predict(ctx: click.Context):
+    """generate osu!std maps from raw audio: the reference's own `predict` command (scripts/predict.py:21-100, same
+    options) with its `diffusion.sample` call (models/inference/model.py:50) running on the B200 path.
+
+    The audio front end, the latent / style models and the `.osu` codec are the reference's (outside this package), so
+    an importable reference checkout (`osu_dreamer` on sys.path, e.g. PYTHONPATH=/path/to/osu-dreamer) is required."""
+    if not torch.cuda.is_available():
+        raise click.ClickException('predict needs a CUDA device: the B200 path has no CPU fallback')
+    try:
+        install()
+        from osu_dreamer.scripts.predict import predict as ref_predict
+    except ImportError as e:
+        raise click.ClickException(f'predict needs an importable reference checkout (osu_dreamer on sys.path): {e}')
+    ref_predict.main(args=list(ctx.args), standalone_mode=False)
+
+
 @click.group()
 def main():
     pass
 
 
 main.add_command(fit_denoiser)
+main.add_command(predict)
 
 if __name__ == '__main__':
     main()

@@ -74,6 +74,21 @@ def test_trainer_from_reference_yaml_schema():
     assert tr.gradient_clip_val == 1.0 and abs(tr.current_lr() - 3e-4 * 0.3) < 1e-12
 
 
+def test_cli_commands_fail_loudly_without_cuda():
+    """fit-denoiser / predict are the reference's two commands for this path (osu_dreamer/__main__.py:19-29); without
+    a CUDA device both must refuse (no CPU fallback) with a clean click error, not a traceback"""
+    from click.testing import CliRunner
+    from osu_dreamer_b200.cli import main
+    assert {'fit-denoiser', 'predict'} <= set(main.commands)
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = CliRunner().invoke(main, ['fit-denoiser', '-c', os.path.join(root, 'osu-dreamer_b200', 'denoiser.yml'), '--synthetic'])
+    assert r.exit_code != 0 and 'no CPU fallback' in r.output
+    r = CliRunner().invoke(main, ['predict', '--model-path', 'x.pt', '--audio-file', 'a.mp3'])
+    assert r.exit_code != 0 and 'no CPU fallback' in r.output
+
+
 @pytest.mark.skipif(not refimport.available(), reason='reference checkout not present on this host')
 def test_reference_checkpoint_interchange():
     """a reference state dict loads into the mirror and back (strict), and the reference YAML parses."""
