@@ -491,7 +491,9 @@ int launch_final_norm_proj_out(const float* x, const float* Wo, const float* bo,
 
 // ------------------------------------------------------------------------------------------------
 // u head (model.py:58-65,99): dwconv3(6) -> 1x1 6->64 -> SiLU -> dwconv3(64) -> 1x1 64->64 -> SiLU -> sum over l.
-// Block = 64 tokens of one sample (+1 halo each side); fsum[b][64] accumulated with atomics (mean = /L).
+// Block = UH_TOK tokens of one sample (+1 halo each side) -> one partial row fpart[b][block][64]; u_final_kernel adds
+// the rows in block order (no float atomics: the sampler is then bit-reproducible run to run -- a last-bit change of u
+// is amplified by the bf16 roundings of the following forwards to ~1e-3 in individual outputs).
 struct UHeadW {
   const float *w0, *b0;  // [6][3], [6]
   const float *w1, *b1;  // [64][6], [64]
@@ -499,7 +501,7 @@ struct UHeadW {
   const float *w4, *b4;  // [64][64], [64]
 };
 static constexpr int UH_TOK = 32;
-__global__ void __launch_bounds__(256) u_head_kernel(const float* __restrict__ xt, UHeadW w, float* __restrict__ fsum,
+__global__ void __launch_bounds__(256) u_head_kernel(const float* __restrict__ xt, UHeadW w, float* __restrict__ fpart,
                                                      float* __restrict__ h1_save, float* __restrict__ h2pre_save, int L) {
   __shared__ float c1[UH_TOK + 2][6];
   __shared__ float h1[UH_TOK + 2][65];
@@ -561,20 +563,23 @@ __global__ void __launch_bounds__(256) u_head_kernel(const float* __restrict__ x
     red[grp][u] = part;
   }
   __syncthreads();
-  if (tid < 64) atomicAdd(fsum + (size_t)b * 64 + tid, red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid]);
+  if (tid < 64)
+    fpart[((size_t)b * gridDim.x + blockIdx.x) * 64 + tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
 }
-int launch_u_head(const float* xt, const float* const* w8, float* fsum, float* h1_save, float* h2pre_save, int B,
+size_t u_head_partial_floats(int B, int L) { return (size_t)B * ceil_div(L, UH_TOK) * 64; }
+int launch_u_head(const float* xt, const float* const* w8, float* fpart, float* h1_save, float* h2pre_save, int B,
                   int L, cudaStream_t stream) {
   UHeadW w{w8[0], w8[1], w8[2], w8[3], w8[4], w8[5], w8[6], w8[7]};
-  OSD_CUDA(cudaMemsetAsync(fsum, 0, (size_t)B * 64 * sizeof(float), stream));
   dim3 grid(ceil_div(L, UH_TOK), B);
-  u_head_kernel<<<grid, 256, 0, stream>>>(xt, w, fsum, h1_save, h2pre_save, L);
+  u_head_kernel<<<grid, 256, 0, stream>>>(xt, w, fpart, h1_save, h2pre_save, L);
   OSD_LAUNCHED();
   return 0;
 }
 
 // u = u_scale * softplus(u_out(f * (1 + scale) + shift)),  f = fsum / L,  (scale | shift) = u_mod(cg)  (model.py:99-102)
-__global__ void u_final_kernel(const float* __restrict__ fsum, const float* __restrict__ umod /*[B][128]*/,
+// fsum[b][64] = sum over the u_head blocks of fpart[b][block][64], in block order (kept for the backward).
+__global__ void u_final_kernel(const float* __restrict__ fpart, int nblk, float* __restrict__ fsum,
+                               const float* __restrict__ umod /*[B][128]*/,
                                const float* __restrict__ wout /*[64]*/, const float* __restrict__ bout, float u_scale,
                                float inv_L, float* __restrict__ u, int Bn) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -582,7 +587,10 @@ __global__ void u_final_kernel(const float* __restrict__ fsum, const float* __re
   if (b >= Bn) return;
   float acc = 0.f;
   for (int i = lane; i < 64; i += 32) {
-    const float f = fsum[(size_t)b * 64 + i] * inv_L;
+    float tot = 0.f;
+    for (int k = 0; k < nblk; ++k) tot += fpart[((size_t)b * nblk + k) * 64 + i];
+    fsum[(size_t)b * 64 + i] = tot;
+    const float f = tot * inv_L;
     const float fm = f * (1.f + umod[(size_t)b * 128 + i]) + umod[(size_t)b * 128 + 64 + i];
     acc = fmaf(wout[i], fm, acc);
   }
@@ -593,9 +601,10 @@ __global__ void u_final_kernel(const float* __restrict__ fsum, const float* __re
     u[b] = u_scale * sp;
   }
 }
-int launch_u_final(const float* fsum, const float* umod, const float* wout, const float* bout, float u_scale, int L,
-                   float* u, int B, cudaStream_t stream) {
-  u_final_kernel<<<ceil_div(B, 4), 128, 0, stream>>>(fsum, umod, wout, bout, u_scale, 1.0f / (float)L, u, B);
+int launch_u_final(const float* fpart, float* fsum, const float* umod, const float* wout, const float* bout,
+                   float u_scale, int L, float* u, int B, cudaStream_t stream) {
+  u_final_kernel<<<ceil_div(B, 4), 128, 0, stream>>>(fpart, ceil_div(L, UH_TOK), fsum, umod, wout, bout, u_scale,
+                                                     1.0f / (float)L, u, B);
   OSD_LAUNCHED();
   return 0;
 }

@@ -22,10 +22,11 @@ int launch_prenorm_mod_dwconv(const float* x, const float* mod, const float* wco
 int launch_swiglu_norm(const void* vg, void* hn, float* rinv_out, int is_fp32, int T, cudaStream_t stream);
 int launch_final_norm_proj_out(const float* x, const float* Wo, const float* bo, float* v, int B, int L,
                                cudaStream_t stream);
-int launch_u_head(const float* xt, const float* const* w8, float* fsum, float* h1_save, float* h2pre_save, int B,
+size_t u_head_partial_floats(int B, int L);  // fpart: one 64-float row per u_head block
+int launch_u_head(const float* xt, const float* const* w8, float* fpart, float* h1_save, float* h2pre_save, int B,
                   int L, cudaStream_t stream);
-int launch_u_final(const float* fsum, const float* umod, const float* wout, const float* bout, float u_scale, int L,
-                   float* u, int B, cudaStream_t stream);
+int launch_u_final(const float* fpart, float* fsum, const float* umod, const float* wout, const float* bout,
+                   float u_scale, int L, float* u, int B, cudaStream_t stream);
 int launch_sample_update(float* x, const float* v, const float* u, const float* eta_dev, int B, int L,
                          cudaStream_t stream);
 int launch_sample_eta(const float* u, int B, float sqrt_c0, int num_steps, float* eta_out, cudaStream_t stream);

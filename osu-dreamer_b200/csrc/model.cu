@@ -81,6 +81,7 @@ ActPlan make_plan(int B, int L, int a_batch, int mode, int save) {
   };
   a.x_final = save ? take2(T * 512 * 4) : a.x0;
   a.fsum = take2((size_t)B * 64 * 4);
+  a.fpart = take2(u_head_partial_floats(B, L) * 4);
   a.uh1 = save ? take2(T * 64 * 4) : 0;
   a.uh2 = save ? take2(T * 64 * 4) : 0;
   a.total = tot;
@@ -243,9 +244,10 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
   const float* uw[8] = {c.P[P_UH0_W], c.P[P_UH0_B], c.P[P_UH1_W], c.P[P_UH1_B],
                         c.P[P_UH3_W], c.P[P_UH3_B], c.P[P_UH4_W], c.P[P_UH4_B]};
   float* fsum = reinterpret_cast<float*>(c.ws + pl.fsum);
-  OSD_TRY(launch_u_head(xt, uw, fsum, c.save ? reinterpret_cast<float*>(c.ws + pl.uh1) : nullptr,
+  float* fpart = reinterpret_cast<float*>(c.ws + pl.fpart);
+  OSD_TRY(launch_u_head(xt, uw, fpart, c.save ? reinterpret_cast<float*>(c.ws + pl.uh1) : nullptr,
                         c.save ? reinterpret_cast<float*>(c.ws + pl.uh2) : nullptr, B, L, s));
-  OSD_TRY(launch_u_final(fsum, c.cond.umod(), c.P[P_UOUT_W], c.P[P_UOUT_B], sqrtf(2.0f * OSD_E), L, u, B, s));
+  OSD_TRY(launch_u_final(fpart, fsum, c.cond.umod(), c.P[P_UOUT_W], c.P[P_UOUT_B], sqrtf(2.0f * OSD_E), L, u, B, s));
   return 0;
 }
 

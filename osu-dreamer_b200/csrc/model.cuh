@@ -62,6 +62,7 @@ struct ActPlan {
   size_t layer_stride;  // 0 when buffers are shared by all layers
   size_t x_final;       // fp32 [T,512] output of the last layer (after the layer blocks)
   size_t fsum;          // fp32 [B,64]
+  size_t fpart;         // fp32 [B, u_head blocks, 64]: per-block partial sums of the u head (deterministic mean)
   size_t uh1, uh2;      // fp32 [T,64] u-head saves (training only)
   size_t total;
 };

@@ -83,6 +83,7 @@ class _Runtime:
         self.packed = None
         self.ws = {}
         self.rope = {}
+        self.graphs = {}
 
     def __deepcopy__(self, memo):
         return _Runtime()
@@ -254,19 +255,69 @@ class DiffusionModel(nn.Module):
         x = torch.randn(style.size(0), self.emb_dim, audio.size(-1), device=audio.device)
         return self.sample_from(audio, style, x, num_steps)
 
-    @torch.no_grad()
-    def sample_from(self, audio: Tensor, style: Tensor, x: Tensor, num_steps: int) -> Tensor:
-        rt = self._ensure(audio.device)
+    #: sampler launch mode: True = always replay a captured CUDA graph, False = never, None = automatic (graphs for
+    #: launch-bound shapes: B * l <= GRAPH_AUTO_TOKENS, e.g. `predict` on one song -- l ~ 1-2 k frames, B = a few
+    #: difficulties -- where the ~6500 kernels of a 64-step sample are each only microseconds long)
+    graph_sampler = None
+    GRAPH_AUTO_TOKENS = 32768
+
+    def _sample_eager(self, audio: Tensor, style: Tensor, x: Tensor, num_steps: int, eta_u0: Tensor):
+        """conditioning + the whole (num_steps + 1)-forward loop, in place on x; enqueues only (capturable)."""
+        rt = self._rt
         a_tok, cond = self._conditioning_tokens(audio, style)
         a_batch, _, L = audio.shape
         B = style.shape[0]
-        x = x.float().contiguous().clone()
         ws = self._workspace(B, L, a_batch, 0)
         extra = self._workspace(B, L, a_batch, 0, tag='sample')
-        self.last_eta_u0 = torch.empty(2, dtype=torch.float32, device=x.device)
-        lib.sample(rt.parr, rt.packed, self._mode(), a_tok, cond, self._rope(L, x.device), x, num_steps,
-                   float(self.c0), a_batch, ws, extra, self.last_eta_u0)
-        return x
+        rope = self._rope(L, x.device)
+        lib.sample(rt.parr, rt.packed, self._mode(), a_tok, cond, rope, x, num_steps, float(self.c0), a_batch, ws,
+                   extra, eta_u0)
+        return (a_tok, cond, ws, extra, rope, rt.parr, rt.packed)  # everything the enqueued work points at
+
+    @torch.no_grad()
+    def sample_from(self, audio: Tensor, style: Tensor, x: Tensor, num_steps: int) -> Tensor:
+        rt = self._ensure(audio.device)
+        a_batch, _, L = audio.shape
+        B = style.shape[0]
+        use_graph = self.graph_sampler if self.graph_sampler is not None else (B * L <= self.GRAPH_AUTO_TOKENS)
+        if not use_graph:
+            x = x.float().contiguous().clone()
+            self.last_eta_u0 = torch.empty(2, dtype=torch.float32, device=x.device)
+            self._sample_eager(audio.float().contiguous(), style.float().contiguous(), x, num_steps, self.last_eta_u0)
+            return x
+        # CUDA-graph path: first call of a shape runs eagerly (lazy module loading, one-time function attributes,
+        # workspace / rope allocation), the second captures, later ones only copy the inputs and replay.
+        key = (rt.key, B, L, a_batch, int(num_steps), audio.device)
+        ent = rt.graphs.get(key)
+        if ent is None:
+            if len(rt.graphs) > 4:
+                rt.graphs.clear()
+            x = x.float().contiguous().clone()
+            self.last_eta_u0 = torch.empty(2, dtype=torch.float32, device=x.device)
+            self._sample_eager(audio.float().contiguous(), style.float().contiguous(), x, num_steps, self.last_eta_u0)
+            rt.graphs[key] = 'warm'
+            return x
+        if ent == 'warm':
+            dev = audio.device
+            st = {'audio': torch.empty(a_batch, audio.shape[1], L, dtype=torch.float32, device=dev),
+                  'style': torch.empty(B, style.shape[1], dtype=torch.float32, device=dev),
+                  'x': torch.empty(B, self.emb_dim, L, dtype=torch.float32, device=dev),
+                  'eta_u0': torch.empty(2, dtype=torch.float32, device=dev)}
+            st['audio'].copy_(audio)
+            st['style'].copy_(style)
+            st['x'].copy_(x)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st['keep'] = self._sample_eager(st['audio'], st['style'], st['x'], num_steps, st['eta_u0'])
+            st['graph'] = g
+            ent = rt.graphs[key] = st
+        ent['audio'].copy_(audio)
+        ent['style'].copy_(style)
+        ent['x'].copy_(x)
+        ent['graph'].replay()
+        self.last_eta_u0 = ent['eta_u0'].clone()
+        return ent['x'].clone()
 
 
 Denoiser = DiffusionModel  # the north-star's name for the same module
