@@ -20,7 +20,7 @@ import click
 import torch
 import yaml
 
-from .data import LatentWindows, batches, split_mapsets, synthetic_batches
+from .data import DeviceFeeder, LatentWindows, split_mapsets, synthetic_batches
 from .trainer import DiffusionTrainer
 
 
@@ -104,8 +104,9 @@ def fit_denoiser(config: str, ckpt_path: str | None, synthetic: bool, max_steps:
         def epochs():
             e = 0
             while max_epochs < 0 or e < max_epochs:
-                yield batches(LatentWindows(train_sets, d['seq_len'], d.get('shuffle_buffer_size', 1),
-                                            d.get('max_per_map', -1), seed=e), d['batch_size'], rank, world)
+                yield DeviceFeeder(LatentWindows(train_sets, d['seq_len'], d.get('shuffle_buffer_size', 1),
+                                                 d.get('max_per_map', -1), seed=e), d['batch_size'], rank, world,
+                                   device=torch.device('cuda', local))
                 e += 1
     t0, best = time.time(), float('inf')
     for epoch, it in enumerate(epochs()):

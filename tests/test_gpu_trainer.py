@@ -126,3 +126,33 @@ def test_first_step_matches_oracle_adamw(oracle_sd):
         worst = max(worst, 1 - agree)
     print('worst sign disagreement of the first update', worst)
     assert worst < 0.05
+
+
+@pytest.mark.gpu
+def test_device_feeder_overlapped_h2d_matches_host_batches(tmp_path):
+    """DeviceFeeder: pinned ring + side-stream H2D; the device batches must equal the host collation, in order, also
+    when the consumer is slower or faster than the producer and the ring wraps several times"""
+    import time
+    import numpy as np
+    from osu_dreamer_b200.data import DeviceFeeder, LatentWindows, batches
+    rng = np.random.default_rng(0)
+    for ms in range(6):
+        d = tmp_path / f'set{ms}'
+        d.mkdir()
+        l = 900 + 41 * ms
+        np.save(d / 'h.npy', rng.standard_normal((128, l)).astype(np.float32))
+        for k in range(3):
+            np.savez(d / f'm{k}.latent.npz', z=rng.standard_normal((6, l)).astype(np.float32),
+                     s=rng.standard_normal(32).astype(np.float32), labels=rng.random(5).astype(np.float32))
+    sets = sorted(p for p in tmp_path.iterdir() if p.is_dir())
+    direct = list(batches(LatentWindows(sets, 96, 8, -1, seed=5), 4, pin=False))
+    assert len(direct) >= 12
+    for delay in (0.0, 0.01):
+        got = []
+        for b in DeviceFeeder(LatentWindows(sets, 96, 8, -1, seed=5), 4, device='cuda', depth=2):
+            assert all(t.is_cuda for t in b)
+            got.append(tuple((t * 1.0).cpu() for t in b))  # consume on the current stream
+            time.sleep(delay)
+        assert len(got) == len(direct)
+        for a, b in zip(direct, got):
+            assert all(torch.equal(x, y) for x, y in zip(a, b))

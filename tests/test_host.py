@@ -130,3 +130,71 @@ def test_latent_cache_reader(tmp_path):
     assert len(bs) >= 2 and bs[0][0].shape == (4, 128, 152) and bs[0][1].shape == (4, 6, 152) and bs[0][2].shape == (4, 32)
     full = list(LatentWindows(val, None))
     assert full[0].z.shape[0] == 6 and full[0].h.shape[1] == full[0].z.shape[1]
+
+
+def _make_cache(root, n_sets=5, maps_per_set=3, seed=0, h_dtype=np.float32):
+    rng = np.random.default_rng(seed)
+    for ms in range(n_sets):
+        d = root / f'set{ms}'
+        d.mkdir()
+        l = 700 + 53 * ms
+        np.save(d / 'h.npy', rng.standard_normal((128, l)).astype(h_dtype))
+        for k in range(maps_per_set):
+            np.savez(d / f'm{k}.latent.npz', z=rng.standard_normal((6, l)).astype(np.float32),
+                     s=rng.standard_normal(32).astype(np.float32), labels=rng.random(5).astype(np.float32))
+    return sorted(p for p in root.iterdir() if p.is_dir())
+
+
+@pytest.mark.skipif(not refimport.available(), reason='reference checkout not present on this host')
+@pytest.mark.parametrize('seq_len,buf,mpm', [(160, 1, -1), (160, 7, 2), (300, 16, -1), (None, 1, -1)])
+def test_latent_windows_match_reference_stream(tmp_path, seq_len, buf, mpm):
+    """same cache, same global seeds -> the reader yields the reference LatentDataset's samples, in its order
+    (osu_dreamer/data/modules/latent.py:86-149, single-process path)"""
+    import sys
+    refimport._install_stubs()
+    if refimport.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, refimport.REFERENCE_ROOT)
+    from osu_dreamer.data.modules.latent import LatentDataset
+    from osu_dreamer_b200.data import LatentWindows
+    sets = _make_cache(tmp_path)
+    torch.manual_seed(123)
+    ref = list(LatentDataset(sets, seq_len, buf, mpm))
+    torch.manual_seed(123)
+    ours = list(LatentWindows(sets, seq_len, buf, mpm, rng='global'))
+    assert len(ref) == len(ours) and len(ref) > 0
+    for a, b in zip(ref, ours):
+        for x, y in zip(a, b):
+            assert x.dtype == y.dtype and torch.equal(x, y)
+
+
+def test_prefetcher_order_errors_and_pinned_batches(tmp_path):
+    from osu_dreamer_b200.data import LatentWindows, Prefetcher, batches
+    sets = _make_cache(tmp_path, h_dtype=np.float16)  # a half-precision cache is converted on the way out
+    direct = list(batches(LatentWindows(sets, 128, 4, -1, seed=3), 4, pin=False))
+    pre = list(Prefetcher(batches(LatentWindows(sets, 128, 4, -1, seed=3), 4, pin=False), depth=2))
+    assert len(direct) == len(pre) > 2 and direct[0][0].dtype == torch.float32
+    for a, b in zip(direct, pre):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+    # rank sharding: rank r takes batch k*world + r; every rank takes the same number of steps (a trailing
+    # incomplete round is dropped, otherwise the gradient all-reduce of the last step would hang)
+    for world in (2, 3):
+        per_rank = [list(batches(LatentWindows(sets, 128, 4, -1, seed=3), 4, rank=r, world=world, pin=False)) for r in range(world)]
+        assert all(len(p) == len(direct) // world for p in per_rank)
+        for r, p in enumerate(per_rank):
+            for k, b in enumerate(p):
+                assert torch.equal(b[0], direct[k * world + r][0]) and torch.equal(b[2], direct[k * world + r][2])
+    # the feeder (host mode without a GPU: recycled buffers, background thread) yields the same batches
+    from osu_dreamer_b200.data import DeviceFeeder
+    fed = list(DeviceFeeder(LatentWindows(sets, 128, 4, -1, seed=3), 4, device=None, depth=2))
+    assert len(fed) == len(direct)
+    for a, b in zip(direct, fed):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+    def boom():
+        yield direct[0]
+        raise RuntimeError('loader failed')
+    p = Prefetcher(boom())
+    next(p)
+    with pytest.raises(RuntimeError, match='loader failed'):
+        next(p)
+    p.close()
