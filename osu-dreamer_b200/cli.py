@@ -44,19 +44,64 @@ def build_trainer(cfg: dict) -> DiffusionTrainer:
     return DiffusionTrainer(**m, gradient_clip_val=float(clip))
 
 
+def _plain(x):
+    """dataclasses -> dicts (recursively): the checkpoint must unpickle without this package, and the reference's
+    `dataclass_from_dict` (models/inference/artifact.py:52-71) rebuilds its own args classes from dicts"""
+    import dataclasses
+    if dataclasses.is_dataclass(x) and not isinstance(x, type):
+        return {f.name: _plain(getattr(x, f.name)) for f in dataclasses.fields(x)}
+    if isinstance(x, dict):
+        return {k: _plain(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return type(x)(_plain(v) for v in x)
+    return x
+
+
 def save_checkpoint(path: str, tr: DiffusionTrainer, epoch: int):
-    """Lightning-shaped checkpoint: what export-inference reads (models/inference/artifact.py:18-42)."""
-    hp = dict(tr.hparams)
-    torch.save({'state_dict': {k: v.detach().cpu() for k, v in tr.state_dict().items()}, 'hyper_parameters': hp,
+    """Lightning-shaped checkpoint (`state_dict` with the reference's keys diffusion.* / diffusion_ema.module.* /
+    diffusion_ema.n_averaged, `hyper_parameters`, `global_step`, `epoch`): what the reference's export-inference
+    reads (models/inference/artifact.py:15-35).  Plain tensors / dicts only."""
+    torch.save({'state_dict': {k: v.detach().cpu() for k, v in tr.state_dict().items()},
+                'hyper_parameters': _plain(dict(tr.hparams)),
                 'global_step': tr.global_step, 'epoch': epoch,
                 'optimizer_state': {k: tr._opt[k].cpu() for k in ('m', 'v')} if tr._opt else None}, path)
 
 
 def load_checkpoint(path: str, tr: DiffusionTrainer):
+    """resume: weights + EMA (+ AdamW moments and the step count when the checkpoint carries them; a checkpoint
+    written by the reference's Lightning run restores weights, EMA and the step)."""
     ck = torch.load(path, map_location='cpu', weights_only=False)
     tr.load_state_dict(ck['state_dict'])
     tr.global_step = int(ck.get('global_step', 0))
+    opt = ck.get('optimizer_state')
+    if opt is not None:
+        tr._opt = {'m': opt['m'].clone(), 'v': opt['v'].clone()}  # adopted by configure_optimizers when sizes match
     return ck
+
+
+def save_inference(latent_ckpt_path: str, denoiser_ckpt_path: str, style_ckpt_path: str, output_path: str):
+    """`export-inference` (scripts/export_inference.py:6-13, models/inference/artifact.py:9-42): one artifact
+    {'hparams', 'state_dict'} with latent.* from the latent checkpoint and the EMA weights of the denoiser and the
+    style model renamed to diffusion.* / style.*; the reference's `load_inference` / `predict` read it."""
+    ck = {k: torch.load(p, map_location='cpu', weights_only=False)
+          for k, p in (('latent', latent_ckpt_path), ('denoiser', denoiser_ckpt_path), ('style', style_ckpt_path))}
+    hp = {k: ck['latent']['hyper_parameters'][k] for k in ('emb_dim', 'style_dim', 'n_downs', 'stride', 'latent_args')}
+    hp['diffusion_args'] = ck['denoiser']['hyper_parameters']['diffusion_args']
+    hp['style_args'] = ck['style']['hyper_parameters']['style_args']
+    sd = {k: v for k, v in ck['latent']['state_dict'].items() if k.startswith('latent.')}
+    for src, prefix, dst in (('denoiser', 'diffusion_ema.module.', 'diffusion.'), ('style', 'style_ema.module.', 'style.')):
+        sd.update({dst + k[len(prefix):]: v for k, v in ck[src]['state_dict'].items() if k.startswith(prefix)})
+    torch.save({'hparams': hp, 'state_dict': sd}, output_path)
+
+
+@click.command('export-inference')
+@click.option('--latent-ckpt-path', type=click.Path(exists=True, dir_okay=False), default='latent.ckpt', help='path to the latent checkpoint')
+@click.option('--denoiser-ckpt-path', type=click.Path(exists=True, dir_okay=False), default='denoiser.ckpt', help='path to the denoiser checkpoint')
+@click.option('--style-ckpt-path', type=click.Path(exists=True, dir_okay=False), default='style.ckpt', help='path to the style model checkpoint')
+@click.option('--output-path', type=click.Path(exists=False, dir_okay=False), default='inference.pt', help='artifact output path')
+def export_inference(latent_ckpt_path: str, denoiser_ckpt_path: str, style_ckpt_path: str, output_path: str):
+    """export an inference model artifact from training checkpoints"""
+    save_inference(latent_ckpt_path, denoiser_ckpt_path, style_ckpt_path, output_path)
 
 
 @click.command('fit-denoiser')
@@ -161,6 +206,7 @@ def main():
 
 main.add_command(fit_denoiser)
 main.add_command(predict)
+main.add_command(export_inference)
 
 if __name__ == '__main__':
     main()

@@ -79,7 +79,7 @@ def test_cli_commands_fail_loudly_without_cuda():
     a CUDA device both must refuse (no CPU fallback) with a clean click error, not a traceback"""
     from click.testing import CliRunner
     from osu_dreamer_b200.cli import main
-    assert {'fit-denoiser', 'predict'} <= set(main.commands)
+    assert {'fit-denoiser', 'predict', 'export-inference'} <= set(main.commands)
     if torch.cuda.is_available():
         pytest.skip('CUDA present')
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -100,6 +100,48 @@ def test_reference_checkpoint_interchange():
     from osu_dreamer_b200.cli import build_trainer
     cfg = yaml.safe_load(open(os.path.join(refimport.REFERENCE_ROOT, 'osu_dreamer/models/diffusion/model.yml')))
     assert build_trainer(cfg).val_batches == 8
+
+
+@pytest.mark.skipif(not refimport.available(), reason='reference checkout not present on this host')
+def test_checkpoint_feeds_reference_export_inference(tmp_path):
+    """a checkpoint written by this package goes through the REFERENCE's save_inference, and through this package's
+    export-inference, to the same artifact; the reference rebuilds its DiffusionModel from the artifact's hparams and
+    loads the EMA weights strictly (models/inference/artifact.py:9-49)"""
+    import sys
+    from osu_dreamer_b200.cli import build_trainer, load_checkpoint, save_checkpoint, save_inference
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = yaml.safe_load(open(os.path.join(root, 'osu-dreamer_b200', 'denoiser.yml')))
+    tr = build_trainer(cfg)
+    tr.diffusion.load_state_dict(O.make_state_dict(1234))
+    tr.diffusion_ema.module.load_state_dict(O.make_state_dict(77))
+    tr.global_step = 123
+    save_checkpoint(str(tmp_path / 'denoiser.ckpt'), tr, epoch=4)
+    ck = torch.load(tmp_path / 'denoiser.ckpt', weights_only=True)  # plain tensors / containers only: no pickled classes
+    assert ck['global_step'] == 123 and isinstance(ck['hyper_parameters']['diffusion_args'], dict)
+    latent_hp = dict(emb_dim=6, style_dim=32, n_downs=3, stride=3, latent_args=dict(h_dim=128))
+    torch.save({'hyper_parameters': latent_hp, 'state_dict': {'latent.proj_emb.weight': torch.zeros(128, 6, 1), 'other': torch.zeros(1)}},
+               tmp_path / 'latent.ckpt')
+    torch.save({'hyper_parameters': dict(style_args=dict(h_dim=256)), 'state_dict': {'style_ema.module.u_out.bias': torch.zeros(1),
+                                                                                     'style.u_out.bias': torch.ones(1)}},
+               tmp_path / 'style.ckpt')
+    ns = refimport.import_reference()
+    refimport._install_stubs()
+    from osu_dreamer.models.inference.artifact import save_inference as ref_save, dataclass_from_dict
+    paths = [str(tmp_path / f) for f in ('latent.ckpt', 'denoiser.ckpt', 'style.ckpt')]
+    ref_save(*paths, str(tmp_path / 'ref.pt'))
+    save_inference(*paths, str(tmp_path / 'ours.pt'))
+    a, b = torch.load(tmp_path / 'ref.pt', weights_only=True), torch.load(tmp_path / 'ours.pt', weights_only=True)
+    assert a['hparams'] == b['hparams'] and a['state_dict'].keys() == b['state_dict'].keys()
+    assert all(torch.equal(a['state_dict'][k], b['state_dict'][k]) for k in a['state_dict'])
+    assert sum(k.startswith('diffusion.') for k in a['state_dict']) == 164 and 'style.u_out.bias' in a['state_dict']
+    args = dataclass_from_dict(ns.DiffusionModelArgs, a['hparams']['diffusion_args'])
+    ref = ns.DiffusionModel(a['hparams']['emb_dim'], a['hparams']['latent_args']['h_dim'], a['hparams']['style_dim'], args)
+    ref.load_state_dict({k[len('diffusion.'):]: v for k, v in a['state_dict'].items() if k.startswith('diffusion.')}, strict=True)
+    assert torch.equal(ref.proj_in.weight, O.make_state_dict(77)['proj_in.weight'])  # the EMA copy, not the live weights
+    # resume round trip
+    tr2 = build_trainer(cfg)
+    load_checkpoint(str(tmp_path / 'denoiser.ckpt'), tr2)
+    assert tr2.global_step == 123 and torch.equal(tr2.diffusion.proj_in.weight, tr.diffusion.proj_in.weight)
 
 
 def test_flat_buffers_are_aligned():
