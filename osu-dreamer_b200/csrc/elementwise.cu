@@ -2,6 +2,8 @@
 // depthwise conv, SwiGLU + RMSNorm(1365), gated residual, output heads.  Token-major activations
 // [T = B*L, C] (C contiguous); one warp per token row unless noted.  All statistics in fp32.
 #include "kernels.cuh"
+
+#include <algorithm>
 #include "ptx.cuh"
 
 namespace osd {
@@ -392,28 +394,40 @@ __global__ void swiglu_norm_kernel(const T* __restrict__ vg, T* __restrict__ hn,
   const T* row = vg + (size_t)t * (2 * HIDP);
   float hs[44];  // 1408 / 32
   float ss = 0.f;
+  if constexpr (sizeof(T) == 2) {
+    // all 22 loads of the row are issued before the first use (5.6 KB in flight per warp): the kernel is a pure
+    // HBM stream and was latency-bound with the loads interleaved into the math
+    uint2 va[11], ga[11];
 #pragma unroll
-  for (int i = 0; i < 11; ++i) {  // 11 chunks of 128 columns; lane owns 4 consecutive
-    const int c0 = i * 128 + lane * 4;
-    float v[4], g[4];
-    if constexpr (sizeof(T) == 2) {
-      const uint2 a = *reinterpret_cast<const uint2*>(row + c0);
-      const uint2 bq = *reinterpret_cast<const uint2*>(row + HIDP + c0);
-      const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&a);
-      const __nv_bfloat162* bp = reinterpret_cast<const __nv_bfloat162*>(&bq);
-      v[0] = __low2float(ap[0]), v[1] = __high2float(ap[0]), v[2] = __low2float(ap[1]), v[3] = __high2float(ap[1]);
-      g[0] = __low2float(bp[0]), g[1] = __high2float(bp[0]), g[2] = __low2float(bp[1]), g[3] = __high2float(bp[1]);
-    } else {
-      const float4 a = *reinterpret_cast<const float4*>(row + c0);
-      const float4 bq = *reinterpret_cast<const float4*>(row + HIDP + c0);
-      v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
-      g[0] = bq.x, g[1] = bq.y, g[2] = bq.z, g[3] = bq.w;
+    for (int i = 0; i < 11; ++i) {
+      va[i] = *reinterpret_cast<const uint2*>(row + i * 128 + lane * 4);
+      ga[i] = *reinterpret_cast<const uint2*>(row + HIDP + i * 128 + lane * 4);
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float h = v[e] * silu_f(g[e]);
-      hs[4 * i + e] = h;
-      ss = fmaf(h, h, ss);
+    for (int i = 0; i < 11; ++i) {
+      float v[4], g[4];
+      unpack_bf16x4(va[i], v);
+      unpack_bf16x4(ga[i], g);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float h = v[e] * g[e] * __fdividef(1.0f, 1.0f + __expf(-g[e]));  // silu with the fast reciprocal (2 ulp)
+        hs[4 * i + e] = h;
+        ss = fmaf(h, h, ss);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 11; ++i) {  // 11 chunks of 128 columns; lane owns 4 consecutive
+      const int c0 = i * 128 + lane * 4;
+      const float4 a = *reinterpret_cast<const float4*>(row + c0);
+      const float4 bq = *reinterpret_cast<const float4*>(row + HIDP + c0);
+      const float v[4] = {a.x, a.y, a.z, a.w}, g[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float h = v[e] * silu_f(g[e]);
+        hs[4 * i + e] = h;
+        ss = fmaf(h, h, ss);
+      }
     }
   }
   ss = warp_sum(ss);
@@ -434,6 +448,69 @@ __global__ void swiglu_norm_kernel(const T* __restrict__ vg, T* __restrict__ hn,
     }
   }
 }
+// bf16 training / inference path: persistent, bulk-copy staged.  Each warp owns rows w, w + W, w + 2W ... and keeps
+// SWS_ST of them in flight as 1-D bulk copies (cp.async.bulk, one 5632-byte vg row each) into its private
+// shared-memory ring, so the bytes in flight (8 warps x 3 rows x 5.6 KB per SM) do not depend on registers or on how
+// the compiler schedules loads; the math then reads the row from shared memory (conflict-free 8-byte accesses).
+static constexpr int SWS_ST = 3, SWS_WARPS = 8, SWS_ROW = 2 * HIDP * 2;
+__global__ void __launch_bounds__(SWS_WARPS * 32, 1) swiglu_norm_stream_kernel(const __nv_bfloat16* __restrict__ vg,
+                                                                               __nv_bfloat16* __restrict__ hn,
+                                                                               float* __restrict__ rinv_out, int Tn) {
+  extern __shared__ __align__(128) uint8_t sws[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* ring = sws + (size_t)warp * SWS_ST * SWS_ROW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sws + (size_t)SWS_WARPS * SWS_ST * SWS_ROW) + warp * SWS_ST;
+  if (lane == 0) {
+    for (int i = 0; i < SWS_ST; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  const int stride = gridDim.x * SWS_WARPS;
+  const int first = blockIdx.x * SWS_WARPS + warp;
+  auto issue = [&](int k) {  // k-th row of this warp -> ring stage k % SWS_ST (lane 0 only)
+    const long long t = first + (long long)k * stride;
+    if (t < Tn) {
+      mbar_expect_tx(&bars[k % SWS_ST], SWS_ROW);
+      bulk_load_1d(ring + (k % SWS_ST) * SWS_ROW, vg + (size_t)t * 2 * HIDP, SWS_ROW, &bars[k % SWS_ST]);
+    }
+  };
+  if (lane == 0)
+    for (int k = 0; k < SWS_ST - 1; ++k) issue(k);
+  for (int k = 0;; ++k) {
+    const long long t = first + (long long)k * stride;
+    if (t >= Tn) break;
+    if (lane == 0) {
+      fence_proxy_async_smem();  // the stage refilled below was read (generic proxy) in the previous iteration
+      issue(k + SWS_ST - 1);
+    }
+    mbar_wait(&bars[k % SWS_ST], (k / SWS_ST) & 1);
+    const uint8_t* row = ring + (k % SWS_ST) * SWS_ROW;
+    float hs[44];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 11; ++i) {
+      const uint2 va = *reinterpret_cast<const uint2*>(row + (i * 128 + lane * 4) * 2);
+      const uint2 ga = *reinterpret_cast<const uint2*>(row + (HIDP + i * 128 + lane * 4) * 2);
+      float v[4], g[4];
+      unpack_bf16x4(va, v);
+      unpack_bf16x4(ga, g);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float h = v[e] * g[e] * __fdividef(1.0f, 1.0f + __expf(-g[e]));  // silu with the fast reciprocal (2 ulp)
+        hs[4 * i + e] = h;
+        ss = fmaf(h, h, ss);
+      }
+    }
+    __syncwarp();  // every lane has finished reading this stage before lane 0 may refill it
+    ss = warp_sum(ss);
+    const float inv = rsqrtf(ss * (1.0f / HID) + RMS_EPS);
+    if (rinv_out != nullptr && lane == 0) rinv_out[t] = inv;
+#pragma unroll
+    for (int i = 0; i < 11; ++i)
+      *reinterpret_cast<uint2*>(hn + (size_t)t * HIDP + i * 128 + lane * 4) =
+          make_uint2(pack_bf16(hs[4 * i] * inv, hs[4 * i + 1] * inv), pack_bf16(hs[4 * i + 2] * inv, hs[4 * i + 3] * inv));
+  }
+}
 // is_fp32 = 2: fp32 vg in, bf16 (hi | lo) hn out [T, 2*HIDP]
 int launch_swiglu_norm(const void* vg, void* hn, float* rinv_out, int is_fp32, int T, cudaStream_t stream) {
   if (is_fp32 == 2)
@@ -442,9 +519,17 @@ int launch_swiglu_norm(const void* vg, void* hn, float* rinv_out, int is_fp32, i
   else if (is_fp32)
     swiglu_norm_kernel<float><<<ceil_div(T, 8), 256, 0, stream>>>(static_cast<const float*>(vg),
                                                                   static_cast<float*>(hn), rinv_out, T, nullptr);
-  else
-    swiglu_norm_kernel<__nv_bfloat16><<<ceil_div(T, 8), 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(vg), static_cast<__nv_bfloat16*>(hn), rinv_out, T, nullptr);
+  else {
+    constexpr int smem = SWS_WARPS * SWS_ST * SWS_ROW + SWS_WARPS * SWS_ST * 8;
+    static bool set = false;
+    if (!set) {
+      OSD_CUDA(cudaFuncSetAttribute(swiglu_norm_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      set = true;
+    }
+    const int grid = std::min(ceil_div(T, SWS_WARPS), num_sms());
+    swiglu_norm_stream_kernel<<<grid, SWS_WARPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(vg),
+                                                                     static_cast<__nv_bfloat16*>(hn), rinv_out, T);
+  }
   OSD_LAUNCHED();
   return 0;
 }

@@ -327,6 +327,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// 8-byte read-only global load that the compiler may not sink towards its use (volatile): streaming kernels issue a
+// whole row of these up front so that enough bytes are in flight to cover HBM latency
+__device__ __forceinline__ uint2 ldg_stream_v2(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
 // 4 bf16 (8 bytes) -> 4 floats: a bf16 is the upper half of the fp32 with the same value
 __device__ __forceinline__ void unpack_bf16x4(uint2 q, float* f) {
   f[0] = __uint_as_float(q.x << 16), f[1] = __uint_as_float(q.x & 0xffff0000u);
