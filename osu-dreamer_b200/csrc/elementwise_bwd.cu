@@ -385,31 +385,60 @@ int launch_dwconv_prenorm_bwd(const void* dz2, const void* hmod, const float* x1
 // mean(dhn * hn) is a warp sum + an 11-entry exchange through shared memory (double-buffered: one barrier per
 // batch), and the outputs are produced from the registers of the same single read.
 static constexpr int HID = 1365, HIDP = 1408;
-static constexpr int SWB_ROWS = 128, SWB_R = 4, SWB_WARPS = HIDP / 128;
+static constexpr int SWB_ROWS = 128, SWB_R = 4, SWB_WARPS = HIDP / 128, SWB_ST = 3;
+static constexpr int SWB_VG_BYTES = SWB_R * 2 * HIDP * 2, SWB_D_BYTES = SWB_R * HIDP * 2;
+static constexpr int SWB_STAGE = SWB_VG_BYTES + SWB_D_BYTES;  // 4 rows of vg (contiguous) + 4 rows of dhn (contiguous)
+static constexpr int SWB_SMEM = SWB_ST * SWB_STAGE + 64;
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// Rows reach the block as 1-D bulk copies (cp.async.bulk): SWB_R consecutive rows of vg and of dhn are contiguous in
+// memory, so a stage is two copies; thread 0 keeps SWB_ST stages in flight (a stage is refilled right after the block
+// barrier that follows its register reads), so the bytes in flight do not depend on registers or on instruction
+// scheduling.
 __global__ void __launch_bounds__(SWB_WARPS * 32, 2) swiglu_norm_bwd_kernel(const __nv_bfloat16* __restrict__ vg,
                                                                          const __nv_bfloat16* __restrict__ dhn,
                                                                          const float* __restrict__ rinv,
                                                                          __nv_bfloat16* __restrict__ dvg,
                                                                          float* __restrict__ dbvg, int T) {
+  extern __shared__ __align__(128) uint8_t swb[];
   __shared__ float sdot[2][SWB_R][SWB_WARPS + 1];
+  uint64_t* full = reinterpret_cast<uint64_t*>(swb + SWB_ST * SWB_STAGE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = warp * 128 + lane * 4;
   const int t0 = blockIdx.x * SWB_ROWS;
   const int t1 = min(T, t0 + SWB_ROWS);
+  const int nb = (t1 - t0 + SWB_R - 1) / SWB_R;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SWB_ST; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int k) {  // batch k -> stage k % SWB_ST (thread 0 only); the last batch of a block may be short
+    if (k >= nb) return;
+    const int tb = t0 + k * SWB_R;
+    const int rows = min(SWB_R, t1 - tb);
+    uint8_t* st = swb + (k % SWB_ST) * SWB_STAGE;
+    mbar_expect_tx(&full[k % SWB_ST], (uint32_t)rows * (2 * HIDP * 2 + HIDP * 2));
+    bulk_load_1d(st, vg + (size_t)tb * 2 * HIDP, (uint32_t)rows * 2 * HIDP * 2, &full[k % SWB_ST]);
+    bulk_load_1d(st + SWB_VG_BYTES, dhn + (size_t)tb * HIDP, (uint32_t)rows * HIDP * 2, &full[k % SWB_ST]);
+  };
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < SWB_ST; ++k) issue(k);
+  }
   float csv[4] = {0.f, 0.f, 0.f, 0.f}, csg[4] = {0.f, 0.f, 0.f, 0.f};
-  int it = 0;
-  for (int tb = t0; tb < t1; tb += SWB_R, ++it) {
-    uint2 va[SWB_R], ga[SWB_R], da[SWB_R];
+  for (int k = 0; k < nb; ++k) {
+    const int tb = t0 + k * SWB_R;
+    const uint8_t* st = swb + (k % SWB_ST) * SWB_STAGE;
     float rr[SWB_R];
 #pragma unroll
-    for (int r = 0; r < SWB_R; ++r) {
-      const int t = min(tb + r, t1 - 1);  // tail rows re-read the last row (their results are discarded)
-      const __nv_bfloat16* row = vg + (size_t)t * 2 * HIDP;
-      va[r] = *reinterpret_cast<const uint2*>(row + c0);
-      ga[r] = *reinterpret_cast<const uint2*>(row + HIDP + c0);
-      da[r] = *reinterpret_cast<const uint2*>(dhn + (size_t)t * HIDP + c0);
-      rr[r] = rinv[t];
+    for (int r = 0; r < SWB_R; ++r) rr[r] = rinv[min(tb + r, t1 - 1)];
+    mbar_wait(&full[k % SWB_ST], (k / SWB_ST) & 1);
+    uint2 va[SWB_R], ga[SWB_R], da[SWB_R];
+#pragma unroll
+    for (int r = 0; r < SWB_R; ++r) {  // rows past t1 hold stale bytes of an earlier batch: finite, results discarded
+      const uint8_t* row = st + r * (2 * HIDP * 2);
+      va[r] = *reinterpret_cast<const uint2*>(row + c0 * 2);
+      ga[r] = *reinterpret_cast<const uint2*>(row + (HIDP + c0) * 2);
+      da[r] = *reinterpret_cast<const uint2*>(st + SWB_VG_BYTES + r * (HIDP * 2) + c0 * 2);
     }
     float part[SWB_R];
 #pragma unroll
@@ -427,16 +456,20 @@ __global__ void __launch_bounds__(SWB_WARPS * 32, 2) swiglu_norm_bwd_kernel(cons
     for (int r = 0; r < SWB_R; ++r) part[r] = warp_sum(part[r]);
     if (lane == 0) {
 #pragma unroll
-      for (int r = 0; r < SWB_R; ++r) sdot[it & 1][r][warp] = part[r];
+      for (int r = 0; r < SWB_R; ++r) sdot[k & 1][r][warp] = part[r];
     }
-    __syncthreads();
+    __syncthreads();  // (a) the row statistics are complete; (b) every thread has copied its part of stage k out
+    if (threadIdx.x == 0) {
+      fence_proxy_async_smem();
+      issue(k + SWB_ST);  // refill the stage just drained: SWB_ST batches stay in flight
+    }
 #pragma unroll
     for (int r = 0; r < SWB_R; ++r) {
       const int t = tb + r;
       if (t >= t1) break;  // block-uniform
       float dot = 0.f;
 #pragma unroll
-      for (int w = 0; w < SWB_WARPS; ++w) dot += sdot[it & 1][r][w];
+      for (int w = 0; w < SWB_WARPS; ++w) dot += sdot[k & 1][r][w];
       const float rinv_t = rr[r];
       dot = dot * rinv_t * (1.0f / HID);  // mean(dhn * hn), hn = hs * r
       float v[4], g[4], d[4];
@@ -471,7 +504,12 @@ __global__ void __launch_bounds__(SWB_WARPS * 32, 2) swiglu_norm_bwd_kernel(cons
 }
 int launch_swiglu_norm_bwd(const void* vg, const void* dhn, const float* rinv, void* dvg, float* dbvg, int T,
                            cudaStream_t s) {
-  swiglu_norm_bwd_kernel<<<ceil_div(T, SWB_ROWS), SWB_WARPS * 32, 0, s>>>(static_cast<const __nv_bfloat16*>(vg),
+  static bool set = false;
+  if (!set) {
+    OSD_CUDA(cudaFuncSetAttribute(swiglu_norm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWB_SMEM));
+    set = true;
+  }
+  swiglu_norm_bwd_kernel<<<ceil_div(T, SWB_ROWS), SWB_WARPS * 32, SWB_SMEM, s>>>(static_cast<const __nv_bfloat16*>(vg),
                                                                         static_cast<const __nv_bfloat16*>(dhn), rinv,
                                                                         static_cast<__nv_bfloat16*>(dvg), dbvg, T);
   OSD_LAUNCHED();
@@ -490,7 +528,8 @@ int launch_swiglu_norm_bwd(const void* vg, const void* dhn, const float* rinv, v
 static constexpr int QKB = 128;
 // gin aliases dqkv: every element is read (through gin) by the thread that later overwrites it and by no other
 // thread, so declaring the read side const/restrict is safe and lets the compiler hoist the loads of the next
-// rows above the stores of the current one (several rows in flight per warp; 0.65 -> ms before / after in DESIGN.md).
+// rows above the stores of the current one.  (A bulk-copy staged variant of this kernel -- 3 x 48 KB stages, one block
+// of 8 warps per SM -- was slower, 0.745 vs 0.516 ms: at 142 registers / 8 warps the per-row math bound it.)
 __global__ void __launch_bounds__(256) qknorm_rope_bwd_kernel(__nv_bfloat16* __restrict__ dqkv,
                                                               const __nv_bfloat16* __restrict__ gin,
                                                               const __nv_bfloat16* __restrict__ raw,
