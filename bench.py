@@ -283,7 +283,7 @@ def run_cuda(args):
             y, lse = lib.attn_fwd(qkv, Ba, L)
             dy = torch.randn(Ba * L, 1024, device=dev).to(torch.bfloat16)
             bound = torch.tensor([14.0], device=dev)  # randn scores / 8 stay far below 2^14: same kernel path the model runs
-            ms_f = time_kernel(lambda: lib.attn_fwd(qkv, Ba, L, bound_log2=bound, variant=4), iters=3, warm=1)
+            ms_f = time_kernel(lambda: lib.attn_fwd(qkv, Ba, L, bound_log2=bound, variant=7), iters=3, warm=1)  # the model's variant
             ms_b = time_kernel(lambda: lib.attn_bwd_fused(qkv, y, dy, lse, Ba, L), iters=3, warm=1)
             fl_f = 4.0 * Ba * 16 * L * L * 64
             kern = {'attn_fwd': {'ms': ms_f, 'tflops': fl_f / ms_f / 1e9},
@@ -291,15 +291,29 @@ def run_cuda(args):
             dom = 'attn_bwd_fused' if 8 * ms_b > 8 * ms_f else 'attn_fwd'
             ach = kern[dom]['tflops']
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact shape (B=16, L=8192), from the
-            # committed ncu --set full capture profiles/r01h_ncu_attention_summary.json
+            # latest committed ncu --set full capture (profiles/ncu_attention_summary_latest.json, written by
+            # tools/ncu_summary.py from tools/gpu_round.sh's capture of tools/prof_attn.py 16 8192)
             ncu_traffic = {'attn_bwd_fused': 1.622335e9 + 1.030786e9, 'attn_fwd': 0.805537e9 + 0.259025e9}
+            ncu_src = 'profiles/r01h_ncu_attention_summary.json'
+            try:
+                latest = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_attention_summary_latest.json')
+                gb = lambda v: float(v.split()[0]) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[v.split()[1]]
+                for kk in json.load(open(latest))['kernels']:
+                    tot = gb(kk['dram__bytes_read.sum']) + gb(kk['dram__bytes_write.sum'])
+                    if 'attn_bwd_fused_kernel' in kk['Kernel Name']:
+                        ncu_traffic['attn_bwd_fused'] = tot
+                    elif 'attn_fwd_db_kernel' in kk['Kernel Name']:
+                        ncu_traffic['attn_fwd'] = tot
+                ncu_src = 'profiles/ncu_attention_summary_latest.json'
+            except Exception:  # noqa: keep the constants of the r01h capture
+                pass
             alg_bytes = {'attn_bwd_fused': Ba * L * (3072 * 2 + 1024 * 2 + 2048 * 2 + 1024 * 4),  # q,k,v + dO~ in; dk,dv + fp32 dq out
                          'attn_fwd': Ba * L * (3072 * 2 + 1024 * 2)}
             line['roofline'] = {'bound': 'tensor', 'kernel': dom, 'achieved': ach, 'peak': peaks['tf_burst'],
                                 'unit': 'TFLOP/s', 'frac': ach / peaks['tf_burst'],
                                 'traffic': ncu_traffic[dom] if (Ba, L) == (16, 8192) else None,
                                 'peak_source': peaks['source'] + ', burst (kernel timed alone)',
-                                'traffic_note': 'DRAM bytes per launch from ncu (profiles/r01h_ncu_attention_summary.json) vs '
+                                'traffic_note': f'DRAM bytes per launch from ncu ({ncu_src}) vs '
                                                 f'{alg_bytes[dom] / 1e9:.2f} GB algorithmic: the fp32 dQ accumulator is partly evicted and '
                                                 're-read between its TMA reduce-adds (1.2x); K/V/Q/dO re-reads are served by L2',
                                 'flop_convention': 'algorithmic = 2 x forward (SURVEY 8(d)); the single-pass kernel executes 2.5 x forward '
