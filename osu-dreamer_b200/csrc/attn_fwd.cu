@@ -391,6 +391,7 @@ int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log
                     cudaStream_t stream) {
   OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd: bad arguments");
   if (variant == 4) return launch_attn_fwd_db(qkv, y, lse, bound_log2, B, L, H, stream);  // double-buffered S
+  if (variant == 8) return launch_attn_fwd_db_dr(qkv, y, lse, bound_log2, B, L, H, stream);  // direct exponent
   if (variant == 7) return launch_attn_fwd_db_qt(qkv, y, lse, bound_log2, B, L, H, stream);  // Q in TMEM
   if (variant == 6) return launch_attn_fwd_db_pf(qkv, y, lse, bound_log2, B, L, H, stream);  // + probes / S prefetch
   if (variant == 5) return launch_attn_fwd_w8(qkv, y, lse, bound_log2, B, L, H, stream);  // + 8 softmax warps

@@ -21,7 +21,8 @@ static constexpr int DB_T128 = 128 * 128;
 static constexpr int DB_T64 = 64 * 128;
 static constexpr int DB_STAGES = 3;
 static constexpr int DB_SMEM_TILES = DB_T128 + 2 * DB_STAGES * DB_T64;
-static constexpr int DB_SMEM_BYTES = DB_SMEM_TILES + 256;
+static constexpr int DB_ONES = 2048;  // variant 8: [16 x 64] bf16 tile of ones (B operand of the row-sum MMA)
+static constexpr int DB_SMEM_BYTES = DB_SMEM_TILES + DB_ONES + 256;
 static constexpr uint32_t DB_TMEM_COLS = 256;
 
 struct AttnDbParams {
@@ -46,10 +47,18 @@ __device__ __forceinline__ float db_ex2(float x) {
 // the math, and (b) issue the TMEM load of S_{j+1} before storing / publishing P_j, so the load latency hides behind
 // the store + fence + arrive tail.  ncu source view of the non-PF kernel: 10 % of the softmax warps' samples sit on
 // the s_full probe, 5 % on the o_ready probe, 7 % on the TMEM load and 9 % on the store tail.
+// DR (variant 8, needs QT; active when the bound is <= 60 octaves, else the kernel behaves like variant 7): fewer
+// instructions per score in the softmax warps, because the step is power-bound:
+//  * Q is multiplied by scale*log2(e) (and re-rounded to bf16) while it is copied into TMEM, so S arrives in octaves and
+//    P = 2^S needs no FFMA; without the "- bound" shift 2^S <= 2^60 and the 8192-term row sums stay far inside fp32 / bf16
+//    range, and the shift cancels in O / l anyway;
+//  * the row sum l = sum_j P_ij is accumulated by the tensor core: one extra N=16 MMA per kv step, P (TMEM) x a tile of
+//    ones (shared memory) into 16 more TMEM columns -- 1/8 of the PV MMA's time on a pipe that is 38 % busy -- instead
+//    of 32 FADD2 per thread and step; it sums the bf16-rounded P, the same values the PV MMA multiplies.
 // QT (variant 7): the Q tile is copied into TMEM once (columns [192, 224)) and is the A operand of S = Q K^T from
 // there (tcgen05.mma .ts), which halves the shared-memory operand reads of the kernel (Q 16 KB + K 8 KB + V 8 KB per
 // kv step -> 16 KB).
-template <bool PF, bool QT>
+template <bool PF, bool QT, bool DR = false>
 __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid_constant__ AttnDbParams p) {
   extern __shared__ uint8_t smem_raw[];
   if (p.only_if_online && p.bound_log2 != nullptr && *p.bound_log2 < 3.0e38f) return;
@@ -59,12 +68,19 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
   {
     uint32_t dyn;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    if (pad + DB_SMEM_TILES + 160 > dyn) __trap();
+    if (pad + DB_SMEM_TILES + DB_ONES + 160 > dyn) __trap();
   }
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + DB_T128;
   uint8_t* sV = sK + DB_STAGES * DB_T64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + DB_STAGES * DB_T64);
+  uint8_t* sOnes = sV + DB_STAGES * DB_T64;  // 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + DB_ONES);
+  // direct mode (DR): decided once per CTA from the bound
+  bool direct = false;
+  if (DR) {
+    const float bnd = p.bound_log2 != nullptr ? *p.bound_log2 : INFINITY;
+    direct = bnd <= 60.0f;
+  }
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [3]
   uint64_t* k_empty = bars + 4;   // [3]
@@ -131,6 +147,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
     if (elect_one()) {
       const uint32_t idesc_s = make_idesc(FMT_BF16, 0, 0, 128, 64);
       const uint32_t idesc_o = make_idesc(FMT_BF16, 0, 1, 128, 64);
+      const uint32_t idesc_l = make_idesc(FMT_BF16, 0, 0, 128, 16);
       const uint32_t aQ = smem_u32(sQ);
       const uint32_t tO = tmem_base + 128;
       auto issue_s = [&](int j) {
@@ -167,6 +184,13 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ts(tO, tP + k * 8, make_smem_desc(aV + k * 16 * 128, 0, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        if (DR && direct) {  // l += P_j x ones  (columns [224, 240))
+          const uint32_t aOnes = smem_u32(sOnes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ts(tmem_base + 224, tP + k * 8, make_smem_desc(aOnes + k * 32, 0, 1024), idesc_l,
+                        (j > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(&v_empty[st]);
         umma_commit(o_ready);
         if (j + 2 < n_kv) issue_s(j + 2);  // reuses S_{j&1}: issued after the MMA that read P_j from it
@@ -186,6 +210,17 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(rq[4 * u]), "=r"(rq[4 * u + 1]), "=r"(rq[4 * u + 2]), "=r"(rq[4 * u + 3])
                      : "r"(base + ((u ^ (row & 7)) << 4)));
+      if (DR && direct) {
+        const float cq = p.scale_log2;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const float lo = __uint_as_float(rq[u] << 16) * cq, hi = __uint_as_float(rq[u] & 0xffff0000u) * cq;
+          rq[u] = pack_bf16(lo, hi);
+        }
+        // the tile of ones: 2048 bytes, 16 per thread of the 128 softmax threads
+        *reinterpret_cast<uint4*>(sOnes + (threadIdx.x - 64) * 16) = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        fence_proxy_async_smem();
+      }
       __syncwarp();
       tmem_st32(tmem_base + 192 + lane_off, rq);
       tmem_wait_st();
@@ -193,11 +228,11 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(qt_ready);
     }
-    const float c = p.scale_log2;
+    const float c = (DR && direct) ? 1.0f : p.scale_log2;  // direct mode: Q was pre-scaled, S is already in octaves
     float bound = INFINITY;
     if (p.bound_log2 != nullptr) bound = __ldg(p.bound_log2);
     const bool fixed = bound < 3.0e38f;
-    float m = fixed ? bound / c : -INFINITY, l = 0.f;
+    float m = (DR && direct) ? 0.f : (fixed ? bound / c : -INFINITY), l = 0.f;
     const bool pf = PF && fixed;
     uint32_t r0[32], r1[32];
     bool have = false;  // r0 / r1 already hold (or are receiving) S_j
@@ -232,7 +267,13 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
       const float2 c2 = make_float2(c, c), n2 = make_float2(neg_mc, neg_mc);
       uint32_t pk[32];
       float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
-      if (valid >= 64) {
+      if (DR && direct && valid >= 64) {  // P = 2^S: no shift, no row sum (the tensor core accumulates it)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          pk[i >> 1] = pack_bf16(db_ex2(__uint_as_float(r0[i])), db_ex2(__uint_as_float(r0[i + 1])));
+          pk[16 + (i >> 1)] = pack_bf16(db_ex2(__uint_as_float(r1[i])), db_ex2(__uint_as_float(r1[i + 1])));
+        }
+      } else if (valid >= 64) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const float2 a = ffma2(make_float2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])), c2, n2);
@@ -299,6 +340,13 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
     }
     mbar_wait(o_ready, (n_kv - 1) & 1);
     tc_fence_after();
+    if (DR && direct) {  // the row sums accumulated by the ones-tile MMA (all 16 columns are equal)
+      uint32_t rl[16];
+      __syncwarp();
+      tmem_ld16(tmem_base + 224 + lane_off, rl);
+      tmem_wait_ld();
+      l = __uint_as_float(rl[0]);
+    }
     const float inv_l = 1.0f / l;
     const int q = q0 + row;
     const bool ok = q < p.L;
@@ -331,7 +379,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
 
 int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                              int only_if_online, cudaStream_t stream);
-template <bool PF, bool QT>
+template <bool PF, bool QT, bool DR = false>
 static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                                 int only_if_online, cudaStream_t stream);
 int launch_attn_fwd_db(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
@@ -342,6 +390,10 @@ int launch_attn_fwd_db_qt(const void* qkv, void* y, float* lse, const float* bou
                           cudaStream_t stream) {
   return launch_attn_fwd_db_t<false, true>(qkv, y, lse, bound_log2, B, L, H, 0, stream);
 }
+int launch_attn_fwd_db_dr(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                          cudaStream_t stream) {
+  return launch_attn_fwd_db_t<false, true, true>(qkv, y, lse, bound_log2, B, L, H, 0, stream);
+}
 int launch_attn_fwd_db_pf(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                           cudaStream_t stream) {
   return launch_attn_fwd_db_t<true, false>(qkv, y, lse, bound_log2, B, L, H, 0, stream);
@@ -350,7 +402,7 @@ int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* 
                              int only_if_online, cudaStream_t stream) {
   return launch_attn_fwd_db_t<false, false>(qkv, y, lse, bound_log2, B, L, H, only_if_online, stream);
 }
-template <bool PF, bool QT>
+template <bool PF, bool QT, bool DR>
 static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                                 int only_if_online, cudaStream_t stream) {
   OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd_db: bad arguments");
@@ -370,12 +422,12 @@ static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const floa
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<PF, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES));
+    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<PF, QT, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES));
     attr_set = true;
   }
   const long long grid = (long long)ceil_div(L, 128) * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_fwd_db: grid too large");
-  attn_fwd_db_kernel<PF, QT><<<(unsigned)grid, DB_THREADS, DB_SMEM_BYTES, stream>>>(p);
+  attn_fwd_db_kernel<PF, QT, DR><<<(unsigned)grid, DB_THREADS, DB_SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
   return 0;
 }

@@ -91,6 +91,8 @@ int launch_attn_fwd_db(const void* qkv, void* y, float* lse, const float* bound_
                        cudaStream_t stream);
 int launch_attn_fwd_db_qt(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                           cudaStream_t stream);  // variant 7: Q tile resident in TMEM (A operand of S = Q K^T)
+int launch_attn_fwd_db_dr(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                          cudaStream_t stream);  // variant 8: + pre-scaled Q (P = 2^S) and row sums by a ones-tile MMA
 int launch_attn_fwd_db_pf(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                           cudaStream_t stream);  // variant 6: early barrier probes + S prefetch
 int launch_attn_fwd_x3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
