@@ -318,13 +318,11 @@ def run_cuda(args):
                                                 're-read between its TMA reduce-adds (1.2x); K/V/Q/dO re-reads are served by L2',
                                 'flop_convention': 'algorithmic = 2 x forward (SURVEY 8(d)); the single-pass kernel executes 2.5 x forward '
                                                    '(5 GEMMs: S, dP, dV, dK, dQ), so its tensor pipe runs at 1.25 x the quoted rate',
-                                'limits_note': 'd=64 attention is bound by TMEM->register bandwidth (tcgen05.ld, 64 B/clk/SM): the backward moves '
-                                               '160 KB of fp32 accumulators per 128x128 tile = 2560 clk and measures 2703 clk (0.95 of that floor, '
-                                               'ncu sm__cycles_elapsed); the forward 1024 clk per pair of steps (equal to its SFU floor) and measures '
-                                               '1355 (0.76); under load the B200 sits at its 1000 W power cap (sm clock 1.6-1.65 GHz of 1.965), '
-                                               'see DESIGN.md 5',
-                                'tmem_ld_floor': {'bytes_per_clk_per_sm': 64, 'bwd_bytes_per_tile': 163840, 'bwd_clk_per_tile_floor': 2560,
-                                                  'bwd_clk_per_tile_measured_ncu': 2703, 'frac': 0.947},
+                                'limits_note': 'd=64 attention (ncu, profiles/ncu_attention_summary_latest.json): forward SFU pipe 76 % busy '
+                                               '(16384 exponentials per 128x128 tile = 1024 clk of 16-lane SFU), tensor pipe 38 %; backward tensor '
+                                               'pipe 48 %, shared-memory pipe 65-80 %; TMEM->register bandwidth is NOT the bound (tools/micro/'
+                                               'ldtm_bench.cu: 475-910 B/clk/SM vs 59 used); under load the B200 sits at its 1000 W power cap '
+                                               '(sm clock 1.6-1.65 GHz of 1.965), see DESIGN.md 5',
                                 'algorithmic_flops_per_launch': (2 * fl_f if dom != 'attn_fwd' else fl_f),
                                 'kernels': kern,
                                 'share_of_step': {k: 8 * v['ms'] / (sec / args.steps * 1e3) for k, v in kern.items()}}
