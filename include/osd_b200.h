@@ -72,7 +72,8 @@ OSD_API int osd_gemm(const void* A, int a_major, int64_t lda, const void* B, int
 
 /* qkv projection with the fused epilogue: bias + per-head RMSNorm(q), RMSNorm(k) + RoPE
  * (osu_dreamer/common/attn.py:75-81).  x [T,512], w [3072,512], out bf16 [T,3072];
- * rope table [L][2][32] fp32 (cos|sin) from osd_rope_table; raw_out (optional) receives the pre-norm
+ * rope = the table written by osd_rope_table (osd_rope_table_floats(L) floats: [L][2][32] cos|sin followed by a copy
+ * transposed per 32 positions, which the epilogue reads); raw_out (optional) receives the pre-norm
  * projections for the backward pass. */
 OSD_API int osd_qkv_proj(const void* x, const void* w, const float* bias, const float* qnorm_w, const float* knorm_w,
                  const float* rope, void* out, void* raw_out, int T, int L, int elem, void* stream);
@@ -81,6 +82,9 @@ OSD_API int osd_qkv_proj(const void* x, const void* w, const float* bias, const 
  * fp32 exactly as osu_dreamer/common/attn.py:16-21 does; inv_freq_host are the 32 fp32 values
  * 10000 ** (arange(0,64,2)/-64). */
 OSD_API int osd_rope_table(const float* inv_freq_host, int L, float* rope, void* stream);
+/* size in floats of the buffer osd_rope_table fills (L*64 + ceil(L/32)*2048): every `rope` argument of this library
+ * points at such a buffer */
+OSD_API size_t osd_rope_table_floats(int L);
 
 /* Bidirectional flash attention (head_dim 64, bf16): replaces F.scaled_dot_product_attention at
  * osu_dreamer/common/attn.py:82.  qkv bf16 [B*L, 3*H*64] token-major (q | k | v column blocks, head h at

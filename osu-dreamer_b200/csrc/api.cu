@@ -33,6 +33,8 @@ int osd_qkv_proj(const void* x, const void* w, const float* bias, const float* q
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 
+size_t osd_rope_table_floats(int L) { return rope_table_floats(L); }
+
 int osd_rope_table(const float* inv_freq_host, int L, float* rope, void* stream) {
   return launch_rope_table(inv_freq_host, L, rope, static_cast<cudaStream_t>(stream));
 }

@@ -30,22 +30,32 @@ struct InvFreq {
 };
 // rope[l][0][i] = cos(l*f_i), rope[l][1][i] = sin(l*f_i); the product l*f_i is rounded to fp32 first,
 // as torch.outer(arange(N).float(), inv_freq) does in osu_dreamer/common/attn.py:16-21.
-__global__ void rope_table_kernel(InvFreq f, int L, float* __restrict__ rope) {
+// A second copy follows at rope + L*64, transposed per block of 32 positions: ropeT[l/32][j][l%32][4] with j = 0..7 the
+// cos float4 groups and j = 8..15 the sin groups.  The qkv GEMM epilogue (one thread per token row, 32 consecutive
+// rows per warp) reads it with lane-consecutive 16-byte loads (4 wavefronts per request instead of 32).
+__global__ void rope_table_kernel(InvFreq f, int L, int Lp, float* __restrict__ rope) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= L * 32) return;
+  if (idx >= Lp * 32) return;
   const int l = idx >> 5, i = idx & 31;
   const float ang = __fmul_rn(static_cast<float>(l), f.v[i]);
   float s, c;
   sincosf(ang, &s, &c);
-  rope[(size_t)l * 64 + i] = c;
-  rope[(size_t)l * 64 + 32 + i] = s;
+  if (l < L) {
+    rope[(size_t)l * 64 + i] = c;
+    rope[(size_t)l * 64 + 32 + i] = s;
+  }
+  float* t = rope + (size_t)L * 64 + (size_t)(l >> 5) * 2048;
+  t[((i >> 2) * 32 + (l & 31)) * 4 + (i & 3)] = c;
+  t[((8 + (i >> 2)) * 32 + (l & 31)) * 4 + (i & 3)] = s;
 }
+size_t rope_table_floats(int L) { return (size_t)L * 64 + (size_t)ceil_div(L, 32) * 2048; }
 int launch_rope_table(const float* inv_freq_host, int L, float* rope, cudaStream_t stream) {
   OSD_CHECK(inv_freq_host && rope && L > 0, "rope_table: bad arguments");
   InvFreq f;
   for (int i = 0; i < 32; ++i) f.v[i] = inv_freq_host[i];
-  const int n = L * 32;
-  rope_table_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(f, L, rope);
+  const int Lp = ceil_div(L, 32) * 32;
+  const int n = Lp * 32;
+  rope_table_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(f, L, Lp, rope);
   OSD_LAUNCHED();
   return 0;
 }

@@ -275,11 +275,15 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_cons
             for (int j = 0; j < 64; ++j) ss = fmaf(x[j], x[j], ss);
             const float r = rsqrtf(ss * inv_d + eps);
             const float4* wn = reinterpret_cast<const float4*>(which == 0 ? p.qnorm_w : p.knorm_w);
-            const float4* cs = reinterpret_cast<const float4*>(p.rope + (size_t)pos * 64);
+            // rope values of this thread's token from the 32-row-transposed copy of the table
+            // ([pos / 32][j][pos % 32][4], behind the [L][64] rows): the warp's 32 rows are consecutive positions, so
+            // each 16-byte load is lane-consecutive (4 wavefronts per request; the row layout needed 32)
+            const float4* cs = reinterpret_cast<const float4*>(p.rope + (size_t)p.L * 64 + (size_t)(pos >> 5) * 2048) + (pos & 31);
+            constexpr int cstep = 32;
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 cc = __ldg(cs + j4);
-              const float4 sn = __ldg(cs + 8 + j4);
+              const float4 cc = __ldg(cs + j4 * cstep);
+              const float4 sn = __ldg(cs + (8 + j4) * cstep);
               const float4 wa = __ldg(wn + j4), wb = __ldg(wn + 8 + j4);
               const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
               const float sv[4] = {sn.x, sn.y, sn.z, sn.w};

@@ -4,6 +4,7 @@
 
 namespace osd {
 
+size_t rope_table_floats(int L);  // [L][64] + the 32-row-transposed copy
 int launch_rope_table(const float* inv_freq_host, int L, float* rope, cudaStream_t stream);
 int launch_cf_to_tm(const float* in, void* out, int out_bf16, int B, int C, int L, cudaStream_t stream);
 int launch_tm_to_cf(const void* in, int in_fp32, float* out, int B, int C, int L, cudaStream_t stream);

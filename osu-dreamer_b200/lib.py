@@ -83,10 +83,11 @@ def gemm(A, B, C, bias=None, a_major=MAJOR_K, b_major=MAJOR_K, epi=EPI_STORE, sp
 
 
 def rope_table(L: int, device) -> torch.Tensor:
-    """[L, 2, 32] fp32 cos|sin table; inv_freq formed exactly as osu_dreamer/common/attn.py:16-18."""
+    """fp32 cos|sin table [L, 2, 32] followed by its 32-row-transposed copy (flat, osd_rope_table_floats(L) floats);
+    inv_freq formed exactly as osu_dreamer/common/attn.py:16-18."""
     inv_freq = (10000 ** (torch.arange(0, 64, 2).float() / -64)).contiguous()
     arr = (c_float * 32)(*inv_freq.tolist())
-    out = torch.empty(L, 2, 32, dtype=torch.float32, device=device)
+    out = torch.empty(_sz('osd_rope_table_floats', L), dtype=torch.float32, device=device)
     _check(load().osd_rope_table(arr, c_int(L), ptr(out), stream()))
     return out
 
