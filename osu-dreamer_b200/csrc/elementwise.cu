@@ -310,23 +310,41 @@ template <typename TOut>
 __global__ void __launch_bounds__(256) prenorm_mod_dwconv_kernel(
     const float* __restrict__ x, const float* __restrict__ mod, const float* __restrict__ wconv /*[512][5]*/,
     const float* __restrict__ bconv, TOut* __restrict__ z, __nv_bfloat16* __restrict__ hmod_out, int L, int split) {
-  extern __shared__ float sh[];  // [DW_TOK + 4][512]
+  extern __shared__ __align__(128) float sh[];  // [DW_TOK + 4][512] + one mbarrier
   const int b = blockIdx.y;
   const int l0 = blockIdx.x * DW_TOK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* sc = mod + (size_t)b * 1536;
   const float* shf = sc + 512;
+  // the tile's rows (with 2 halo rows each side, clipped to the sample) are contiguous in x: ONE bulk copy brings the
+  // 72 KB in, so a block has all of its bytes in flight from its first instruction (three blocks per SM overlap each
+  // other's load / math / store phases); rows outside the sample are zero-filled
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sh + (DW_TOK + 4) * D);
+  const int lo = max(l0 - 2, 0), hi = min(l0 + DW_TOK + 2, L);  // valid rows [lo, hi)
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    const uint32_t bytes = (uint32_t)(hi - lo) * D * 4;
+    mbar_expect_tx(bar, bytes);
+    bulk_load_1d(sh + (lo - (l0 - 2)) * D, x + ((size_t)b * L + lo) * D, bytes, bar);
+  }
+  for (int rr = warp; rr < DW_TOK + 4; rr += 8) {
+    const int l = l0 + rr - 2;
+    if (l < 0 || l >= L) {
+      float* dst = sh + rr * D;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) *reinterpret_cast<float4*>(dst + v * 128 + lane * 4) = make_float4(0, 0, 0, 0);
+    }
+  }
+  __syncthreads();  // barrier initialised (and the zero rows written) before anyone waits / reads
+  mbar_wait(bar, 0);
   for (int rr = warp; rr < DW_TOK + 4; rr += 8) {
     const int l = l0 + rr - 2;
     float* dst = sh + rr * D;
-    if (l < 0 || l >= L) {
-#pragma unroll
-      for (int v = 0; v < 4; ++v) *reinterpret_cast<float4*>(dst + v * 128 + lane * 4) = make_float4(0, 0, 0, 0);
-      continue;
-    }
+    if (l < 0 || l >= L) continue;
     const size_t t = (size_t)b * L + l;
     float r[16];
-    load_row_f32(x + t * D, r, lane);
+    load_row_f32(dst, r, lane);
     const float inv = row_inv_rms(r);
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -376,7 +394,7 @@ __global__ void __launch_bounds__(256) prenorm_mod_dwconv_kernel(
 int launch_prenorm_mod_dwconv(const float* x, const float* mod, const float* wconv, const float* bconv, void* z,
                               int z_fp32, void* hmod_out, int B, int L, cudaStream_t stream, int split) {
   dim3 grid(ceil_div(L, DW_TOK), B);
-  const int smem = (DW_TOK + 4) * D * 4;
+  const int smem = (DW_TOK + 4) * D * 4 + 16;
   if (z_fp32) {
     auto k = prenorm_mod_dwconv_kernel<float>;
     OSD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -526,11 +526,15 @@ int launch_swiglu_norm_bwd(const void* vg, const void* dhn, const float* rinv, v
 // 3-step shuffles.  dq can be taken straight from the fp32 accumulator of the single-pass attention backward
 // (dq_acc, scaled by dq_scale) when its fallback flag is clear, which replaces that path's convert pass.
 static constexpr int QKB = 128;
+#ifndef OSD_QKB_BLOCKS
+#define OSD_QKB_BLOCKS 2
+#endif
+static constexpr int QKB_BLOCKS = OSD_QKB_BLOCKS;  // resident blocks per SM the register allocation targets (A/B: 3 spills 96 B)
 // gin aliases dqkv: every element is read (through gin) by the thread that later overwrites it and by no other
 // thread, so declaring the read side const/restrict is safe and lets the compiler hoist the loads of the next
 // rows above the stores of the current one.  (A bulk-copy staged variant of this kernel -- 3 x 48 KB stages, one block
 // of 8 warps per SM -- was slower, 0.745 vs 0.516 ms: at 142 registers / 8 warps the per-row math bound it.)
-__global__ void __launch_bounds__(256) qknorm_rope_bwd_kernel(__nv_bfloat16* __restrict__ dqkv,
+__global__ void __launch_bounds__(256, QKB_BLOCKS) qknorm_rope_bwd_kernel(__nv_bfloat16* __restrict__ dqkv,
                                                               const __nv_bfloat16* __restrict__ gin,
                                                               const __nv_bfloat16* __restrict__ raw,
                                                               const float* __restrict__ rope,
