@@ -156,6 +156,22 @@ OSD_API void osd_debug_attn_bwd_trace(unsigned long long* buf, int cta);
 /* same for the forward kernel variant 5 (2 x 1024 records) */
 OSD_API void osd_debug_attn_fwd_trace(unsigned long long* buf, int cta);
 
+/* ---- style model inference: the sampler that runs right before diffusion.sample in LDM.sample
+ * (osu_dreamer/models/inference/model.py:48; osu_dreamer/models/style/model.py:72-119, style_dim 32, h_dim 256, depth 8,
+ * expand 4, label_features 128 -- models/style/model.yml:68-75).  params = HOST array of OSD_STYLE_NUM_PARAMS device
+ * pointers (fp32) in the reference's state-dict order: cond_proj_w, cond_proj_b, null_labels, rff.W, rff.b,
+ * proj_in.{weight,bias}, proj_out.0.weight, proj_out.1.{weight,bias}, u_out.{weight,bias}, films.i.{weight,bias} (i < 8),
+ * blocks.i.0.{weight,bias}, blocks.i.3.{weight,bias} (i < 8).  scratch: osd_style_scratch_floats(B) floats. */
+#define OSD_STYLE_NUM_PARAMS 60
+OSD_API size_t osd_style_scratch_floats(int B);
+/* StyleModel.forward (model.py:81-99): st [B,32], labels [B,5] (values < 0 select the null embedding) -> u [B], v [B,32] */
+OSD_API int osd_style_forward(const float* const* params, const float* st, const float* labels, float* u, float* v,
+                              float* scratch, int B, void* stream);
+/* StyleModel.sample (model.py:101-119): s_inout [B,32] holds the initial noise on entry and the style codes on exit;
+ * the probe forward, eta and all num_steps updates stay on the device; eta_u0_out (nullable) receives {eta, u0}. */
+OSD_API int osd_style_sample(const float* const* params, const float* labels, float* s_inout, int num_steps,
+                             float* scratch, float* eta_u0_out, int B, void* stream);
+
 /* Gradient of DiffusionModel.forward (what autograd computes for the reference at train.py:84 + Lightning's
  * backward): given du [B] and dv [B,6,L], ACCUMULATES the parameter gradients into grads[164] (HOST array of
  * DEVICE fp32 pointers, parameter shapes).  `workspace` is the save=1 workspace the forward filled;

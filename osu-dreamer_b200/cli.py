@@ -36,6 +36,11 @@ def install() -> None:
     for name in ('osu_dreamer.models.inference.model', 'osu_dreamer.models.diffusion.train'):
         if name in sys.modules:
             sys.modules[name].DiffusionModel = denoiser.DiffusionModel
+    # the style sampler that LDM.sample runs right before diffusion.sample (models/inference/model.py:48): inference
+    # mirror only, so it is swapped into the inference module, not into the style trainer
+    from . import style
+    inf = importlib.import_module('osu_dreamer.models.inference.model')
+    inf.StyleModel = style.StyleModel
 
 
 def build_trainer(cfg: dict) -> DiffusionTrainer:

@@ -35,6 +35,16 @@ int osd_qkv_proj(const void* x, const void* w, const float* bias, const float* q
 
 size_t osd_rope_table_floats(int L) { return rope_table_floats(L); }
 
+size_t osd_style_scratch_floats(int B) { return style_scratch_floats(B); }
+int osd_style_forward(const float* const* params, const float* st, const float* labels, float* u, float* v, float* scratch,
+                      int B, void* stream) {
+  return launch_style_forward(params, st, labels, u, v, scratch, B, static_cast<cudaStream_t>(stream));
+}
+int osd_style_sample(const float* const* params, const float* labels, float* s_inout, int num_steps, float* scratch,
+                     float* eta_u0_out, int B, void* stream) {
+  return launch_style_sample(params, labels, s_inout, num_steps, scratch, eta_u0_out, B, static_cast<cudaStream_t>(stream));
+}
+
 int osd_rope_table(const float* inv_freq_host, int L, float* rope, void* stream) {
   return launch_rope_table(inv_freq_host, L, rope, static_cast<cudaStream_t>(stream));
 }

@@ -4,6 +4,12 @@
 
 namespace osd {
 
+// style model inference (style.cu); params = 60 device pointers in the reference's state-dict order
+size_t style_scratch_floats(int B);
+int launch_style_forward(const float* const* params, const float* st, const float* labels, float* u, float* v, float* scratch,
+                         int B, cudaStream_t s);
+int launch_style_sample(const float* const* params, const float* labels, float* s_io, int num_steps, float* scratch,
+                        float* eta_u0_out, int B, cudaStream_t s);
 size_t rope_table_floats(int L);  // [L][64] + the 32-row-transposed copy
 int launch_rope_table(const float* inv_freq_host, int L, float* rope, cudaStream_t stream);
 int launch_cf_to_tm(const float* in, void* out, int out_bf16, int B, int C, int L, cudaStream_t stream);

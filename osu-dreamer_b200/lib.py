@@ -251,3 +251,35 @@ def loss_fwd_bwd(xt, x1, u, v, c0, osl_w, del_w):
     _check(load().osd_loss_fwd_bwd(ptr(xt), ptr(x1), ptr(u), ptr(v), c_float(c0), c_float(osl_w), c_float(del_w),
                                    c_int(B), c_int(L), ptr(out4), ptr(du), ptr(dv), ptr(scratch), stream()))
     return out4, du, dv
+
+
+# ------------------------------------------------------------------ style model inference (csrc/style.cu)
+STYLE_NUM_PARAMS = 60
+
+
+def style_param_array(tensors):
+    """HOST array of device pointers, reference state-dict order (parameters and the two Fourier-feature buffers)."""
+    if len(tensors) != STYLE_NUM_PARAMS:
+        raise OsdError(f'style model: expected {STYLE_NUM_PARAMS} tensors, got {len(tensors)}')
+    for t in tensors:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()) or t.data_ptr() % 16:
+            raise OsdError('style model tensors must be contiguous, 16-byte aligned fp32 CUDA tensors (no CPU path)')
+    return (c_void_p * STYLE_NUM_PARAMS)(*[t.data_ptr() for t in tensors])
+
+
+def style_forward(parr, st, labels):
+    B = st.shape[0]
+    u = torch.empty(B, dtype=torch.float32, device=st.device)
+    v = torch.empty(B, st.shape[1], dtype=torch.float32, device=st.device)
+    scratch = torch.empty(_sz('osd_style_scratch_floats', B), dtype=torch.float32, device=st.device)
+    _check(load().osd_style_forward(parr, ptr(st), ptr(labels), ptr(u), ptr(v), ptr(scratch), c_int(B), stream()))
+    return u, v
+
+
+def style_sample(parr, labels, s, num_steps):
+    """in place on s [B, 32]; returns the {eta, u0} pair (device tensor)."""
+    B = s.shape[0]
+    scratch = torch.empty(_sz('osd_style_scratch_floats', B), dtype=torch.float32, device=s.device)
+    eta_u0 = torch.empty(2, dtype=torch.float32, device=s.device)
+    _check(load().osd_style_sample(parr, ptr(labels), ptr(s), c_int(num_steps), ptr(scratch), ptr(eta_u0), c_int(B), stream()))
+    return eta_u0

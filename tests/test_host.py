@@ -240,3 +240,24 @@ def test_prefetcher_order_errors_and_pinned_batches(tmp_path):
     with pytest.raises(RuntimeError, match='loader failed'):
         next(p)
     p.close()
+
+
+def test_style_mirror_state_dict_contract_and_no_cpu_path(golden_dir):
+    """the inference mirror of StyleModel carries the reference's parameter / buffer names, shapes and order
+    (tests/golden/nb_spec.json, written from the reference module) and refuses to run without CUDA or under autograd"""
+    import json
+    from osu_dreamer_b200 import lib
+    from osu_dreamer_b200.style import StyleModel, StyleModelArgs
+    spec = json.load(open(os.path.join(golden_dir, 'nb_spec.json')))['style']
+    m = StyleModel(32, StyleModelArgs(label_features=128, h_dim=256, depth=8, expand=4))
+    sd = m.state_dict()
+    assert [(k, list(v.shape)) for k, v in sd.items()] == [(k, list(s)) for k, s in spec] and len(sd) == lib.STYLE_NUM_PARAMS
+    assert abs(m.c0 - 64 * (1 - torch.tensor(2.3263478740408408).sigmoid().item()) ** 2) < 1e-12 and m.u_scale == 8.0
+    assert float(m.u_out.bias) == pytest.approx(-0.4328) and float(m.proj_out[1].weight.abs().max()) == 0.0
+    with pytest.raises(lib.OsdError):
+        StyleModel(16, StyleModelArgs(128, 256, 8, 4))
+    if not torch.cuda.is_available():
+        with torch.no_grad(), pytest.raises(lib.OsdError, match='no CPU path'):
+            m(torch.randn(2, 32), torch.rand(2, 5))
+    with pytest.raises(lib.OsdError, match='inference-only'):
+        m(torch.randn(2, 32), torch.rand(2, 5))
