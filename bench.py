@@ -136,7 +136,7 @@ def run_reference(args):
     threads = min(os.cpu_count() or 1, 32)
     Ls, Bs = 512, 2
     sec = cpu_train_step_seconds(Ls, Bs, max(1, min(args.steps, 5)), max(0, min(args.warmup, 1)), threads)
-    # samples/s measured at L=2048; the same arithmetic at L=8192 costs F(8192)/F(2048) more per sample
+    # samples/s measured at L=512; the same arithmetic at L=8192 costs F(8192)/F(512) more per sample
     v_sample = Bs / sec
     scale = f_fwd(Ls) / f_fwd(SEQ)
     value = v_sample * scale

@@ -39,8 +39,13 @@ def install() -> None:
     # the style sampler that LDM.sample runs right before diffusion.sample (models/inference/model.py:48): inference
     # mirror only, so it is swapped into the inference module, not into the style trainer
     from . import style
-    inf = importlib.import_module('osu_dreamer.models.inference.model')
-    inf.StyleModel = style.StyleModel
+    try:
+        inf = importlib.import_module('osu_dreamer.models.inference.model')
+    except ImportError:  # a training-only environment without the inference module's dependencies
+        inf = None
+    if inf is not None:
+        inf.StyleModel = style.StyleModel
+        inf.DiffusionModel = denoiser.DiffusionModel
 
 
 def build_trainer(cfg: dict) -> DiffusionTrainer:

@@ -140,7 +140,7 @@ def param_array(tensors):
     return (c_void_p * NUM_PARAMS)(*[t.data_ptr() for t in tensors])
 
 
-def attn_fwd(qkv, B, L, H=16, want_lse=True, bound_log2=None, variant=0):
+def attn_fwd(qkv, B, L, H=16, want_lse=True, bound_log2=None, variant=7):
     T = B * L
     y = torch.empty(T, H * 64, dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device) if want_lse else None
