@@ -156,6 +156,33 @@ OSD_API void osd_debug_attn_bwd_trace(unsigned long long* buf, int cta);
 /* same for the forward kernel variant 5 (2 x 1024 records) */
 OSD_API void osd_debug_attn_fwd_trace(unsigned long long* buf, int cta);
 
+/* ---- latent model, inference half: LatentModel.audio_encoder before and LatentModel.decode after diffusion.sample in
+ * LDM.sample (osu_dreamer/models/inference/model.py:47,51; models/latent/model.py:53,103-133, unet.py, spec_features.py;
+ * h_dim 128, expand 4 -> hidden 341, radius 2, stride 3 -- models/latent/model.yml:88-101).  fp32, channels-first
+ * [B, C, L] like the reference; x and y are distinct caller-owned device buffers. */
+/* one residual SwiGLU block of `layer` (unet.py:50-54): y = x + RMSNorm_g2(SwiGLU(RMSNorm_g1(x)(1+scale)+shift))(1+gate).
+ * w8 = HOST array of 8 device pointers {norms.j.gamma, blocks.j.0.proj_vg.0.weight [128,1,5], .bias, proj_vg.1.weight
+ * [682,128,1], .bias, proj_o.weight [128,341,1], .bias, blocks.j.1.gamma}; film = films.j(cond) [B,384] (scale | shift |
+ * gate) or NULL for the unconditional layers. */
+OSD_API int osd_lat_block(const float* x, float* y, const float* const* w8, const float* film, int B, int L, void* stream);
+/* rms_norm over dim 1 (common/rms_norm.py:7-16) with optional gamma [C] and optional SiLU (act = 1); N = product of the
+ * trailing dims */
+OSD_API int osd_lat_rmsnorm(const float* x, const float* gamma, float* y, int B, int C, long long N, int act, void* stream);
+/* pointwise Conv1d / Linear: y[b,o,n] = act(bias[o] + sum_i W[o,i] x[b,i,n]); act 0 none, 1 SiLU, 2 sigmoid on channels
+ * < act_channels (LatentModel.decode's hit signals, model.py:127-130) */
+OSD_API int osd_lat_conv1x1(const float* x, const float* W, const float* bias, float* y, int B, int Cin, int Cout, long long N,
+                            int act, int act_channels, void* stream);
+/* SpecFeatures' strided Conv2d (spec_features.py:20,23): kernel (kh,3), stride (sh,1), padding (1,1) */
+OSD_API int osd_lat_conv2d(const float* x, const float* W, const float* bias, float* y, int B, int Cin, int Cout, int Ain, int L,
+                           int kh, int sh, void* stream);
+/* UNetEncoder down (unet.py:60-64): depthwise Conv1d k=3 pad 1 + AvgPool1d(3) -> [B,C,L/3];
+ * UNetDecoder up (unet.py:81-85): nearest Upsample x3 + depthwise Conv1d k=3 pad 1 -> [B,C,3l] */
+OSD_API int osd_lat_down3(const float* x, const float* w, const float* bias, float* y, int B, int C, int L, void* stream);
+OSD_API int osd_lat_up3(const float* x, const float* w, const float* bias, float* y, int B, int C, int l, void* stream);
+/* mixer (unet.py:126): y = x + p * g; p has batch p_batch (1 = the broadcast audio skips of predict, or B) */
+OSD_API int osd_lat_mix(const float* x, const float* p, const float* g, float* y, int B, long long per_sample, int p_batch,
+                        void* stream);
+
 /* ---- style model inference: the sampler that runs right before diffusion.sample in LDM.sample
  * (osu_dreamer/models/inference/model.py:48; osu_dreamer/models/style/model.py:72-119, style_dim 32, h_dim 256, depth 8,
  * expand 4, label_features 128 -- models/style/model.yml:68-75).  params = HOST array of OSD_STYLE_NUM_PARAMS device

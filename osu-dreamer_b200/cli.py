@@ -36,15 +36,16 @@ def install() -> None:
     for name in ('osu_dreamer.models.inference.model', 'osu_dreamer.models.diffusion.train'):
         if name in sys.modules:
             sys.modules[name].DiffusionModel = denoiser.DiffusionModel
-    # the style sampler that LDM.sample runs right before diffusion.sample (models/inference/model.py:48): inference
-    # mirror only, so it is swapped into the inference module, not into the style trainer
-    from . import style
+    # the other three calls of LDM.sample (models/inference/model.py:47-51: latent.audio_encoder, style.sample,
+    # latent.decode) have inference-only mirrors: they are swapped into the inference module, not into the trainers
+    from . import latent, style
     try:
         inf = importlib.import_module('osu_dreamer.models.inference.model')
     except ImportError:  # a training-only environment without the inference module's dependencies
         inf = None
     if inf is not None:
         inf.StyleModel = style.StyleModel
+        inf.LatentModel = latent.LatentModel  # inference half: audio_encoder / decode around diffusion.sample
         inf.DiffusionModel = denoiser.DiffusionModel
 
 

@@ -35,6 +35,30 @@ int osd_qkv_proj(const void* x, const void* w, const float* bias, const float* q
 
 size_t osd_rope_table_floats(int L) { return rope_table_floats(L); }
 
+int osd_lat_block(const float* x, float* y, const float* const* w8, const float* film, int B, int L, void* stream) {
+  return launch_lat_block(x, y, w8, film, B, L, static_cast<cudaStream_t>(stream));
+}
+int osd_lat_rmsnorm(const float* x, const float* gamma, float* y, int B, int C, long long N, int act, void* stream) {
+  return launch_lat_rmsnorm(x, gamma, y, B, C, N, act, static_cast<cudaStream_t>(stream));
+}
+int osd_lat_conv1x1(const float* x, const float* W, const float* bias, float* y, int B, int Cin, int Cout, long long N, int act,
+                    int act_channels, void* stream) {
+  return launch_lat_conv1x1(x, W, bias, y, B, Cin, Cout, N, act, act_channels, static_cast<cudaStream_t>(stream));
+}
+int osd_lat_conv2d(const float* x, const float* W, const float* bias, float* y, int B, int Cin, int Cout, int Ain, int L, int kh,
+                   int sh, void* stream) {
+  return launch_lat_conv2d(x, W, bias, y, B, Cin, Cout, Ain, L, kh, sh, static_cast<cudaStream_t>(stream));
+}
+int osd_lat_down3(const float* x, const float* w, const float* bias, float* y, int B, int C, int L, void* stream) {
+  return launch_lat_down3(x, w, bias, y, B, C, L, static_cast<cudaStream_t>(stream));
+}
+int osd_lat_up3(const float* x, const float* w, const float* bias, float* y, int B, int C, int l, void* stream) {
+  return launch_lat_up3(x, w, bias, y, B, C, l, static_cast<cudaStream_t>(stream));
+}
+int osd_lat_mix(const float* x, const float* p, const float* g, float* y, int B, long long per_sample, int p_batch, void* stream) {
+  return launch_lat_mix(x, p, g, y, B, per_sample, p_batch, static_cast<cudaStream_t>(stream));
+}
+
 size_t osd_style_scratch_floats(int B) { return style_scratch_floats(B); }
 int osd_style_forward(const float* const* params, const float* st, const float* labels, float* u, float* v, float* scratch,
                       int B, void* stream) {

@@ -4,6 +4,17 @@
 
 namespace osd {
 
+// latent model, inference half (latent.cu): fp32 channels-first building blocks
+int launch_lat_block(const float* x, float* y, const float* const* w8, const float* film, int B, int L, cudaStream_t s);
+int launch_lat_rmsnorm(const float* x, const float* gamma, float* y, int B, int C, long long N, int act, cudaStream_t s);
+int launch_lat_conv1x1(const float* x, const float* W, const float* bias, float* y, int B, int Cin, int Cout, long long N,
+                       int act, int act_channels, cudaStream_t s);
+int launch_lat_conv2d(const float* x, const float* W, const float* bias, float* y, int B, int Cin, int Cout, int Ain, int L,
+                      int kh, int sh, cudaStream_t s);
+int launch_lat_down3(const float* x, const float* w, const float* bias, float* y, int B, int C, int L, cudaStream_t s);
+int launch_lat_up3(const float* x, const float* w, const float* bias, float* y, int B, int C, int l, cudaStream_t s);
+int launch_lat_mix(const float* x, const float* p, const float* g, float* y, int B, long long per_sample, int p_batch,
+                   cudaStream_t s);
 // style model inference (style.cu); params = 60 device pointers in the reference's state-dict order
 size_t style_scratch_floats(int B);
 int launch_style_forward(const float* const* params, const float* st, const float* labels, float* u, float* v, float* scratch,

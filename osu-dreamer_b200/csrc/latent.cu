@@ -1,0 +1,348 @@
+// Latent model, inference half (reference: osu_dreamer/models/latent/{model,unet,spec_features}.py): the
+// `audio_encoder` that runs before `diffusion.sample` and the `decode` that runs after it inside LDM.sample
+// (models/inference/model.py:47,51).  Width 128, fp32, channels-first [B, C, L] like the reference; ~0.7 TFLOP per song
+// against 179 TFLOP per sampled latent, so these kernels are written for exact fp32 parity first (CUDA cores, fp32
+// accumulation in the reference's order of operations up to summation order), not for the tensor pipe.
+//   lat_block      one residual SwiGLU block of `layer` (unet.py:50-54): RMSNorm*gamma -> FiLM -> depthwise conv k=5 ->
+//                  1x1 128->682 -> v*silu(g) -> RMSNorm(341) -> 1x1 341->128 -> RMSNorm*gamma -> *(1+gate) -> +x, fused per
+//                  32-token tile in shared memory
+//   lat_rmsnorm    RMSNorm over the channel dim with gamma (+ SiLU): out_norm, the stem norms, the mixer norm
+//   lat_conv1x1    pointwise conv / linear with optional activation (mixers, proj_emb, proj_out, stem, FiLM, heads)
+//   lat_conv2d     the two strided stem convolutions of SpecFeatures (kernel (kh,3), stride (sh,1), padding (1,1))
+//   lat_down3 / lat_up3   depthwise conv k=3 + AvgPool(3) / nearest upsample x3 + depthwise conv k=3
+//   lat_mix        x + p * g (mixer, unet.py:126)
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace osd {
+
+static constexpr int LC = 128, LH = 341, LTL = 32, LHALO = 2, LTT = LTL + 2 * LHALO;
+static constexpr float L_EPS = 1e-6f;
+
+struct LatBlockW {
+  const float *g1, *dw_w, *dw_b, *w1, *b1, *w2, *b2, *g2;
+};
+
+// dynamic smem layout (floats): xs [128][36] | hs [128][36] | zs [128][32] | vg [682][32] | part [8][36] | inv [36]
+static constexpr int LB_XS = 0, LB_HS = LB_XS + LC * LTT, LB_ZS = LB_HS + LC * LTT, LB_VG = LB_ZS + LC * LTL,
+                     LB_PART = LB_VG + 2 * LH * LTL, LB_INV = LB_PART + 8 * LTT, LB_FLOATS = LB_INV + LTT;
+
+// per-token sum over a set of rows held by the warps -> inv[tt] = rsqrt(sum / n + eps); all 256 threads call it
+__device__ __forceinline__ void lat_finish_stat(float* part, float* inv, float mine0, float mine1, float n) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  part[warp * LTT + lane] = mine0;
+  if (lane < LTT - 32) part[warp * LTT + 32 + lane] = mine1;
+  __syncthreads();
+  if (threadIdx.x < LTT) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w * LTT + threadIdx.x];
+    inv[threadIdx.x] = rsqrtf(t / n + L_EPS);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1) lat_block_kernel(const float* __restrict__ x, float* __restrict__ y, LatBlockW w,
+                                                           const float* __restrict__ film /*[B][384] or null*/, int L) {
+  extern __shared__ __align__(16) float sm[];
+  float *xs = sm + LB_XS, *hs = sm + LB_HS, *zs = sm + LB_ZS, *vg = sm + LB_VG, *part = sm + LB_PART, *inv = sm + LB_INV;
+  const int b = blockIdx.y, t0 = blockIdx.x * LTL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xb = x + (size_t)b * LC * L;
+  // P0: x tile with halo (zeros outside the sequence)
+  for (int c = warp; c < LC; c += 8)
+    for (int tt = lane; tt < LTT; tt += 32) {
+      const int t = t0 - LHALO + tt;
+      xs[c * LTT + tt] = (t >= 0 && t < L) ? xb[(size_t)c * L + t] : 0.f;
+    }
+  __syncthreads();
+  // P1: rms over the 128 channels per token
+  {
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = warp; c < LC; c += 8) {
+      const float a = xs[c * LTT + lane];
+      s0 = fmaf(a, a, s0);
+      if (lane < LTT - 32) {
+        const float a1 = xs[c * LTT + 32 + lane];
+        s1 = fmaf(a1, a1, s1);
+      }
+    }
+    lat_finish_stat(part, inv, s0, s1, (float)LC);
+  }
+  // P2: h = norm(x) * gamma * (1 + scale) + shift, zero outside the sequence (the conv's zero padding)
+  for (int c = warp; c < LC; c += 8) {
+    const float g = w.g1[c];
+    const float sc = film ? film[(size_t)b * 3 * LC + c] : 0.f, sh = film ? film[(size_t)b * 3 * LC + LC + c] : 0.f;
+    for (int tt = lane; tt < LTT; tt += 32) {
+      const int t = t0 - LHALO + tt;
+      hs[c * LTT + tt] = (t >= 0 && t < L) ? (xs[c * LTT + tt] * inv[tt] * g) * (1.f + sc) + sh : 0.f;
+    }
+  }
+  __syncthreads();
+  // P3: depthwise conv k=5, pad 2
+  for (int c = warp; c < LC; c += 8) {
+    float a = w.dw_b[c];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) a = fmaf(w.dw_w[c * 5 + k], hs[c * LTT + lane + k], a);
+    zs[c * LTL + lane] = a;
+  }
+  __syncthreads();
+  // P4: vg[n][t] = b1[n] + sum_c W1[n][c] z[c][t]   (682 rows, two per warp and pass; lane = token)
+  for (int n = 2 * warp; n < 2 * LH; n += 16) {
+    const float4* r0 = reinterpret_cast<const float4*>(w.w1 + (size_t)n * LC);
+    const float4* r1 = reinterpret_cast<const float4*>(w.w1 + (size_t)(n + 1) * LC);
+    float a0 = w.b1[n], a1 = w.b1[n + 1];
+#pragma unroll 8
+    for (int c4 = 0; c4 < LC / 4; ++c4) {
+      const float4 p = __ldg(r0 + c4), q = __ldg(r1 + c4);
+      const float z0 = zs[(4 * c4) * LTL + lane], z1 = zs[(4 * c4 + 1) * LTL + lane], z2 = zs[(4 * c4 + 2) * LTL + lane],
+                  z3 = zs[(4 * c4 + 3) * LTL + lane];
+      a0 = fmaf(p.x, z0, a0), a0 = fmaf(p.y, z1, a0), a0 = fmaf(p.z, z2, a0), a0 = fmaf(p.w, z3, a0);
+      a1 = fmaf(q.x, z0, a1), a1 = fmaf(q.y, z1, a1), a1 = fmaf(q.z, z2, a1), a1 = fmaf(q.w, z3, a1);
+    }
+    vg[n * LTL + lane] = a0;
+    vg[(n + 1) * LTL + lane] = a1;
+  }
+  __syncthreads();
+  // P5: h = v * silu(g) in place over the v rows; rms over the 341 hidden channels
+  {
+    float s0 = 0.f;
+    for (int j = warp; j < LH; j += 8) {
+      const float v = vg[j * LTL + lane], g = vg[(LH + j) * LTL + lane];
+      const float h = v * (g / (1.0f + expf(-g)));
+      vg[j * LTL + lane] = h;
+      s0 = fmaf(h, h, s0);
+    }
+    lat_finish_stat(part, inv, s0, 0.f, (float)LH);
+  }
+  // P6: o[c][t] = b2[c] + sum_j W2[c][j] hn[j][t]  -> zs (rows of W2 are 341 floats: scalar broadcast loads)
+  {
+    const float iv = inv[lane];
+    for (int c = 2 * warp; c < LC; c += 16) {
+      const float* r0 = w.w2 + (size_t)c * LH;
+      const float* r1 = r0 + LH;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < LH; ++j) {
+        const float h = vg[j * LTL + lane];
+        a0 = fmaf(__ldg(r0 + j), h, a0);
+        a1 = fmaf(__ldg(r1 + j), h, a1);
+      }
+      zs[c * LTL + lane] = fmaf(a0, iv, w.b2[c]);       // W2 (hn) = (W2 h) * inv: the norm is a per-token scalar
+      zs[(c + 1) * LTL + lane] = fmaf(a1, iv, w.b2[c + 1]);
+    }
+  }
+  __syncthreads();
+  // P7: rms over channels of o, gain gamma, (1 + gate), residual
+  {
+    float s0 = 0.f;
+    for (int c = warp; c < LC; c += 8) {
+      const float a = zs[c * LTL + lane];
+      s0 = fmaf(a, a, s0);
+    }
+    lat_finish_stat(part, inv, s0, 0.f, (float)LC);
+  }
+  const int t = t0 + lane;
+  if (t < L) {
+    float* yb = y + (size_t)b * LC * L;
+    const float iv = inv[lane];
+    for (int c = warp; c < LC; c += 8) {
+      const float gt = film ? film[(size_t)b * 3 * LC + 2 * LC + c] : 0.f;
+      yb[(size_t)c * L + t] = xs[c * LTT + LHALO + lane] + (zs[c * LTL + lane] * iv * w.g2[c]) * (1.f + gt);
+    }
+  }
+}
+
+int launch_lat_block(const float* x, float* y, const float* const* w8, const float* film, int B, int L, cudaStream_t s) {
+  OSD_CHECK(x && y && w8 && x != y && B > 0 && L > 0, "lat_block: bad arguments (x and y must be distinct buffers)");
+  LatBlockW w{w8[0], w8[1], w8[2], w8[3], w8[4], w8[5], w8[6], w8[7]};
+  const int smem = LB_FLOATS * 4;
+  static bool set = false;
+  if (!set) {
+    OSD_CUDA(cudaFuncSetAttribute(lat_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    set = true;
+  }
+  dim3 grid(ceil_div(L, LTL), B);
+  lat_block_kernel<<<grid, 256, smem, s>>>(x, y, w, film, L);
+  OSD_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// y[b][c][n] = act(x[b][c][n] * rsqrt(mean_c x^2 + eps) * gamma[c]); N = product of the trailing dims; act 0 none, 1 SiLU
+__global__ void lat_rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float* __restrict__ y, int C,
+                                   long long N, long long total, int act) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long b = i / N, n = i % N;
+  const float* p = x + b * C * N + n;
+  float ss = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = p[(long long)c * N];
+    ss = fmaf(v, v, ss);
+  }
+  const float inv = rsqrtf(ss / (float)C + L_EPS);
+  float* q = y + b * C * N + n;
+  for (int c = 0; c < C; ++c) {
+    float v = p[(long long)c * N] * inv;
+    if (gamma != nullptr) v *= gamma[c];
+    if (act == 1) v = v / (1.0f + expf(-v));
+    q[(long long)c * N] = v;
+  }
+}
+int launch_lat_rmsnorm(const float* x, const float* gamma, float* y, int B, int C, long long N, int act, cudaStream_t s) {
+  OSD_CHECK(x && y && B > 0 && C > 0 && N > 0, "lat_rmsnorm: bad arguments");
+  const long long total = (long long)B * N;
+  lat_rmsnorm_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, gamma, y, C, N, total, act);
+  OSD_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// y[b][o][n] = act(bias[o] + sum_i W[o][i] x[b][i][n]); act 0 none, 1 SiLU, 2 sigmoid on channels < act_channels
+__global__ void __launch_bounds__(128) lat_conv1x1_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, float* __restrict__ y, int Cin,
+                                                          int Cout, long long N, int act, int act_channels) {
+  extern __shared__ float xs[];  // [Cin][128]
+  const int b = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * 128, n = n0 + threadIdx.x;
+  const float* xb = x + (long long)b * Cin * N;
+  for (int i = 0; i < Cin; ++i) xs[i * 128 + threadIdx.x] = (n < N) ? xb[(long long)i * N + n] : 0.f;
+  __syncthreads();
+  if (n >= N) return;
+  float* yb = y + (long long)b * Cout * N + n;
+  for (int o = 0; o < Cout; ++o) {
+    const float* wr = W + (long long)o * Cin;
+    float a = bias ? bias[o] : 0.f;
+    for (int i = 0; i < Cin; ++i) a = fmaf(__ldg(wr + i), xs[i * 128 + threadIdx.x], a);
+    if (act == 1) a = a / (1.0f + expf(-a));
+    else if (act == 2 && o < act_channels) a = 1.0f / (1.0f + expf(-a));
+    yb[(long long)o * N] = a;
+  }
+}
+int launch_lat_conv1x1(const float* x, const float* W, const float* bias, float* y, int B, int Cin, int Cout, long long N,
+                       int act, int act_channels, cudaStream_t s) {
+  OSD_CHECK(x && W && y && B > 0 && Cin > 0 && Cin <= 256 && Cout > 0 && N > 0, "lat_conv1x1: bad arguments");
+  const int smem = Cin * 128 * 4;
+  static int max_set = 0;
+  if (smem > max_set) {
+    OSD_CUDA(cudaFuncSetAttribute(lat_conv1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    max_set = smem;
+  }
+  dim3 grid((unsigned)((N + 127) / 128), B);
+  lat_conv1x1_kernel<<<grid, 128, smem, s>>>(x, W, bias, y, Cin, Cout, N, act, act_channels);
+  OSD_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem convolution: y[b][o][a][l] = bias[o] + sum_{i,p,q} W[o][i][p][q] x[b][i][a*sh + p - 1][l + q - 1], kernel (kh, 3),
+// stride (sh, 1), padding (1, 1), zero padded; A_out = (A_in + 2 - kh) / sh + 1
+__global__ void lat_conv2d_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                                  float* __restrict__ y, int Cin, int Cout, int Ain, int Aout, int L, int kh, int sh,
+                                  long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int l = (int)(idx % L);
+  long long r = idx / L;
+  const int a = (int)(r % Aout);
+  r /= Aout;
+  const int o = (int)(r % Cout);
+  const int b = (int)(r / Cout);
+  float acc = bias[o];
+  for (int i = 0; i < Cin; ++i)
+    for (int p = 0; p < kh; ++p) {
+      const int ai = a * sh + p - 1;
+      if (ai < 0 || ai >= Ain) continue;
+      const float* xr = x + (((long long)b * Cin + i) * Ain + ai) * L;
+      const float* wr = W + (((long long)o * Cin + i) * kh + p) * 3;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int li = l + q - 1;
+        if (li >= 0 && li < L) acc = fmaf(wr[q], xr[li], acc);
+      }
+    }
+  y[idx] = acc;
+}
+int launch_lat_conv2d(const float* x, const float* W, const float* bias, float* y, int B, int Cin, int Cout, int Ain, int L,
+                      int kh, int sh, cudaStream_t s) {
+  OSD_CHECK(x && W && bias && y && B > 0 && Ain + 2 >= kh && sh > 0 && L > 0, "lat_conv2d: bad arguments");
+  const int Aout = (Ain + 2 - kh) / sh + 1;
+  const long long total = (long long)B * Cout * Aout * L;
+  lat_conv2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, W, bias, y, Cin, Cout, Ain, Aout, L, kh, sh, total);
+  OSD_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// down: depthwise conv k=3 pad 1, then AvgPool1d(3) (unet.py:60-64): y [B][C][L/3]
+__global__ void lat_down3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                 float* __restrict__ y, int C, int L, int Lo, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % Lo);
+  const long long bc = idx / Lo;
+  const int c = (int)(bc % C);
+  const float* xr = x + bc * L;
+  const float w0 = w[c * 3], w1 = w[c * 3 + 1], w2 = w[c * 3 + 2], bb = bias[c];
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int t = 3 * j + i;
+    float v = bb;
+    if (t - 1 >= 0) v = fmaf(w0, xr[t - 1], v);
+    v = fmaf(w1, xr[t], v);
+    if (t + 1 < L) v = fmaf(w2, xr[t + 1], v);
+    acc += v;
+  }
+  y[idx] = acc / 3.0f;
+}
+// up: nearest upsample x3, then depthwise conv k=3 pad 1 (unet.py:81-85): y [B][C][3 l]
+__global__ void lat_up3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                               float* __restrict__ y, int C, int l, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Lo = 3 * l;
+  const int t = (int)(idx % Lo);
+  const long long bc = idx / Lo;
+  const int c = (int)(bc % C);
+  const float* xr = x + bc * l;
+  float v = bias[c];
+  if (t - 1 >= 0) v = fmaf(w[c * 3], xr[(t - 1) / 3], v);
+  v = fmaf(w[c * 3 + 1], xr[t / 3], v);
+  if (t + 1 < Lo) v = fmaf(w[c * 3 + 2], xr[(t + 1) / 3], v);
+  y[idx] = v;
+}
+int launch_lat_down3(const float* x, const float* w, const float* bias, float* y, int B, int C, int L, cudaStream_t s) {
+  OSD_CHECK(x && w && bias && y && B > 0 && C > 0 && L >= 3, "lat_down3: bad arguments");
+  const int Lo = L / 3;
+  const long long total = (long long)B * C * Lo;
+  lat_down3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, w, bias, y, C, L, Lo, total);
+  OSD_LAUNCHED();
+  return 0;
+}
+int launch_lat_up3(const float* x, const float* w, const float* bias, float* y, int B, int C, int l, cudaStream_t s) {
+  OSD_CHECK(x && w && bias && y && B > 0 && C > 0 && l > 0, "lat_up3: bad arguments");
+  const long long total = (long long)B * C * 3 * l;
+  lat_up3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, w, bias, y, C, l, total);
+  OSD_LAUNCHED();
+  return 0;
+}
+
+// y = x + p * g ; p may be broadcast over the batch (p_batch == 1: the audio skips of `predict`)
+__global__ void lat_mix_kernel(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ g,
+                               float* __restrict__ y, long long per_sample, int p_bcast, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  y[i] = fmaf(p[p_bcast ? i % per_sample : i], g[i], x[i]);
+}
+int launch_lat_mix(const float* x, const float* p, const float* g, float* y, int B, long long per_sample, int p_batch,
+                   cudaStream_t s) {
+  OSD_CHECK(x && p && g && y && B > 0 && per_sample > 0 && (p_batch == 1 || p_batch == B), "lat_mix: bad arguments");
+  const long long total = (long long)B * per_sample;
+  lat_mix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, p, g, y, per_sample, p_batch == 1 && B > 1, total);
+  OSD_LAUNCHED();
+  return 0;
+}
+
+}  // namespace osd

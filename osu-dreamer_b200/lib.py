@@ -283,3 +283,75 @@ def style_sample(parr, labels, s, num_steps):
     eta_u0 = torch.empty(2, dtype=torch.float32, device=s.device)
     _check(load().osd_style_sample(parr, ptr(labels), ptr(s), c_int(num_steps), ptr(scratch), ptr(eta_u0), c_int(B), stream()))
     return eta_u0
+
+
+# ------------------------------------------------------------------ latent model, inference half (csrc/latent.cu)
+def _f32(t):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise OsdError('latent ops take contiguous fp32 CUDA tensors (no CPU path)')
+    return t
+
+
+def lat_block(x, w8, film=None):
+    """one residual SwiGLU block (unet.py:50-54); x [B,128,L] -> new tensor; w8 = the block's 8 tensors; film [B,384] or None"""
+    B, C, L = x.shape
+    y = torch.empty_like(x)
+    arr = (c_void_p * 8)(*[_f32(t).data_ptr() for t in w8])
+    _check(load().osd_lat_block(ptr(_f32(x)), ptr(y), arr, ptr(_f32(film)) if film is not None else c_void_p(0), c_int(B), c_int(L), stream()))
+    return y
+
+
+def lat_rmsnorm(x, gamma=None, silu=False):
+    B, C = x.shape[0], x.shape[1]
+    N = x.numel() // (B * C)
+    y = torch.empty_like(x)
+    _check(load().osd_lat_rmsnorm(ptr(_f32(x)), ptr(_f32(gamma)) if gamma is not None else c_void_p(0), ptr(y), c_int(B), c_int(C),
+                                  ctypes.c_longlong(N), c_int(1 if silu else 0), stream()))
+    return y
+
+
+def lat_conv1x1(x, w, b, act=0, act_channels=0):
+    """x [B,Cin,N] (or [B,Cin] for a Linear) , w [Cout,Cin(,1)]"""
+    lin = x.dim() == 2
+    B, Cin = x.shape[0], x.shape[1]
+    N = 1 if lin else x.shape[2]
+    Cout = w.shape[0]
+    y = torch.empty((B, Cout) if lin else (B, Cout, N), dtype=torch.float32, device=x.device)
+    _check(load().osd_lat_conv1x1(ptr(_f32(x)), ptr(_f32(w)), ptr(_f32(b)) if b is not None else c_void_p(0), ptr(y), c_int(B), c_int(Cin),
+                                  c_int(Cout), ctypes.c_longlong(N), c_int(act), c_int(act_channels), stream()))
+    return y
+
+
+def lat_conv2d(x, w, b, sh):
+    B, Cin, Ain, L = x.shape
+    Cout, _, kh, kw = w.shape
+    if kw != 3:
+        raise OsdError('lat_conv2d: kernel width must be 3')
+    Aout = (Ain + 2 - kh) // sh + 1
+    y = torch.empty(B, Cout, Aout, L, dtype=torch.float32, device=x.device)
+    _check(load().osd_lat_conv2d(ptr(_f32(x)), ptr(_f32(w)), ptr(_f32(b)), ptr(y), c_int(B), c_int(Cin), c_int(Cout), c_int(Ain), c_int(L),
+                                 c_int(kh), c_int(sh), stream()))
+    return y
+
+
+def lat_down3(x, w, b):
+    B, C, L = x.shape
+    y = torch.empty(B, C, L // 3, dtype=torch.float32, device=x.device)
+    _check(load().osd_lat_down3(ptr(_f32(x)), ptr(_f32(w)), ptr(_f32(b)), ptr(y), c_int(B), c_int(C), c_int(L), stream()))
+    return y
+
+
+def lat_up3(x, w, b):
+    B, C, l = x.shape
+    y = torch.empty(B, C, 3 * l, dtype=torch.float32, device=x.device)
+    _check(load().osd_lat_up3(ptr(_f32(x)), ptr(_f32(w)), ptr(_f32(b)), ptr(y), c_int(B), c_int(C), c_int(l), stream()))
+    return y
+
+
+def lat_mix(x, p, g):
+    """x + p * g; p may have batch 1 (broadcast)"""
+    B = x.shape[0]
+    per = x.numel() // B
+    y = torch.empty_like(x)
+    _check(load().osd_lat_mix(ptr(_f32(x)), ptr(_f32(p)), ptr(_f32(g)), ptr(y), c_int(B), ctypes.c_longlong(per), c_int(p.shape[0]), stream()))
+    return y

@@ -261,3 +261,25 @@ def test_style_mirror_state_dict_contract_and_no_cpu_path(golden_dir):
             m(torch.randn(2, 32), torch.rand(2, 5))
     with pytest.raises(lib.OsdError, match='inference-only'):
         m(torch.randn(2, 32), torch.rand(2, 5))
+
+
+def test_latent_mirror_state_dict_contract(golden_dir):
+    """the inference mirror of LatentModel carries the reference's full parameter tree -- names, shapes, order
+    (tests/golden/nb_spec.json, written from the reference module) -- deep-copies, and refuses to run without CUDA"""
+    import copy
+    import json
+    from osu_dreamer_b200 import lib
+    from osu_dreamer_b200.latent import LatentModel, LatentModelArgs, LayerArgs
+    spec = json.load(open(os.path.join(golden_dir, 'nb_spec.json')))['latent']
+    m = LatentModel(6, 32, 3, 3, LatentModelArgs(128, LayerArgs(8, 4, 2), 64, 16))
+    assert [(k, list(v.shape)) for k, v in m.state_dict().items()] == [(k, list(s)) for k, s in spec]
+    assert m.chunk_size == 27 and m.a_dim == 128
+    assert float(getattr(m.decoder.mixers, '0').gate.weight.abs().max()) == 0.0  # zero-initialised like the reference (unet.py:119)
+    assert float(getattr(getattr(m.decoder.layers, '0').blocks, '0')._modules['1'].gamma[0]) == pytest.approx(1e-3)
+    m2 = copy.deepcopy(m)
+    assert m2.audio_encoder._owner[0] is m2
+    # dict-form arguments, as rebuilt from an inference artifact's hparams (models/inference/artifact.py:52-71)
+    LatentModel(6, 32, 3, 3, dict(h_dim=128, ae_args=dict(n_layers=8, expand=4, radius=2), style_head_dim=64, style_heads=16))
+    if not torch.cuda.is_available():
+        with pytest.raises(lib.OsdError, match='no CPU path'):
+            m.audio_encoder(torch.randn(1, 72, 27))
