@@ -283,3 +283,39 @@ def test_latent_mirror_state_dict_contract(golden_dir):
     if not torch.cuda.is_available():
         with pytest.raises(lib.OsdError, match='no CPU path'):
             m.audio_encoder(torch.randn(1, 72, 27))
+
+
+@pytest.mark.skipif(not refimport.available(), reason='reference checkout not present on this host')
+def test_install_swaps_every_model_of_ldm_and_artifacts_load(tmp_path):
+    """after cli.install() the REFERENCE's own LDM (models/inference/model.py:27-32) is built from the three B200 mirrors,
+    and an artifact written from reference-initialised weights loads into it strictly through the reference's
+    load_inference (models/inference/artifact.py:44-49) -- the wiring `predict` relies on (no kernels run here)"""
+    import sys
+    refimport._install_stubs()
+    if refimport.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, refimport.REFERENCE_ROOT)
+    import importlib
+    inf = importlib.import_module('osu_dreamer.models.inference.model')
+    art = importlib.import_module('osu_dreamer.models.inference.artifact')
+    dm = importlib.import_module('osu_dreamer.models.diffusion.model')
+    bb = importlib.import_module('osu_dreamer.models.diffusion.backbone')
+    saved = (inf.LatentModel, inf.StyleModel, inf.DiffusionModel, dm.DiffusionModel, dm.DiffusionModelArgs, bb.BackboneArgs)
+    hparams = dict(emb_dim=6, style_dim=32, n_downs=3, stride=3,
+                   latent_args=dict(h_dim=128, ae_args=dict(n_layers=8, expand=4, radius=2), style_head_dim=64, style_heads=16),
+                   style_args=dict(label_features=128, h_dim=256, depth=8, expand=4),
+                   diffusion_args=dict(global_cond_dim=512, backbone_dim=512, u_head_dim=64,
+                                       backbone_args=dict(depth=8, expand=4, head_dim=64, n_heads=16, radius=2)))
+    try:
+        ref_ldm = inf.LDM(art.dataclass_from_dict(inf.LDMArgs, hparams))  # the unmodified reference, reference init
+        torch.save({'hparams': hparams, 'state_dict': ref_ldm.state_dict()}, tmp_path / 'inference.pt')
+        from osu_dreamer_b200 import cli, denoiser, latent, style
+        cli.install()
+        ours = art.load_inference(tmp_path / 'inference.pt')  # strict load_state_dict inside
+        assert isinstance(ours.latent, latent.LatentModel) and isinstance(ours.style, style.StyleModel)
+        assert isinstance(ours.diffusion, denoiser.DiffusionModel)
+        a, b = ref_ldm.state_dict(), ours.state_dict()
+        assert list(a.keys()) == list(b.keys()) and all(torch.equal(a[k], b[k]) for k in a)
+        assert ours.latent.chunk_size == ref_ldm.latent.chunk_size == 27 and callable(ours.latent.audio_encoder)
+        assert abs(ours.style.c0 - ref_ldm.style.c0) < 1e-12 and abs(ours.diffusion.c0 - ref_ldm.diffusion.c0) < 1e-12
+    finally:  # install() patches the imported reference modules: put the originals back for the other tests
+        inf.LatentModel, inf.StyleModel, inf.DiffusionModel, dm.DiffusionModel, dm.DiffusionModelArgs, bb.BackboneArgs = saved
