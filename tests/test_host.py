@@ -317,5 +317,14 @@ def test_install_swaps_every_model_of_ldm_and_artifacts_load(tmp_path):
         assert list(a.keys()) == list(b.keys()) and all(torch.equal(a[k], b[k]) for k in a)
         assert ours.latent.chunk_size == ref_ldm.latent.chunk_size == 27 and callable(ours.latent.audio_encoder)
         assert abs(ours.style.c0 - ref_ldm.style.c0) < 1e-12 and abs(ours.diffusion.c0 - ref_ldm.diffusion.c0) < 1e-12
+        # the package's own pipeline class reads the same artifact without the reference
+        from osu_dreamer_b200.ldm import load_artifact, pad_to_multiple
+        own = load_artifact(tmp_path / 'inference.pt', device='cpu')
+        c = own.state_dict()
+        assert list(a.keys()) == list(c.keys()) and all(torch.equal(a[k], c[k]) for k in a)
+        from osu_dreamer.data.modules.beatmap import pad_to_multiple as ref_pad
+        x = torch.randn(72, 100)
+        assert torch.equal(pad_to_multiple(x, 27), ref_pad(x, 27)) and pad_to_multiple(x, 27).shape[-1] == 108
+        assert pad_to_multiple(x[:, :54], 27) is not None and pad_to_multiple(x[:, :54], 27).shape[-1] == 54
     finally:  # install() patches the imported reference modules: put the originals back for the other tests
         inf.LatentModel, inf.StyleModel, inf.DiffusionModel, dm.DiffusionModel, dm.DiffusionModelArgs, bb.BackboneArgs = saved
