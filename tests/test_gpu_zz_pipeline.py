@@ -34,6 +34,7 @@ def test_ldm_sample_matches_composed_oracles(golden_dir):
                        **{'diffusion.' + k: v for k, v in dsd.items()}}, strict=True)
     m = m.cuda().eval()
     m.diffusion.precision = 'fp32'  # fp32-grade denoiser: the comparison below is then an fp32-class one
+    m.diffusion.graph_sampler = False  # eager launches (graph replay has its own test, tests/test_gpu_forward.py)
     g = torch.Generator().manual_seed(21)
     L, B, steps = 27 * 64 - 7, 2, 3
     audio = torch.randn(72, L, generator=g)
