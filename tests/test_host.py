@@ -328,3 +328,24 @@ def test_install_swaps_every_model_of_ldm_and_artifacts_load(tmp_path):
         assert pad_to_multiple(x[:, :54], 27) is not None and pad_to_multiple(x[:, :54], 27).shape[-1] == 54
     finally:  # install() patches the imported reference modules: put the originals back for the other tests
         inf.LatentModel, inf.StyleModel, inf.DiffusionModel, dm.DiffusionModel, dm.DiffusionModelArgs, bb.BackboneArgs = saved
+
+
+def test_rank_sharding_properties():
+    """data.batch_refs over arbitrary stream lengths / batch sizes / world sizes: every rank takes the same number of
+    steps, rank r's k-th batch is global batch k*world + r, nothing is duplicated, only a trailing incomplete round (and a
+    trailing partial batch) is dropped"""
+    from hypothesis import given, settings, strategies as st
+    from osu_dreamer_b200.data import batch_refs
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(0, 200), bs=st.integers(1, 9), world=st.integers(1, 5))
+    def check(n, bs, world):
+        per_rank = [list(batch_refs(list(range(n)), bs, r, world)) for r in range(world)]
+        full = n // bs
+        rounds = full // world
+        assert all(len(p) == rounds for p in per_rank)
+        for r, p in enumerate(per_rank):
+            for k, grp in enumerate(p):
+                g = k * world + r
+                assert grp == list(range(g * bs, (g + 1) * bs))
+    check()
