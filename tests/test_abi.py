@@ -48,3 +48,17 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dp, f)).read()
                 assert 'oracle' not in src.replace('# oracle', ''), f'{f} mentions oracle'
+
+
+def test_header_is_plain_c99(tmp_path):
+    """the drop-in boundary is a C ABI: include/osd_b200.h must compile as strict C99 (no C++ / torch types)"""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / 'hdr.c'
+    src.write_text('#include "osd_b200.h"\nint main(void) { return osd_abi_version() == 0; }\n')
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-fsyntax-only', '-I', os.path.join(root, 'include'), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
