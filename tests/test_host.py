@@ -253,7 +253,7 @@ def test_style_mirror_state_dict_contract_and_no_cpu_path(golden_dir):
     sd = m.state_dict()
     assert [(k, list(v.shape)) for k, v in sd.items()] == [(k, list(s)) for k, s in spec] and len(sd) == lib.STYLE_NUM_PARAMS
     assert abs(m.c0 - 64 * (1 - torch.tensor(2.3263478740408408).sigmoid().item()) ** 2) < 1e-12 and m.u_scale == 8.0
-    assert float(m.u_out.bias) == pytest.approx(-0.4328) and float(m.proj_out[1].weight.abs().max()) == 0.0
+    assert float(m.u_out.bias.detach()) == pytest.approx(-0.4328) and float(m.proj_out[1].weight.detach().abs().max()) == 0.0
     with pytest.raises(lib.OsdError):
         StyleModel(16, StyleModelArgs(128, 256, 8, 4))
     if not torch.cuda.is_available():
