@@ -78,6 +78,34 @@ def main():
              n_params_latent=sum(p.numel() for p in lm.parameters()), n_params_style=sum(p.numel() for p in sm.parameters()))
     print('style u', u.tolist(), 'v absmax', float(v.abs().max()), 's_final absmax', float(s_fin.abs().max()))
 
+    # ---- StyleTrainer.forward (models/style/train.py:48-91): loss + gradient norms with seed-matched random draws
+    from osu_dreamer.common.lr_schedule import LRScheduleArgs
+    from osu_dreamer.models.style.train import StyleTrainer
+    tr = StyleTrainer(opt_args=dict(lr=3e-4, weight_decay=0.01), schedule_args=LRScheduleArgs(), label_drop_prob=0.2, osl_weight=1.0,
+                      del_weight=30.0, style_dim=32,
+                      style_args=StyleModelArgs(label_features=N.STYLE_HP['label_features'], h_dim=N.STYLE_HP['h_dim'],
+                                                depth=N.STYLE_HP['depth'], expand=N.STYLE_HP['expand']))
+    torch.set_float32_matmul_precision('highest')  # the constructor sets 'medium' process-wide (train.py:33)
+    tr.style.load_state_dict(ssd, strict=True)
+    g2 = torch.Generator().manual_seed(17)
+    B = 6
+    s1 = torch.randn(B, 32, generator=g2)
+    s1 = s1 * s1.pow(2).mean(1, keepdim=True).add(1e-6).rsqrt()
+    lab = 10 * torch.rand(B, 5, generator=g2)
+    torch.manual_seed(123)  # the draws of train.py:58-64, in order: randperm, rand, randn_like(s1), rand_like(labels)
+    uu = (torch.randperm(B) + torch.rand(B)) / B
+    t = torch.special.ndtri(uu.clamp(1e-6, 1 - 1e-6)).sigmoid()
+    s0 = torch.randn_like(s1)
+    drop = torch.rand_like(lab) < 0.2
+    torch.manual_seed(123)
+    loss, log = tr(tr.style, torch.empty(B, 0, 0), torch.empty(B, 0, 0), s1, lab)
+    loss.backward()
+    gn = {k: float(p.grad.norm()) for k, p in tr.style.named_parameters()}
+    np.savez(os.path.join(OUT, 'nb_style_loss.npz'), s1=s1.numpy(), labels=lab.numpy(), t=t.numpy(), s0=s0.numpy(), drop=drop.numpy(),
+             loss=float(loss.detach()), osl=float(log['osl']), del_=float(log['del']), u_mape=float(log['u_mape']),
+             grad_names=np.array(list(gn.keys())), grad_norms=np.array(list(gn.values())))
+    print('style loss', float(loss.detach()), {k: float(v) for k, v in log.items()})
+
 
 if __name__ == '__main__':
     main()

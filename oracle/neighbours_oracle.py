@@ -183,3 +183,23 @@ def style_sample(sd: SD, labels: Tensor, s_init: Tensor, num_steps: int = 16, hp
         u, v = style_forward(sd, s, labels, hp)
         s = s - eta * u[:, None] * v
     return s, u0, eta
+
+
+# ---------------------------------------------------------------------------------------------- style trainer loss
+def style_trainer_loss(sd: SD, s1: Tensor, labels: Tensor, s0: Tensor, t: Tensor, drop: Tensor,
+                       osl_weight: float = 1.0, del_weight: float = 30.0, hp=STYLE_HP):
+    """StyleTrainer.forward (models/style/train.py:48-91) with its random draws passed in: t [B] (the stratified
+    logit-normal times), s0 [B,S] (noise), drop [B,5] bool (labels replaced by -1) -> (loss, dict(osl, del, u_mape))."""
+    c0 = style_constants(hp['style_dim'])[0]
+    st = torch.lerp(s0, s1, t[:, None])
+    masked = torch.where(drop, torch.full_like(labels, -1.0), labels)
+    u_pred, v_pred = style_forward(sd, st, masked, hp)
+    d_sq = (st - s1).square().sum(1)
+    u_target = (d_sq + c0).sqrt()
+    denoised = st - u_pred[:, None] * v_pred
+    osl = ((denoised - s1).square().sum(1) / (d_sq + c0)).mean()
+    v_target = (st - s1) / u_target[:, None]
+    del_ = (v_pred - v_target).square().sum(1).mean()
+    loss = osl_weight * osl + del_weight * del_
+    u_err = ((u_pred - u_target) / u_target).abs().mean()
+    return loss, dict(osl=osl, del_=del_, u_mape=u_err)
