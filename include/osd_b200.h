@@ -33,7 +33,8 @@ extern "C" {
 #define OSD_API
 #endif
 
-/* ---- model dimensions (osu_dreamer/models/diffusion/model.yml:77-90; fixed at compile time) ---- */
+/* ---- model dimensions (osu_dreamer/models/diffusion/model.yml:77-90).  The widths are compile-time constants of the
+ * kernels; the backbone depth (BackboneArgs.depth, backbone.py:19) is a run-time property carried by `mode` ---- */
 #define OSD_E 6        /* emb_dim       */
 #define OSD_A 128      /* a_dim         */
 #define OSD_S 32       /* style_dim     */
@@ -42,7 +43,8 @@ extern "C" {
 #define OSD_H 16       /* n_heads       */
 #define OSD_HD 64      /* head_dim      */
 #define OSD_DH 1024    /* n_heads*head_dim */
-#define OSD_DEPTH 8
+#define OSD_DEPTH 8      /* default depth (model.yml:85): what a `mode` with depth bits 0 means */
+#define OSD_MAX_DEPTH 32
 #define OSD_HID 1365   /* int(512*4*2/3), osu_dreamer/common/swiglu.py:18 */
 #define OSD_HIDP 1408  /* HID padded to a multiple of 64 (internal) */
 #define OSD_U 64       /* u_head_dim    */
@@ -51,6 +53,10 @@ extern "C" {
 #define OSD_BF16 0     /* bf16 tensor-core operands, fp32 accumulate / residual / statistics */
 #define OSD_F32X3 1    /* fp32-grade: every tensor-core product as the 3-term bf16 split a_hi*b_hi + a_lo*b_hi + a_hi*b_lo
                           (operands stored as (hi | lo) bf16 pairs); inference only */
+
+/* Every `mode` argument below: bits 0-7 = precision, bits 8-15 = backbone depth (0 selects OSD_DEPTH).  A model of depth
+ * d has 20 + 18 * d parameter tensors (osd_num_params): the 6 leading tensors, 18 per layer, the 14 tail tensors. */
+#define OSD_MODE(precision, depth) ((precision) | ((depth) << 8))
 
 OSD_API int osd_abi_version(void);
 OSD_API const char* osd_last_error(void);
@@ -91,7 +97,11 @@ OSD_API size_t osd_rope_table_floats(int L);
  * columns h*64..h*64+63 of its block); y bf16 [B*L, H*64]; lse fp32 [B, H, L] (natural log, nullable).
  * bound_log2: optional DEVICE scalar, an upper bound of the scaled scores in log2 units (q,k are RMS-normalised
  * in this model, so such a bound exists per layer): selects the fixed-max softmax; NULL -> online softmax.
- * variant: 0 = 64-row kv tiles / 3 CTAs per SM, 1 = 128-row kv tiles / 2 CTAs per SM. */
+ * variant: 7 is the kernel the model runs (128 q rows per CTA, 64-row kv tiles, two S accumulators ping-pong, Q tile
+ * resident in TMEM, 2 CTAs per SM; csrc/attn_fwd_db.cu).  The others are kept for A/B measurements: 0 / 1 = single-S
+ * kernel with 64- / 128-row kv tiles and P staged in shared memory, 2 / 3 = the same with P kept in TMEM
+ * (csrc/attn_fwd.cu); 4 = double-buffered S with Q in shared memory, 6 = 4 + early barrier probes and S prefetch,
+ * 8 = 7 + pre-scaled Q and row sums by a ones-tile MMA (csrc/attn_fwd_db.cu).  Anything else is an error. */
 OSD_API int osd_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                          int variant, void* stream);
 
@@ -107,10 +117,13 @@ OSD_API int osd_channels_to_tokens(const float* in, void* out, int out_fp32, int
 #define OSD_NUM_PARAMS 164
 
 /* Sizes the caller must allocate (device memory, 1024-byte aligned). */
+OSD_API int osd_num_params(int mode);                      /* 20 + 18 * depth (164 at the default depth) */
 OSD_API size_t osd_packed_bytes(int mode);                 /* tensor-core operand copies of the weights */
-OSD_API size_t osd_cond_floats(int B);                     /* cg + all adaLN vectors + u_mod (fp32)     */
+OSD_API size_t osd_cond_floats(int B);                     /* cg + all adaLN vectors + u_mod (fp32), default depth */
+OSD_API size_t osd_cond_floats_mode(int B, int mode);      /* the same for the depth carried by mode */
 OSD_API size_t osd_workspace_bytes(int B, int L, int a_batch, int mode, int save);
-OSD_API size_t osd_sample_extra_bytes(int B, int L, int a_batch);
+OSD_API size_t osd_sample_extra_bytes(int B, int L, int a_batch);             /* default depth */
+OSD_API size_t osd_sample_extra_bytes_mode(int B, int L, int a_batch, int mode);
 
 /* Convert the fp32 parameters into padded tensor-core operands (call after every optimizer step /
  * load_state_dict).  HID 1365 is padded to 1408 with zero rows/columns (swiglu.py:18). */
@@ -122,6 +135,13 @@ OSD_API int osd_pack_weights(const float* const* params, void* packed, int mode,
 OSD_API int osd_precompute_conditioning(const float* const* params, const void* packed, int mode, const float* audio,
                                         int a_batch, const float* style, int B, int L, void* scratch, void* a_tok,
                                         float* cond, void* stream);
+
+/* The (a, cg) arguments of DiffusionModel._pred (model.py:86-103) exactly as the reference passes them -- a
+ * [a_batch,128,L] and cg [B,512], fp32 channels-first, possibly edited by the caller since _precompute_conditioning --
+ * turned into what osd_pred_forward consumes: a_tok (token-major operand; (hi | lo) pairs in OSD_F32X3) and the cond pack
+ * (cg copied to its head, then ssg1 / ssg2 of every layer and u_mod evaluated on it). */
+OSD_API int osd_conditioning_from(const float* const* params, int mode, const float* a, int a_batch, const float* cg,
+                                  int B, int L, void* a_tok, float* cond, void* stream);
 
 /* DiffusionModel._pred (model.py:86-103): xt [B,6,L] fp32 -> u [B], v [B,6,L] fp32.  With save != 0 the
  * workspace (osd_workspace_bytes(..., save=1)) keeps every activation osd_pred_backward needs. */
@@ -153,8 +173,6 @@ OSD_API int osd_attn_bwd_fused(const void* qkv, const void* y, const void* dy, c
 /* Debugging aid (tools/trace_attn_bwd.py): record the event timeline of CTA `cta` of the single-pass attention
  * backward into buf (DEVICE memory, 3 x 1024 u64 records: (event << 48) | (tile << 32) | SM clock); null = off. */
 OSD_API void osd_debug_attn_bwd_trace(unsigned long long* buf, int cta);
-/* same for the forward kernel variant 5 (2 x 1024 records) */
-OSD_API void osd_debug_attn_fwd_trace(unsigned long long* buf, int cta);
 
 /* ---- latent model, inference half: LatentModel.audio_encoder before and LatentModel.decode after diffusion.sample in
  * LDM.sample (osu_dreamer/models/inference/model.py:47,51; models/latent/model.py:53,103-133, unet.py, spec_features.py;

@@ -148,8 +148,8 @@ def rope(x: Tensor) -> Tensor:
     """osu_dreamer/common/attn.py:12-29 -- half-split rotation; the angle table
     is built in fp32 exactly as the reference does, then cast to x.dtype."""
     N, D = x.shape[-2], x.shape[-1]
-    inv_freq = 10000 ** (torch.arange(0, D, 2).float() / -D)
-    t = torch.arange(N, dtype=torch.float32)
+    inv_freq = 10000 ** (torch.arange(0, D, 2, device=x.device).float() / -D)
+    t = torch.arange(N, dtype=torch.float32, device=x.device)
     freqs = torch.outer(t, inv_freq)
     x1, x2 = x.chunk(2, dim=-1)
     cos = freqs.cos().to(x.dtype)
@@ -237,13 +237,16 @@ def forward(sd: SD, audio: Tensor, style: Tensor, xt: Tensor, hp=HP, taps=None):
 
 
 @torch.no_grad()
-def sample(sd: SD, audio: Tensor, style: Tensor, x_init: Tensor, num_steps: int, hp=HP):
+def sample(sd: SD, audio: Tensor, style: Tensor, x_init: Tensor, num_steps: int, hp=HP, u0: float | None = None):
     """osu_dreamer/models/diffusion/model.py:117-138 with the initial noise
-    passed in (the reference draws it from the global generator at :125)."""
+    passed in (the reference draws it from the global generator at :125).
+    `u0` (optional) injects the probe's batch mean: samples only interact through it, so a few samples of a
+    large batch can be checked against the oracle without running the oracle on the whole batch."""
     c0, _ = constants(hp['emb_dim'])
     a, cg = precompute_conditioning(sd, audio, style)
     x = x_init
-    u0 = pred(sd, a, cg, x, hp)[0].mean().item()
+    if u0 is None:
+        u0 = pred(sd, a, cg, x, hp)[0].mean().item()
     eta = 1.0 - (math.sqrt(c0) / max(u0, math.sqrt(c0) + 1e-6)) ** (1.0 / num_steps)
     for _ in range(num_steps):
         u, v = pred(sd, a, cg, x, hp)

@@ -35,11 +35,42 @@ def grad_summary(named_grads):
     return np.array(names), np.array(norms), np.stack(heads)
 
 
+def golden_validation(ns, sd):
+    """DiffusionTrainer.validation_step (train.py:128-139) of the unmodified reference on one ragged full-length map:
+    l = 8 * 96 + 5 frames -> 8 segments of 96 (the tail is dropped), EMA weights, values read from what it logs."""
+    l, seed = 8 * 96 + 5, 41
+    inp = O.make_inputs(1, l, seed=seed)
+    trainer = ns.DiffusionTrainer(
+        val_batches=8, opt_args=dict(lr=3e-4, weight_decay=0.01),
+        schedule_args=ns.LRScheduleArgs(warmup_steps=1000, warmup_init=0.3, decay_start=30000),
+        osl_weight=1.0, del_weight=30.0, emb_dim=6, a_dim=128, style_dim=32,
+        diffusion_args=refimport.default_args(ns))
+    trainer.diffusion_ema.module.load_state_dict(sd)  # the EMA copy is what validation uses; `diffusion` keeps its init
+    torch.set_float32_matmul_precision('highest')  # see main(): train.py:53 sets 'medium' process-wide
+    labels = torch.zeros(1, 5)
+    torch.manual_seed(123)
+    trainer.validation_step((inp['h'], inp['x1'], inp['s'], labels), 0)
+    logged = {k: float(v) for k, v in trainer.logged.items()}
+    torch.manual_seed(123)  # replay the draws of train.py:79,82 at B = 8
+    uu = (torch.randperm(8) + torch.rand(8)) / 8
+    t = torch.special.ndtri(uu.clamp(1e-6, 1 - 1e-6)).sigmoid()
+    # randn_like of the reference's non-contiguous rearranged view (strides (96, 773, 1)) fills a (96, 768, 1)-strided
+    # tensor: NOT the values of randn(8, 6, 96) -- replay it on the same view
+    from einops import rearrange
+    x0 = torch.randn_like(rearrange(inp['x1'][..., :768], '1 ... (b l) -> b ... l', b=8)).contiguous()
+    np.savez(os.path.join(OUT, 'val_l773.npz'), l=l, seed=seed, perm_plus_rand=(uu * 8).numpy(), t=t.numpy(), x0=x0.numpy(),
+             keys=np.array(sorted(logged)), vals=np.array([logged[k] for k in sorted(logged)]))
+    print('validation_step', logged)
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
     ns = refimport.import_reference(with_trainer=True)
     sd = O.make_state_dict(1234)
+    if len(sys.argv) > 1 and sys.argv[1] == 'val':  # only the round-2 addition (the other fixtures stay byte-identical)
+        golden_validation(ns, sd)
+        return
 
     # ---- known-answer constants and default-init facts (SURVEY.md 8(c)) ----
     m0 = ns.DiffusionModel(6, 128, 32, refimport.default_args(ns)).eval()
@@ -145,6 +176,7 @@ def main():
         emas.append(torch.cat([ema.module.weight.detach().reshape(-1), ema.module.bias.detach().reshape(-1)]).clone())
     np.savez(os.path.join(OUT, 'adamw_ema.npz'), p0=p0.numpy(), grads=torch.stack(grads).numpy(),
              params=torch.stack(ps).numpy(), emas=torch.stack(emas).numpy(), grad_norms=np.array(norms_))
+    golden_validation(ns, sd)
     print('done')
 
 

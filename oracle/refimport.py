@@ -30,8 +30,8 @@ def _install_stubs():
             def save_hyperparameters(self, *a, **k):
                 pass
 
-            def log_dict(self, *a, **k):
-                pass
+            def log_dict(self, d=None, *a, **k):
+                self.logged = dict(d) if d is not None else {}  # lets make_golden.py read what validation_step logs
 
             def log(self, *a, **k):
                 pass

@@ -576,10 +576,9 @@ int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const 
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   p.trace = g_fb_trace;
   p.trace_cta = g_fb_trace_cta;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first()) {
     OSD_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BYTES));
-    attr_set = true;
   }
   const long long grid = (long long)n_t * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_bwd_fused: grid too large");

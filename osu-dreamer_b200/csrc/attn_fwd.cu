@@ -372,10 +372,9 @@ static int launch_attn_fwd_t(const void* qkv, void* y, float* lse, const float* 
   p.dh = dh;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first()) {
     OSD_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<BKV, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
   }
   const int n_qt = ceil_div(L, AT_BQ);
   const long long grid = (long long)n_qt * H * B;
@@ -394,10 +393,10 @@ int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log
   if (variant == 8) return launch_attn_fwd_db_dr(qkv, y, lse, bound_log2, B, L, H, stream);  // direct exponent
   if (variant == 7) return launch_attn_fwd_db_qt(qkv, y, lse, bound_log2, B, L, H, stream);  // Q in TMEM
   if (variant == 6) return launch_attn_fwd_db_pf(qkv, y, lse, bound_log2, B, L, H, stream);  // + probes / S prefetch
-  if (variant == 5) return launch_attn_fwd_w8(qkv, y, lse, bound_log2, B, L, H, stream);  // + 8 softmax warps
   if (variant == 1) return launch_attn_fwd_t<128, false>(qkv, y, lse, bound_log2, B, L, H, stream);
   if (variant == 2) return launch_attn_fwd_t<64, true>(qkv, y, lse, bound_log2, B, L, H, stream);
   if (variant == 3) return launch_attn_fwd_t<128, true>(qkv, y, lse, bound_log2, B, L, H, stream);
+  OSD_CHECK(variant == 0, "attn_fwd: unknown variant %d (0-4, 6-8)", variant);
   return launch_attn_fwd_t<64, false>(qkv, y, lse, bound_log2, B, L, H, stream);
 }
 

@@ -420,10 +420,9 @@ static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const floa
   p.B = B; p.H = H; p.L = L; p.dh = dh;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first()) {
     OSD_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<PF, QT, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES));
-    attr_set = true;
   }
   const long long grid = (long long)ceil_div(L, 128) * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_fwd_db: grid too large");

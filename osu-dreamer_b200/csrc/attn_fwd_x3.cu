@@ -284,10 +284,9 @@ int launch_attn_fwd_x3(const void* qkv, void* y, float* lse, const float* bound_
   p.B = B; p.H = H; p.L = L; p.dh = dh;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first()) {
     OSD_CUDA(cudaFuncSetAttribute(attn_fwd_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X3_SMEM_BYTES));
-    attr_set = true;
   }
   const long long grid = (long long)ceil_div(L, 128) * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_fwd_x3: grid too large");

@@ -43,6 +43,18 @@ const char* get_error();
   } while (0)
 
 int num_sms();
+// function attributes (cudaFuncSetAttribute) are per device: a `static DeviceOnce once; if (once.first()) {...}` guard
+// runs its body once for every device the process touches
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
 void count_launch();
 unsigned long long launch_count();
 

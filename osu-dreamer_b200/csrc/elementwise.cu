@@ -549,10 +549,9 @@ int launch_swiglu_norm(const void* vg, void* hn, float* rinv_out, int is_fp32, i
                                                                   static_cast<float*>(hn), rinv_out, T, nullptr);
   else {
     constexpr int smem = SWS_WARPS * SWS_ST * SWS_ROW + SWS_WARPS * SWS_ST * 8;
-    static bool set = false;
-    if (!set) {
+    static DeviceOnce once;
+    if (once.first()) {
       OSD_CUDA(cudaFuncSetAttribute(swiglu_norm_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      set = true;
     }
     const int grid = std::min(ceil_div(T, SWS_WARPS), num_sms());
     swiglu_norm_stream_kernel<<<grid, SWS_WARPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(vg),

@@ -363,10 +363,9 @@ __global__ void __launch_bounds__(256) dwconv_prenorm_bwd_kernel(
 int launch_dwconv_prenorm_bwd(const void* dz2, const void* hmod, const float* x1, const float* mod, const float* wconv,
                               float* dx, float* dmod, float* dw, float* db, int B, int L, cudaStream_t s) {
   const int smem = 2 * (DWB_TOK + 4) * D * 2 + 7 * D * 4;
-  static bool set = false;
-  if (!set) {
+  static DeviceOnce once;
+  if (once.first()) {
     OSD_CUDA(cudaFuncSetAttribute(dwconv_prenorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = true;
   }
   dim3 grid(ceil_div(L, DWB_TOK * DWB_SUB), B);
   dwconv_prenorm_bwd_kernel<<<grid, 256, smem, s>>>(static_cast<const __nv_bfloat16*>(dz2),
@@ -504,10 +503,9 @@ __global__ void __launch_bounds__(SWB_WARPS * 32, 2) swiglu_norm_bwd_kernel(cons
 }
 int launch_swiglu_norm_bwd(const void* vg, const void* dhn, const float* rinv, void* dvg, float* dbvg, int T,
                            cudaStream_t s) {
-  static bool set = false;
-  if (!set) {
+  static DeviceOnce once;
+  if (once.first()) {
     OSD_CUDA(cudaFuncSetAttribute(swiglu_norm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWB_SMEM));
-    set = true;
   }
   swiglu_norm_bwd_kernel<<<ceil_div(T, SWB_ROWS), SWB_WARPS * 32, SWB_SMEM, s>>>(static_cast<const __nv_bfloat16*>(vg),
                                                                         static_cast<const __nv_bfloat16*>(dhn), rinv,

@@ -450,10 +450,9 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   p.raw_out = a.raw_out;
 
   auto kern = gemm_kernel<BN, ELEM, QKV, EW>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static DeviceOnce once;  // per instantiation
+  if (once.first()) {
     OSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
   }
   const int total = p.tiles_m * p.tiles_n * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();

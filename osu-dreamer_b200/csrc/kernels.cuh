@@ -93,7 +93,6 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
 // single-pass backward (attn_bwd_fused.cu): dq_acc fp32 [B*L, H*64] is scratch (zeroed and reduced into here),
 // stats fp32 [attn_bwd_fused_stats_floats()] and dy_scaled bf16 [B*L, H*64] are scratch
 size_t attn_bwd_fused_stats_floats(int B, int L, int H);
-void attn_fwd_w8_set_trace(unsigned long long* buf, int cta);  // debugging aid, see osd_debug_attn_fwd_trace
 void attn_bwd_fused_set_trace(unsigned long long* buf, int cta);  // debugging aid, see osd_debug_attn_bwd_trace
 // convert_dq = 0 leaves dq in dq_acc (fp32, unscaled; multiply by attn_bwd_fused_dq_scale()) unless the fallback flag
 // (*attn_bwd_fused_flag(...) != 0) says the two-kernel path wrote dq into dqkv: launch_qknorm_rope_bwd consumes that.
@@ -103,8 +102,6 @@ const int* attn_bwd_fused_flag(const float* stats, int B, int L, int H);
 static inline float attn_bwd_fused_dq_scale() { return 0.125f; }
 int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int variant,
                     cudaStream_t stream);
-int launch_attn_fwd_w8(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
-                       cudaStream_t stream);
 int launch_attn_fwd_db(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                        cudaStream_t stream);
 int launch_attn_fwd_db_qt(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,

@@ -157,10 +157,9 @@ int launch_lat_block(const float* x, float* y, const float* const* w8, const flo
   OSD_CHECK(x && y && w8 && x != y && B > 0 && L > 0, "lat_block: bad arguments (x and y must be distinct buffers)");
   LatBlockW w{w8[0], w8[1], w8[2], w8[3], w8[4], w8[5], w8[6], w8[7]};
   const int smem = LB_FLOATS * 4;
-  static bool set = false;
-  if (!set) {
+  static DeviceOnce once;
+  if (once.first()) {
     OSD_CUDA(cudaFuncSetAttribute(lat_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = true;
   }
   dim3 grid(ceil_div(L, LTL), B);
   lat_block_kernel<<<grid, 256, smem, s>>>(x, y, w, film, L);

@@ -15,7 +15,7 @@ static inline size_t esz_of(int) { return 2; }              // operands are bf16
 static inline int kmul_of(int mode) { return mode == OSD_F32X3 ? 2 : 1; }  // (hi | lo) pairs double the K extent
 static inline size_t al(size_t x) { return align_up(x, 1024); }
 
-PackedLayout packed_layout(int mode) {
+PackedLayout packed_layout(int mode, int depth) {
   PackedLayout p;
   p.esz = esz_of(mode);
   p.kmul = kmul_of(mode);
@@ -36,16 +36,16 @@ PackedLayout packed_layout(int mode) {
   lo += al((size_t)512 * OSD_HIDP * e);
   p.layer0 = off;
   p.layer_stride = lo;
-  off += 8 * lo;
+  off += depth * lo;
   p.bvg = off;
-  off += al((size_t)8 * 2 * OSD_HIDP * 4);
+  off += al((size_t)depth * 2 * OSD_HIDP * 4);
   p.bounds = off;
-  off += al(8 * 4);
+  off += al(depth * 4);
   p.total = off;
   return p;
 }
 
-ActPlan make_plan(int B, int L, int a_batch, int mode, int save) {
+ActPlan make_plan(int B, int L, int a_batch, int mode, int save, int depth) {
   ActPlan a;
   const size_t T = (size_t)B * L, Ta = (size_t)a_batch * L;
   const bool X = mode == OSD_F32X3;
@@ -73,7 +73,7 @@ ActPlan make_plan(int B, int L, int a_batch, int mode, int save) {
   a.f = take(T * 512 * 4);
   a.layer_bytes = o;
   a.layer_stride = save ? o : 0;
-  size_t tot = save ? 8 * o : o;
+  size_t tot = save ? depth * o : o;
   auto take2 = [&](size_t bytes) {
     size_t r = tot;
     tot += al(bytes);
@@ -89,15 +89,15 @@ ActPlan make_plan(int B, int L, int a_batch, int mode, int save) {
 }
 
 // ------------------------------------------------------------------------------------------------
-static int pack_weights(const float* const* P, uint8_t* packed, int mode, cudaStream_t s) {
-  const PackedLayout lay = packed_layout(mode);
+static int pack_weights(const float* const* P, uint8_t* packed, int mode, int depth, cudaStream_t s) {
+  const PackedLayout lay = packed_layout(mode, depth);
   const bool X = mode == OSD_F32X3;
   auto pack = [&](const float* src, void* dst, int rs, int cs, int rd, int cd, int sa, int sp) -> int {
     if (X) return launch_pack_weight_split(src, dst, rs, cs, rd, cd, sa, sp, s);
     return launch_pack_weight(src, dst, 0, rs, cs, rd, cd, sa, sp, s);
   };
   OSD_TRY(pack(P[P_AUDIO_W], packed + lay.wa, 128, 128, 128, 128, 0, 0));
-  for (int l = 0; l < 8; ++l) {
+  for (int l = 0; l < depth; ++l) {
     uint8_t* lb = packed + lay.layer0 + l * lay.layer_stride;
     OSD_TRY(pack(P[lp(l, L_CL_W)], lb + lay.l_cl, 512, 128, 512, 128, 0, 0));
     OSD_TRY(pack(P[lp(l, L_QKV_W)], lb + lay.l_qkv, 3072, 512, 3072, 512, 0, 0));
@@ -111,8 +111,22 @@ static int pack_weights(const float* const* P, uint8_t* packed, int mode, cudaSt
   return 0;
 }
 
-static int precompute_conditioning(const float* const* P, const PackedW& W, int mode, const float* audio, int a_batch,
-                                   const float* style, int B, int L, void* a_tok, float* cond, void* scratch,
+// modulation vectors of every layer (backbone.py:76,82) and u_mod (model.py:100) from cg = cond[0 : B*512]
+static int modulation_from_cg(const float* const* P, int depth, float* cond, int B, cudaStream_t s) {
+  CondPack c{cond, B, depth};
+  for (int l = 0; l < depth; ++l) {
+    OSD_TRY(launch_linear_small(c.cg(), P[lp(l, L_SSG1_W)], P[lp(l, L_SSG1_B)], const_cast<float*>(c.mod1(l)), B, 1536,
+                                512, 0, s));
+    OSD_TRY(launch_linear_small(c.cg(), P[lp(l, L_SSG2_W)], P[lp(l, L_SSG2_B)], const_cast<float*>(c.mod2(l)), B, 1536,
+                                512, 0, s));
+  }
+  const int ts = tail_shift(depth);
+  OSD_TRY(launch_linear_small(c.cg(), P[P_UMOD_W + ts], P[P_UMOD_B + ts], const_cast<float*>(c.umod()), B, 128, 512, 0, s));
+  return 0;
+}
+
+static int precompute_conditioning(const float* const* P, const PackedW& W, int mode, int depth, const float* audio,
+                                   int a_batch, const float* style, int B, int L, void* a_tok, float* cond, void* scratch,
                                    cudaStream_t s) {
   const int Ta = a_batch * L;
   const int X = mode == OSD_F32X3;
@@ -128,18 +142,9 @@ static int precompute_conditioning(const float* const* P, const PackedW& W, int 
   g.elem = ELEM_BF16; g.epi = EPI_SILU; g.C = a_tok; g.ldc = 128 * km; g.c_fp32 = 0; g.split3 = X; g.c_split = X;
   g.bias = P[P_AUDIO_B];
   OSD_TRY(launch_gemm(g, s));
-  // cg = silu(proj_style(style)) (model.py:46,83); modulation vectors for every layer (backbone.py:76,82) and u_mod
-  CondPack c{cond, B};
-  float* cw = cond;
-  OSD_TRY(launch_linear_small(style, P[P_STYLE_W], P[P_STYLE_B], cw, B, 512, 32, 1, s));
-  for (int l = 0; l < 8; ++l) {
-    OSD_TRY(launch_linear_small(c.cg(), P[lp(l, L_SSG1_W)], P[lp(l, L_SSG1_B)], const_cast<float*>(c.mod1(l)), B, 1536,
-                                512, 0, s));
-    OSD_TRY(launch_linear_small(c.cg(), P[lp(l, L_SSG2_W)], P[lp(l, L_SSG2_B)], const_cast<float*>(c.mod2(l)), B, 1536,
-                                512, 0, s));
-  }
-  OSD_TRY(launch_linear_small(c.cg(), P[P_UMOD_W], P[P_UMOD_B], const_cast<float*>(c.umod()), B, 128, 512, 0, s));
-  return 0;
+  // cg = silu(proj_style(style)) (model.py:46,83)
+  OSD_TRY(launch_linear_small(style, P[P_STYLE_W], P[P_STYLE_B], cond, B, 512, 32, 1, s));
+  return modulation_from_cg(P, depth, cond, B, s);
 }
 
 // proj_cl for one layer: cl = a_tok * Wcl^T + b  -> bf16 [Ta, 512]   (backbone.py:63,78)
@@ -166,14 +171,14 @@ static int attn_fwd_variant() {
 struct FwdCtx {
   const float* const* P;
   PackedW W;
-  int mode, B, L, a_batch;
+  int mode, depth, B, L, a_batch;
   CondPack cond;
   const void* a_tok;  // [Ta,128] operand dtype
   const float* rope;
   uint8_t* ws;
   ActPlan plan;
   int save;
-  const uint8_t* cl_hoisted;  // [8][Ta,512] bf16 or null
+  const uint8_t* cl_hoisted;  // [depth][Ta,512] bf16 or null
 };
 
 static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cudaStream_t s) {
@@ -187,12 +192,13 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
   const void* a_tok = c.a_tok;
   const size_t cl_bytes = al((size_t)Ta * 512 * (X ? 4 : 2));
 
+  const int depth = c.depth, ts = tail_shift(depth);
   OSD_TRY(launch_proj_in(xt, c.P[P_IN_W], c.P[P_IN_B], reinterpret_cast<float*>(LB(0) + pl.x0), B, L, s));
-  for (int l = 0; l < 8; ++l) {
+  for (int l = 0; l < depth; ++l) {
     uint8_t* lb = LB(l);
     float* x0 = reinterpret_cast<float*>(lb + pl.x0);
     float* x1 = reinterpret_cast<float*>(lb + pl.x1);
-    float* xo = (l == 7) ? reinterpret_cast<float*>(c.ws + pl.x_final)
+    float* xo = (l == depth - 1) ? reinterpret_cast<float*>(c.ws + pl.x_final)
                          : reinterpret_cast<float*>(LB(l + 1) + pl.x0);
     const void* cl;
     if (c.cl_hoisted != nullptr) {
@@ -238,16 +244,17 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
     OSD_TRY(launch_gemm(po, s));
     OSD_TRY(launch_postnorm_gate_add(x1, reinterpret_cast<float*>(lb + pl.f), c.cond.mod2(l), xo, B, L, s));
   }
-  OSD_TRY(launch_final_norm_proj_out(reinterpret_cast<float*>(c.ws + pl.x_final), c.P[P_OUT_W], c.P[P_OUT_B], v, B, L,
-                                     s));
+  OSD_TRY(launch_final_norm_proj_out(reinterpret_cast<float*>(c.ws + pl.x_final), c.P[P_OUT_W + ts], c.P[P_OUT_B + ts], v,
+                                     B, L, s));
   // ---- distance head (model.py:99-102)
-  const float* uw[8] = {c.P[P_UH0_W], c.P[P_UH0_B], c.P[P_UH1_W], c.P[P_UH1_B],
-                        c.P[P_UH3_W], c.P[P_UH3_B], c.P[P_UH4_W], c.P[P_UH4_B]};
+  const float* uw[8] = {c.P[P_UH0_W + ts], c.P[P_UH0_B + ts], c.P[P_UH1_W + ts], c.P[P_UH1_B + ts],
+                        c.P[P_UH3_W + ts], c.P[P_UH3_B + ts], c.P[P_UH4_W + ts], c.P[P_UH4_B + ts]};
   float* fsum = reinterpret_cast<float*>(c.ws + pl.fsum);
   float* fpart = reinterpret_cast<float*>(c.ws + pl.fpart);
   OSD_TRY(launch_u_head(xt, uw, fpart, c.save ? reinterpret_cast<float*>(c.ws + pl.uh1) : nullptr,
                         c.save ? reinterpret_cast<float*>(c.ws + pl.uh2) : nullptr, B, L, s));
-  OSD_TRY(launch_u_final(fpart, fsum, c.cond.umod(), c.P[P_UOUT_W], c.P[P_UOUT_B], sqrtf(2.0f * OSD_E), L, u, B, s));
+  OSD_TRY(launch_u_final(fpart, fsum, c.cond.umod(), c.P[P_UOUT_W + ts], c.P[P_UOUT_B + ts], sqrtf(2.0f * OSD_E), L, u, B,
+                         s));
   return 0;
 }
 
@@ -257,7 +264,7 @@ struct BwdPlan {
   size_t gWvg, gWpo, gbvg;  // padded fp32 gradient scratch
   size_t total;
 };
-static BwdPlan make_bwd_plan(int B, int L, int a_batch) {
+static BwdPlan make_bwd_plan(int B, int L, int a_batch, int depth) {
   BwdPlan p;
   const size_t T = (size_t)B * L, Ta = (size_t)a_batch * L;
   size_t o = 0;
@@ -281,7 +288,7 @@ static BwdPlan make_bwd_plan(int B, int L, int a_batch) {
   p.a_pre = take(Ta * 128 * 4);
   p.da_pre = take(Ta * 128 * 2);
   p.audio_tm = take(Ta * 128 * 2);
-  p.dcond = take(CondPack::floats(B) * 4);
+  p.dcond = take(CondPack::floats(B, depth) * 4);
   p.dfsum = take((size_t)B * 64 * 4);
   p.dpre_s = take((size_t)B * 512 * 4 * 2);
   p.gWvg = take((size_t)2 * OSD_HIDP * 512 * 4);
@@ -334,34 +341,36 @@ static int pred_backward(const FwdCtx& c, const float* audio, const float* style
   OSD_CHECK(c.a_batch == B, "pred_backward: broadcast audio (a_batch=1) is an inference-only shape");
   OSD_CHECK(c.save, "pred_backward: forward must have been run with save=1");
   const ActPlan& pl = c.plan;
-  const BwdPlan bp = make_bwd_plan(B, L, c.a_batch);
+  const int depth = c.depth, ts = tail_shift(depth);
+  const BwdPlan bp = make_bwd_plan(B, L, c.a_batch, depth);
   auto LB = [&](int l) { return c.ws + (size_t)l * pl.layer_stride; };
   float* dx = reinterpret_cast<float*>(bw + bp.dx);
   void* dh = bw + bp.dh;
   float* dcond = reinterpret_cast<float*>(bw + bp.dcond);
-  CondPack dc{dcond, B};
+  CondPack dc{dcond, B, depth};
   float* da_tok = reinterpret_cast<float*>(bw + bp.da_tok);
   float* gWvg = reinterpret_cast<float*>(bw + bp.gWvg);
   float* gWpo = reinterpret_cast<float*>(bw + bp.gWpo);
   float* gbvg = reinterpret_cast<float*>(bw + bp.gbvg);
-  OSD_CUDA(cudaMemsetAsync(dcond, 0, CondPack::floats(B) * 4, s));
+  OSD_CUDA(cudaMemsetAsync(dcond, 0, CondPack::floats(B, depth) * 4, s));
   OSD_CUDA(cudaMemsetAsync(da_tok, 0, (size_t)T * 128 * 4, s));
 
   // ---- heads
-  OSD_TRY(launch_final_bwd(reinterpret_cast<float*>(c.ws + pl.x_final), dv, c.P[P_OUT_W], dx, G[P_OUT_W], G[P_OUT_B], B,
-                           L, s));
+  OSD_TRY(launch_final_bwd(reinterpret_cast<float*>(c.ws + pl.x_final), dv, c.P[P_OUT_W + ts], dx, G[P_OUT_W + ts],
+                           G[P_OUT_B + ts], B, L, s));
   {
     float* dfsum = reinterpret_cast<float*>(bw + bp.dfsum);
-    OSD_TRY(launch_u_final_bwd(du, reinterpret_cast<float*>(c.ws + pl.fsum), c.cond.umod(), c.P[P_UOUT_W],
-                               c.P[P_UOUT_B], sqrtf(2.0f * OSD_E), L, dfsum, const_cast<float*>(dc.umod()),
-                               G[P_UOUT_W], G[P_UOUT_B], B, s));
-    const float* uw[8] = {c.P[P_UH0_W], c.P[P_UH0_B], c.P[P_UH1_W], c.P[P_UH1_B],
-                          c.P[P_UH3_W], c.P[P_UH3_B], c.P[P_UH4_W], c.P[P_UH4_B]};
-    float* ug[8] = {G[P_UH0_W], G[P_UH0_B], G[P_UH1_W], G[P_UH1_B], G[P_UH3_W], G[P_UH3_B], G[P_UH4_W], G[P_UH4_B]};
+    OSD_TRY(launch_u_final_bwd(du, reinterpret_cast<float*>(c.ws + pl.fsum), c.cond.umod(), c.P[P_UOUT_W + ts],
+                               c.P[P_UOUT_B + ts], sqrtf(2.0f * OSD_E), L, dfsum, const_cast<float*>(dc.umod()),
+                               G[P_UOUT_W + ts], G[P_UOUT_B + ts], B, s));
+    const float* uw[8] = {c.P[P_UH0_W + ts], c.P[P_UH0_B + ts], c.P[P_UH1_W + ts], c.P[P_UH1_B + ts],
+                          c.P[P_UH3_W + ts], c.P[P_UH3_B + ts], c.P[P_UH4_W + ts], c.P[P_UH4_B + ts]};
+    float* ug[8] = {G[P_UH0_W + ts], G[P_UH0_B + ts], G[P_UH1_W + ts], G[P_UH1_B + ts],
+                    G[P_UH3_W + ts], G[P_UH3_B + ts], G[P_UH4_W + ts], G[P_UH4_B + ts]};
     OSD_TRY(launch_u_head_bwd(xt, uw, dfsum, ug, B, L, s));
   }
 
-  for (int l = 7; l >= 0; --l) {
+  for (int l = depth - 1; l >= 0; --l) {
     uint8_t* lb = LB(l);
     const float* x0 = reinterpret_cast<float*>(lb + pl.x0);
     const float* x1 = reinterpret_cast<float*>(lb + pl.x1);
@@ -425,14 +434,14 @@ static int pred_backward(const FwdCtx& c, const float* audio, const float* style
   // ---- conditioning vectors (fp32, tiny)
   float* dcg = dcond;  // [B,512]
   float* scratch = reinterpret_cast<float*>(bw + bp.dpre_s);
-  for (int l = 0; l < 8; ++l) {
+  for (int l = 0; l < depth; ++l) {
     OSD_TRY(launch_linear_small_bwd(dc.mod1(l), nullptr, c.cond.cg(), c.P[lp(l, L_SSG1_W)], G[lp(l, L_SSG1_W)],
                                     G[lp(l, L_SSG1_B)], dcg, nullptr, B, 1536, 512, 0, s));
     OSD_TRY(launch_linear_small_bwd(dc.mod2(l), nullptr, c.cond.cg(), c.P[lp(l, L_SSG2_W)], G[lp(l, L_SSG2_W)],
                                     G[lp(l, L_SSG2_B)], dcg, nullptr, B, 1536, 512, 0, s));
   }
-  OSD_TRY(launch_linear_small_bwd(dc.umod(), nullptr, c.cond.cg(), c.P[P_UMOD_W], G[P_UMOD_W], G[P_UMOD_B], dcg, nullptr,
-                                  B, 128, 512, 0, s));
+  OSD_TRY(launch_linear_small_bwd(dc.umod(), nullptr, c.cond.cg(), c.P[P_UMOD_W + ts], G[P_UMOD_W + ts], G[P_UMOD_B + ts],
+                                  dcg, nullptr, B, 128, 512, 0, s));
   // cg = silu(pre_s): recompute the pre-activation, then the layer's own gradients
   float* pre_s = scratch;
   float* dpre_s = scratch + (size_t)B * 512;
@@ -449,20 +458,49 @@ using namespace osd;
 
 extern "C" {
 
-size_t osd_packed_bytes(int mode) { return packed_layout(mode).total; }
-size_t osd_cond_floats(int B) { return CondPack::floats(B); }
-size_t osd_workspace_bytes(int B, int L, int a_batch, int mode, int save) {
-  return make_plan(B, L, a_batch, mode, save).total;
+// every `mode` argument: precision in bits 0-7, backbone depth in bits 8-15 (0 = OSD_DEPTH), see OSD_MODE()
+#define OSD_SPLIT_MODE(fn)                                                                              \
+  const int depth = depth_of(mode);                                                                     \
+  mode = prec_of(mode);                                                                                 \
+  OSD_CHECK(mode == OSD_BF16 || mode == OSD_F32X3, fn ": bad precision %d", mode);                      \
+  OSD_CHECK(depth >= 1 && depth <= OSD_MAX_DEPTH, fn ": depth %d not in 1..%d", depth, OSD_MAX_DEPTH)
+
+static FwdCtx make_ctx(const float* const* params, const void* packed, int mode, int depth, const void* a_tok,
+                       const float* cond, const float* rope, int B, int L, int a_batch, void* workspace, int save) {
+  FwdCtx c;
+  c.P = params;
+  c.W = PackedW{static_cast<const uint8_t*>(packed), packed_layout(mode, depth)};
+  c.mode = mode; c.depth = depth; c.B = B; c.L = L; c.a_batch = a_batch;
+  c.cond = CondPack{cond, B, depth};
+  c.a_tok = a_tok;
+  c.rope = rope;
+  c.ws = static_cast<uint8_t*>(workspace);
+  c.plan = make_plan(B, L, a_batch, mode, save, depth);
+  c.save = save;
+  c.cl_hoisted = nullptr;
+  return c;
 }
-size_t osd_sample_extra_bytes(int B, int L, int a_batch) {
-  // hoisted proj_cl outputs [8][Ta,512] bf16 + v [B,6,L] + u [B] + eta [2]
-  return 8 * al((size_t)a_batch * L * 512 * 4) + al((size_t)B * 6 * L * 4) + al((size_t)B * 4) + 1024;
+
+int osd_num_params(int mode) { return num_params(depth_of(mode)); }
+size_t osd_packed_bytes(int mode) { return packed_layout(prec_of(mode), depth_of(mode)).total; }
+size_t osd_cond_floats(int B) { return CondPack::floats(B, OSD_DEPTH); }
+size_t osd_cond_floats_mode(int B, int mode) { return CondPack::floats(B, depth_of(mode)); }
+size_t osd_workspace_bytes(int B, int L, int a_batch, int mode, int save) {
+  return make_plan(B, L, a_batch, prec_of(mode), save, depth_of(mode)).total;
+}
+static size_t sample_extra_bytes(int B, int L, int a_batch, int depth) {
+  // hoisted proj_cl outputs [depth][Ta,512] bf16 / fp32 + v [B,6,L] + u [B] + eta [2]
+  return depth * al((size_t)a_batch * L * 512 * 4) + al((size_t)B * 6 * L * 4) + al((size_t)B * 4) + 1024;
+}
+size_t osd_sample_extra_bytes(int B, int L, int a_batch) { return sample_extra_bytes(B, L, a_batch, OSD_DEPTH); }
+size_t osd_sample_extra_bytes_mode(int B, int L, int a_batch, int mode) {
+  return sample_extra_bytes(B, L, a_batch, depth_of(mode));
 }
 
 int osd_pack_weights(const float* const* params, void* packed, int mode, void* stream) {
   OSD_CHECK(params && packed, "osd_pack_weights: null argument");
-  OSD_CHECK(mode == OSD_BF16 || mode == OSD_F32X3, "osd_pack_weights: bad mode %d", mode);
-  return pack_weights(params, static_cast<uint8_t*>(packed), mode, static_cast<cudaStream_t>(stream));
+  OSD_SPLIT_MODE("osd_pack_weights");
+  return pack_weights(params, static_cast<uint8_t*>(packed), mode, depth, static_cast<cudaStream_t>(stream));
 }
 
 int osd_precompute_conditioning(const float* const* params, const void* packed, int mode, const float* audio,
@@ -471,9 +509,27 @@ int osd_precompute_conditioning(const float* const* params, const void* packed, 
   OSD_CHECK(params && packed && audio && style && scratch && a_tok && cond,
             "osd_precompute_conditioning: null argument");
   OSD_CHECK(a_batch == B || a_batch == 1, "osd_precompute_conditioning: audio batch %d must be 1 or B=%d", a_batch, B);
-  PackedW W{static_cast<const uint8_t*>(packed), packed_layout(mode)};
-  return precompute_conditioning(params, W, mode, audio, a_batch, style, B, L, a_tok, cond, scratch,
+  OSD_SPLIT_MODE("osd_precompute_conditioning");
+  PackedW W{static_cast<const uint8_t*>(packed), packed_layout(mode, depth)};
+  return precompute_conditioning(params, W, mode, depth, audio, a_batch, style, B, L, a_tok, cond, scratch,
                                  static_cast<cudaStream_t>(stream));
+}
+
+// The (a, cg) pair of DiffusionModel._pred (model.py:86-103) given as the reference passes it -- a [a_batch,128,L] and
+// cg [B,512], fp32 channels-first -- turned into what osd_pred_forward consumes: a_tok (token-major operand, (hi | lo)
+// pairs in the fp32-grade mode) and the cond pack (cg | modulation vectors of every layer | u_mod).
+int osd_conditioning_from(const float* const* params, int mode, const float* a, int a_batch, const float* cg, int B, int L,
+                          void* a_tok, float* cond, void* stream) {
+  OSD_CHECK(params && a && cg && a_tok && cond, "osd_conditioning_from: null argument");
+  OSD_CHECK(a_batch == B || a_batch == 1, "osd_conditioning_from: audio batch %d must be 1 or B=%d", a_batch, B);
+  OSD_SPLIT_MODE("osd_conditioning_from");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (mode == OSD_F32X3)
+    OSD_TRY(launch_cf_to_tm_split(a, a_tok, a_batch, 128, L, s));
+  else
+    OSD_TRY(launch_cf_to_tm(a, a_tok, 1, a_batch, 128, L, s));
+  if (cg != cond) OSD_CUDA(cudaMemcpyAsync(cond, cg, (size_t)B * 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return modulation_from_cg(params, depth, cond, B, s);
 }
 
 int osd_tokens_to_channels(const void* in, int in_fp32, float* out, int B, int C, int L, void* stream) {
@@ -487,17 +543,8 @@ int osd_pred_forward(const float* const* params, const void* packed, int mode, c
                      const float* rope, const float* xt, float* u, float* v, int B, int L, int a_batch,
                      void* workspace, int save, void* stream) {
   OSD_CHECK(params && packed && a_tok && cond && rope && xt && u && v && workspace, "osd_pred_forward: null argument");
-  FwdCtx c;
-  c.P = params;
-  c.W = PackedW{static_cast<const uint8_t*>(packed), packed_layout(mode)};
-  c.mode = mode; c.B = B; c.L = L; c.a_batch = a_batch;
-  c.cond = CondPack{cond, B};
-  c.a_tok = a_tok;
-  c.rope = rope;
-  c.ws = static_cast<uint8_t*>(workspace);
-  c.plan = make_plan(B, L, a_batch, mode, save);
-  c.save = save;
-  c.cl_hoisted = nullptr;
+  OSD_SPLIT_MODE("osd_pred_forward");
+  const FwdCtx c = make_ctx(params, packed, mode, depth, a_tok, cond, rope, B, L, a_batch, workspace, save);
   return pred_forward(c, xt, u, v, static_cast<cudaStream_t>(stream));
 }
 
@@ -509,24 +556,16 @@ int osd_sample(const float* const* params, const void* packed, int mode, const v
   OSD_CHECK(params && packed && a_tok && cond && rope && x && workspace && extra, "osd_sample: null argument");
   OSD_CHECK(num_steps >= 1, "osd_sample: num_steps must be >= 1");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  FwdCtx c;
-  c.P = params;
-  c.W = PackedW{static_cast<const uint8_t*>(packed), packed_layout(mode)};
-  c.mode = mode; c.B = B; c.L = L; c.a_batch = a_batch;
-  c.cond = CondPack{cond, B};
-  c.a_tok = a_tok;
-  c.rope = rope;
-  c.ws = static_cast<uint8_t*>(workspace);
-  c.plan = make_plan(B, L, a_batch, mode, 0);
-  c.save = 0;
+  OSD_SPLIT_MODE("osd_sample");
+  FwdCtx c = make_ctx(params, packed, mode, depth, a_tok, cond, rope, B, L, a_batch, workspace, 0);
   uint8_t* ex = static_cast<uint8_t*>(extra);
   const int Ta = a_batch * L;
   const size_t cl_bytes = al((size_t)Ta * 512 * (mode == OSD_F32X3 ? 4 : 2));
-  for (int l = 0; l < 8; ++l) OSD_TRY(proj_cl(params, c.W, mode, l, a_tok, Ta, ex + l * cl_bytes, s));
+  for (int l = 0; l < depth; ++l) OSD_TRY(proj_cl(params, c.W, mode, l, a_tok, Ta, ex + l * cl_bytes, s));
   c.cl_hoisted = ex;
-  float* v = reinterpret_cast<float*>(ex + 8 * cl_bytes);
-  float* u = reinterpret_cast<float*>(ex + 8 * cl_bytes + al((size_t)B * 6 * L * 4));
-  float* eta = reinterpret_cast<float*>(ex + 8 * cl_bytes + al((size_t)B * 6 * L * 4) + al((size_t)B * 4));
+  float* v = reinterpret_cast<float*>(ex + depth * cl_bytes);
+  float* u = reinterpret_cast<float*>(ex + depth * cl_bytes + al((size_t)B * 6 * L * 4));
+  float* eta = reinterpret_cast<float*>(ex + depth * cl_bytes + al((size_t)B * 6 * L * 4) + al((size_t)B * 4));
   OSD_TRY(pred_forward(c, x, u, v, s));
   OSD_TRY(launch_sample_eta(u, B, sqrtf(c0), num_steps, eta, s));
   for (int i = 0; i < num_steps; ++i) {
@@ -539,7 +578,7 @@ int osd_sample(const float* const* params, const void* packed, int mode, const v
 }
 
 
-size_t osd_backward_workspace_bytes(int B, int L, int a_batch) { return make_bwd_plan(B, L, a_batch).total; }
+size_t osd_backward_workspace_bytes(int B, int L, int a_batch) { return make_bwd_plan(B, L, a_batch, OSD_MAX_DEPTH).total; }
 
 // Gradient of osd_pred_forward(save=1) composed with osd_precompute_conditioning: given du [B], dv [B,6,L]
 // ACCUMULATES d(loss)/d(parameter) into grads[164] (fp32, parameter shapes, caller zero-initialised or
@@ -551,17 +590,8 @@ int osd_pred_backward(const float* const* params, const void* packed, int mode, 
   OSD_CHECK(params && packed && a_tok && cond && rope && audio && style && xt && du && dv && grads && workspace &&
                 bwd_workspace,
             "osd_pred_backward: null argument");
-  FwdCtx c;
-  c.P = params;
-  c.W = PackedW{static_cast<const uint8_t*>(packed), packed_layout(mode)};
-  c.mode = mode; c.B = B; c.L = L; c.a_batch = a_batch;
-  c.cond = CondPack{cond, B};
-  c.a_tok = a_tok;
-  c.rope = rope;
-  c.ws = static_cast<uint8_t*>(workspace);
-  c.plan = make_plan(B, L, a_batch, mode, 1);
-  c.save = 1;
-  c.cl_hoisted = nullptr;
+  OSD_SPLIT_MODE("osd_pred_backward");
+  const FwdCtx c = make_ctx(params, packed, mode, depth, a_tok, cond, rope, B, L, a_batch, workspace, 1);
   return pred_backward(c, audio, style, xt, du, dv, grads, static_cast<uint8_t*>(bwd_workspace),
                        static_cast<cudaStream_t>(stream));
 }
@@ -574,7 +604,6 @@ int osd_attn_bwd(const void* qkv, const void* y, const void* dy, const float* ls
 // debugging aid (tools/trace_attn_bwd.py): event timeline of one CTA of the single-pass kernel; buf = device
 // buffer of 3 x 1024 u64 records, or null to switch tracing off
 void osd_debug_attn_bwd_trace(unsigned long long* buf, int cta) { attn_bwd_fused_set_trace(buf, cta); }
-void osd_debug_attn_fwd_trace(unsigned long long* buf, int cta) { attn_fwd_w8_set_trace(buf, cta); }
 
 size_t osd_attn_bwd_fused_stats_floats(int B, int L, int H) { return attn_bwd_fused_stats_floats(B, L, H); }
 

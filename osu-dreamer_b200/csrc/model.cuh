@@ -16,6 +16,12 @@ enum {
   P_COUNT = 164
 };
 inline int lp(int layer, int which) { return P_LAYER0 + layer * P_LAYER_STRIDE + which; }
+// `mode` arguments of the C ABI: bits 0-7 precision (OSD_BF16 / OSD_F32X3), bits 8-15 backbone depth (0 = OSD_DEPTH);
+// the tail tensors (proj_out ... u_out) follow the last layer: P_OUT_W + tail_shift(depth)
+inline int prec_of(int mode) { return mode & 0xff; }
+inline int depth_of(int mode) { const int d = (mode >> 8) & 0xff; return d ? d : OSD_DEPTH; }
+inline int tail_shift(int depth) { return (depth - OSD_DEPTH) * P_LAYER_STRIDE; }
+inline int num_params(int depth) { return P_COUNT + tail_shift(depth); }
 
 // ---- packed operand weights (bf16 or fp32-for-tf32), one buffer ----
 struct PackedLayout {
@@ -24,11 +30,11 @@ struct PackedLayout {
   size_t wa;   // [128,128]
   size_t layer0, layer_stride;
   size_t l_cl, l_qkv, l_out, l_vg, l_po;  // offsets inside a layer block (bytes)
-  size_t bvg;                             // fp32 [8][2816]
-  size_t bounds;                          // fp32 [8] attention score bounds (log2 units) per layer
+  size_t bvg;                             // fp32 [depth][2816]
+  size_t bounds;                          // fp32 [depth] attention score bounds (log2 units) per layer
   size_t total;
 };
-PackedLayout packed_layout(int mode);
+PackedLayout packed_layout(int mode, int depth);
 
 struct PackedW {
   const uint8_t* base;
@@ -43,15 +49,16 @@ struct PackedW {
   const float* bvg(int l) const { return reinterpret_cast<const float*>(base + lay.bvg) + (size_t)l * 2 * OSD_HIDP; }
 };
 
-// ---- conditioning pack (fp32): cg [B,512] | mod1 [8][B,1536] | mod2 [8][B,1536] | umod [B,128] ----
+// ---- conditioning pack (fp32): cg [B,512] | mod1 [depth][B,1536] | mod2 [depth][B,1536] | umod [B,128] ----
 struct CondPack {
   const float* base;
   int B;
+  int depth;
   const float* cg() const { return base; }
   const float* mod1(int l) const { return base + (size_t)B * 512 + (size_t)l * B * 1536; }
-  const float* mod2(int l) const { return base + (size_t)B * 512 + (size_t)(8 + l) * B * 1536; }
-  const float* umod() const { return base + (size_t)B * 512 + (size_t)16 * B * 1536; }
-  static size_t floats(int B) { return (size_t)B * (512 + 16 * 1536 + 128); }
+  const float* mod2(int l) const { return base + (size_t)B * 512 + (size_t)(depth + l) * B * 1536; }
+  const float* umod() const { return base + (size_t)B * 512 + (size_t)2 * depth * B * 1536; }
+  static size_t floats(int B, int depth) { return (size_t)B * (512 + (size_t)2 * depth * 1536 + 128); }
 };
 
 // ---- activation plan: per-layer buffers; layer stride 0 (inference, buffers reused) or >0 (training saves) ----
@@ -66,6 +73,6 @@ struct ActPlan {
   size_t uh1, uh2;      // fp32 [T,64] u-head saves (training only)
   size_t total;
 };
-ActPlan make_plan(int B, int L, int a_batch, int mode, int save);
+ActPlan make_plan(int B, int L, int a_batch, int mode, int save, int depth);
 
 }  // namespace osd

@@ -253,10 +253,9 @@ int launch_u_head_bwd(const float* xt, const float* const* w8, const float* dfsu
   UHeadW w{w8[0], w8[1], w8[2], w8[3], w8[4], w8[5], w8[6], w8[7]};
   UHeadG g{g8[0], g8[1], g8[2], g8[3], g8[4], g8[5], g8[6], g8[7]};
   const int smem = (38 * 6 + 36 * 6 + 36 * 64 + 3 * 34 * 64 + 32 * 64 + 32 * 6 + 64 * 65) * 4;
-  static bool set = false;
-  if (!set) {
+  static DeviceOnce once;
+  if (once.first()) {
     OSD_CUDA(cudaFuncSetAttribute(u_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = true;
   }
   dim3 grid(ceil_div(L, UB_TOK * UB_SUB), B);
   u_head_bwd_kernel<<<grid, 256, smem, s>>>(xt, w, dfsum, g, L);

@@ -20,6 +20,16 @@ _lib = None
 
 BF16, TF32 = 0, 1   # operand element kinds of osd_gemm
 MODE_BF16, MODE_F32X3 = 0, 1  # model precision modes (include/osd_b200.h)
+DEFAULT_DEPTH, MAX_DEPTH = 8, 32
+
+
+def mode_of(precision: int, depth: int = DEFAULT_DEPTH) -> int:
+    """OSD_MODE(precision, depth): every `mode` argument of the C ABI carries the backbone depth in bits 8-15."""
+    return precision | (depth << 8)
+
+
+def depth_of(mode: int) -> int:
+    return ((mode >> 8) & 0xff) or DEFAULT_DEPTH
 MAJOR_K, MAJOR_MN = 0, 1
 EPI_STORE, EPI_SILU, EPI_ATOMIC = 0, 1, 2
 
@@ -55,10 +65,14 @@ def ptr(t):
         return c_void_p(0)
     if not t.is_cuda:
         raise OsdError('libosd_b200 has no CPU path: tensor must live on a CUDA device')
+    if t.device.index != torch.cuda.current_device():
+        raise OsdError(f'tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()}: the work would be '
+                       f'enqueued on the wrong device\'s stream (wrap the call in `with torch.cuda.device(t.device)`)')
     return c_void_p(t.data_ptr())
 
 
 def stream():
+    """torch's current stream on the CURRENT device: tensors handed to the library must live there (see `ptr`)."""
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -117,27 +131,32 @@ def packed_bytes(mode):
     return _sz('osd_packed_bytes', mode)
 
 
-def cond_floats(B):
-    return _sz('osd_cond_floats', B)
+def cond_floats(B, mode=0):
+    return _sz('osd_cond_floats_mode', B, mode)
+
+
+def num_params(mode=0):
+    return 20 + 18 * depth_of(mode)
 
 
 def workspace_bytes(B, L, a_batch, mode, save):
     return _sz('osd_workspace_bytes', B, L, a_batch, mode, save)
 
 
-def sample_extra_bytes(B, L, a_batch):
-    return _sz('osd_sample_extra_bytes', B, L, a_batch)
+def sample_extra_bytes(B, L, a_batch, mode=0):
+    return _sz('osd_sample_extra_bytes_mode', B, L, a_batch, mode)
 
 
 def param_array(tensors):
-    """HOST array of device pointers, reference state-dict order."""
-    assert len(tensors) == NUM_PARAMS, len(tensors)
+    """HOST array of device pointers, reference state-dict order (20 + 18 * depth tensors)."""
+    if (len(tensors) - 20) % 18 or not 1 <= (len(tensors) - 20) // 18 <= MAX_DEPTH:
+        raise OsdError(f'{len(tensors)} parameter tensors: expected 20 + 18 * depth')
     for t in tensors:
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise OsdError('parameters must be contiguous fp32 CUDA tensors (no CPU path)')
         if t.data_ptr() % 16:
             raise OsdError('parameter storage must be 16-byte aligned (vector loads)')
-    return (c_void_p * NUM_PARAMS)(*[t.data_ptr() for t in tensors])
+    return (c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
 def attn_fwd(qkv, B, L, H=16, want_lse=True, bound_log2=None, variant=7):
@@ -158,6 +177,12 @@ def precompute_conditioning(parr, packed, mode, audio, style, scratch, a_tok, co
     B = style.shape[0]
     _check(load().osd_precompute_conditioning(parr, ptr(packed), c_int(mode), ptr(audio), c_int(a_batch), ptr(style),
                                               c_int(B), c_int(L), ptr(scratch), ptr(a_tok), ptr(cond), stream()))
+
+
+def conditioning_from(parr, mode, a, cg, L, a_tok, cond):
+    """(a [#B,128,L], cg [B,512]) as DiffusionModel._pred receives them -> (a_tok, cond pack) for pred_forward."""
+    _check(load().osd_conditioning_from(parr, c_int(mode), ptr(a), c_int(a.shape[0]), ptr(cg), c_int(cg.shape[0]),
+                                        c_int(L), ptr(a_tok), ptr(cond), stream()))
 
 
 def pred_forward(parr, packed, mode, a_tok, cond, rope, xt, u, v, a_batch, workspace, save):
@@ -193,11 +218,10 @@ def backward_workspace_bytes(B, L, a_batch):
 
 
 def grad_array(tensors):
-    assert len(tensors) == NUM_PARAMS
     for t in tensors:
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()) or t.data_ptr() % 16:
             raise OsdError('gradient buffers must be contiguous, 16-byte aligned fp32 CUDA tensors')
-    return (c_void_p * NUM_PARAMS)(*[t.data_ptr() for t in tensors])
+    return (c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
 def pred_backward(parr, packed, mode, a_tok, cond, rope, audio, style, xt, du, dv, garr, a_batch, workspace, bwd_ws):

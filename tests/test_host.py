@@ -49,8 +49,14 @@ def test_deepcopy_and_pickle_free_runtime():
 
 def test_args_validation():
     from osu_dreamer_b200.denoiser import DiffusionModel, DiffusionModelArgs, BackboneArgs
+    with pytest.raises(ValueError):  # the widths are compile-time constants of the kernels ...
+        DiffusionModel(6, 128, 32, DiffusionModelArgs(512, 256, BackboneArgs(depth=8, expand=4, head_dim=64, n_heads=16, radius=2)))
     with pytest.raises(ValueError):
-        DiffusionModel(6, 128, 32, DiffusionModelArgs(512, 512, BackboneArgs(depth=4, expand=4, head_dim=64, n_heads=16, radius=2)))
+        DiffusionModel(6, 128, 32, DiffusionModelArgs(512, 512, BackboneArgs(depth=8, expand=4, head_dim=64, n_heads=8, radius=2)))
+    # ... the depth is a run-time argument of the C ABI: 20 + 18 * depth tensors in the reference's registration order
+    m4 = DiffusionModel(6, 128, 32, DiffusionModelArgs(512, 512, BackboneArgs(depth=4, expand=4, head_dim=64, n_heads=16, radius=2)))
+    assert len(m4.state_dict()) == 20 + 18 * 4 and 'net.layers.3.ffn.proj_o.bias' in m4.state_dict()
+    assert 'net.layers.4.ssg1.weight' not in m4.state_dict() and m4._mode() == (4 << 8)
     # dict-shaped args as produced by models/inference/artifact.py:52-71 dataclass_from_dict on older ckpts
     DiffusionModel(6, 128, 32, DiffusionModelArgs(512, 512, dict(depth=8, expand=4, head_dim=64, n_heads=16, radius=2)))
 
