@@ -68,26 +68,64 @@ def _plain(x):
     return x
 
 
-def save_checkpoint(path: str, tr: DiffusionTrainer, epoch: int):
+def save_checkpoint(path: str, tr: DiffusionTrainer, epoch: int, best: float | None = None):
     """Lightning-shaped checkpoint (`state_dict` with the reference's keys diffusion.* / diffusion_ema.module.* /
     diffusion_ema.n_averaged, `hyper_parameters`, `global_step`, `epoch`): what the reference's export-inference
-    reads (models/inference/artifact.py:15-35).  Plain tensors / dicts only."""
+    reads (models/inference/artifact.py:15-35).  Plain tensors / dicts only.  `best_model_score` is what Lightning's
+    ModelCheckpoint restores on resume (model.yml:15-21); `optimizer_state` carries the AdamW moments and their own
+    step counter."""
     torch.save({'state_dict': {k: v.detach().cpu() for k, v in tr.state_dict().items()},
                 'hyper_parameters': _plain(dict(tr.hparams)),
-                'global_step': tr.global_step, 'epoch': epoch,
-                'optimizer_state': {k: tr._opt[k].cpu() for k in ('m', 'v')} if tr._opt else None}, path)
+                'global_step': tr.global_step, 'epoch': epoch, 'best_model_score': best,
+                'optimizer_state': ({'m': tr._opt['m'].cpu(), 'v': tr._opt['v'].cpu(), 'step': tr.adam_step}
+                                    if tr._opt else None)}, path)
 
 
 def load_checkpoint(path: str, tr: DiffusionTrainer):
-    """resume: weights + EMA (+ AdamW moments and the step count when the checkpoint carries them; a checkpoint
-    written by the reference's Lightning run restores weights, EMA and the step)."""
+    """resume: weights + EMA + the LR-schedule step; the AdamW moments and THEIR step count when the checkpoint carries
+    them.  A checkpoint written by the reference's Lightning run has no `optimizer_state` in this shape: the moments then
+    restart at zero and so does the bias-correction step (`tr.adam_step = 0`), exactly like a fresh torch AdamW -- with
+    the bias corrections taken at `global_step` instead, the first update would be (1-b1) g / sqrt((1-b2) g^2) ~ 3.2x a
+    normal Adam step at full learning rate.  Returns the checkpoint dict (`epoch`, `best_model_score` for the loop)."""
     ck = torch.load(path, map_location='cpu', weights_only=False)
     tr.load_state_dict(ck['state_dict'])
     tr.global_step = int(ck.get('global_step', 0))
     opt = ck.get('optimizer_state')
     if opt is not None:
         tr._opt = {'m': opt['m'].clone(), 'v': opt['v'].clone()}  # adopted by configure_optimizers when sizes match
+        tr.adam_step = int(opt.get('step', tr.global_step))
+    else:
+        tr._opt = None
+        tr.adam_step = 0
     return ck
+
+
+_TRAINER_KEYS_HONOURED = {'gradient_clip_val', 'log_every_n_steps', 'max_epochs'}
+_TRAINER_KEYS_NEUTRAL = {'accelerator', 'devices', 'logger', 'callbacks', 'enable_progress_bar', 'default_root_dir', 'strategy',
+                         'num_nodes', 'enable_checkpointing', 'enable_model_summary', 'num_sanity_val_steps'}
+_OPT_KEYS_HONOURED = {'lr', 'betas', 'eps', 'weight_decay'}
+
+
+def check_config(cfg: dict) -> list[str]:
+    """Reference config keys this loop does not implement must not pass silently: settings that would change the
+    arithmetic raise, the rest are reported.  -> list of warnings"""
+    warns = []
+    t = cfg.get('trainer') or {}
+    if int(t.get('accumulate_grad_batches', 1) or 1) != 1:
+        raise click.ClickException('trainer.accumulate_grad_batches != 1 is not implemented (model.yml uses 1)')
+    prec = str(t.get('precision', 'bf16-mixed'))
+    if prec not in ('bf16-mixed', 'bf16', 'bf16-true'):
+        raise click.ClickException(f'trainer.precision={prec!r}: training runs with bf16 tensor-core operands (fp32 accumulate, '
+                                   'residual and statistics) -- the reference\'s bf16-mixed (model.yml:38)')
+    for k in t:
+        if k not in _TRAINER_KEYS_HONOURED | _TRAINER_KEYS_NEUTRAL | {'accumulate_grad_batches', 'precision'}:
+            warns.append(f'trainer.{k} is ignored by this loop')
+    for k, v in ((cfg.get('model') or {}).get('opt_args') or {}).items():
+        if k not in _OPT_KEYS_HONOURED:
+            if k == 'amsgrad' and not v:
+                continue
+            raise click.ClickException(f'model.opt_args.{k}={v!r} is not implemented by the fused AdamW (lr, betas, eps, weight_decay)')
+    return warns
 
 
 def save_inference(latent_ckpt_path: str, denoiser_ckpt_path: str, style_ckpt_path: str, output_path: str):
@@ -124,6 +162,8 @@ def export_inference(latent_ckpt_path: str, denoiser_ckpt_path: str, style_ckpt_
 def fit_denoiser(config: str, ckpt_path: str | None, synthetic: bool, max_steps: int | None, out: str):
     """begin a training run for the diffusion model."""
     cfg = yaml.safe_load(open(config))
+    for w in check_config(cfg):
+        print('warning:', w, file=sys.stderr)
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -137,8 +177,14 @@ def fit_denoiser(config: str, ckpt_path: str | None, synthetic: bool, max_steps:
     seed = cfg.get('seed_everything', True)
     torch.manual_seed((0 if seed is True else int(seed)) + rank)
     tr = build_trainer(cfg)
+    first_epoch, best = 0, float('inf')
     if ckpt_path:
-        load_checkpoint(ckpt_path, tr)
+        ck = load_checkpoint(ckpt_path, tr)
+        # resume AFTER the stored epoch (its window order, seeded by the epoch number, was already trained on) and keep the
+        # best validation loss, so a worse first validation does not overwrite the kept checkpoint
+        first_epoch = int(ck.get('epoch', -1)) + 1
+        if ck.get('best_model_score') is not None:
+            best = float(ck['best_model_score'])
     else:  # every rank starts from rank 0's initialisation
         tr.diffusion_ema.module.load_state_dict(tr.diffusion.state_dict())
     tr = tr.cuda()
@@ -152,20 +198,21 @@ def fit_denoiser(config: str, ckpt_path: str | None, synthetic: bool, max_steps:
     max_epochs = int(tcfg.get('max_epochs', -1))
     if synthetic:
         def epochs():
-            yield synthetic_batches(d['batch_size'], d['seq_len'], seed=rank)
+            yield first_epoch, synthetic_batches(d['batch_size'], d['seq_len'], seed=rank + 7919 * first_epoch)
         val_sets = None
     else:
         train_sets, val_sets = split_mapsets(Path(d.get('data_path', './data')), '*.latent.npz',
                                              d.get('max_val_count', 512), d.get('max_val_frac', .3))
         def epochs():
-            e = 0
+            e = first_epoch
             while max_epochs < 0 or e < max_epochs:
-                yield DeviceFeeder(LatentWindows(train_sets, d['seq_len'], d.get('shuffle_buffer_size', 1),
+                yield e, DeviceFeeder(LatentWindows(train_sets, d['seq_len'], d.get('shuffle_buffer_size', 1),
                                                  d.get('max_per_map', -1), seed=e), d['batch_size'], rank, world,
                                    device=torch.device('cuda', local))
                 e += 1
-    t0, best = time.time(), float('inf')
-    for epoch, it in enumerate(epochs()):
+    t0 = time.time()
+    epoch = first_epoch
+    for epoch, it in epochs():
         for batch in it:
             batch = tuple(t.cuda(non_blocking=True) for t in batch)
             loss, log = tr.training_step(batch, world_size=world)
@@ -174,19 +221,27 @@ def fit_denoiser(config: str, ckpt_path: str | None, synthetic: bool, max_steps:
                       ' '.join(f'train/{k} {float(v):.4f}' for k, v in log.items()) + f' [{time.time() - t0:.0f}s]', flush=True)
             if max_steps is not None and tr.global_step >= max_steps:
                 break
-        if rank == 0 and val_sets:
-            vals = []
-            for vb in LatentWindows(val_sets, None):
-                vals.append(tr.validation_step(tuple(t[None].cuda() for t in vb)))
-            vl = sum(float(v['val/loss']) for v in vals) / max(1, len(vals))
-            print(f'epoch {epoch} val/loss {vl:.4f}', flush=True)
-            if vl < best:  # ModelCheckpoint(monitor=val/loss, mode=min, save_top_k=1), model.yml:15-21
-                best = vl
-                save_checkpoint(out, tr, epoch)
+        if val_sets:
+            # validation maps are sharded over the ranks (map i on rank i mod world) and the sums all-reduced: no rank waits
+            # in the next epoch's gradient all-reduce while another validates, and every rank's generator advances alike
+            acc = torch.zeros(2, dtype=torch.float64, device='cuda')
+            for i, vb in enumerate(LatentWindows(val_sets, None)):
+                if i % world == rank:
+                    acc[0] += float(tr.validation_step(tuple(t[None].cuda() for t in vb))['val/loss'])
+                    acc[1] += 1
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(acc)
+            vl = float(acc[0]) / max(1.0, float(acc[1]))
+            if rank == 0:
+                print(f'epoch {epoch} val/loss {vl:.4f}', flush=True)
+                if vl < best:  # ModelCheckpoint(monitor=val/loss, mode=min, save_top_k=1), model.yml:15-21
+                    save_checkpoint(out, tr, epoch, vl)
+            best = min(best, vl)
         if max_steps is not None and tr.global_step >= max_steps:
             break
     if rank == 0 and (not val_sets or not os.path.exists(out)):
-        save_checkpoint(out, tr, epoch)
+        save_checkpoint(out, tr, epoch, best if best < float('inf') else None)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -80,7 +80,10 @@ class StyleModel(nn.Module):
         ts = self._tensors()
         if any(not t.is_cuda for t in ts):
             raise lib.OsdError('StyleModel tensors must be on a CUDA device: libosd_b200 has no CPU path')
-        return lib.style_param_array([t.detach().float().contiguous() for t in ts]), ts
+        # the converted tensors (copies when a parameter is not already contiguous fp32, e.g. after .half()) must outlive
+        # the enqueued kernels: the caller keeps the returned list until its library call has been issued
+        conv = [t.detach().float().contiguous() for t in ts]
+        return lib.style_param_array(conv), conv
 
     def forward(self, st: Tensor, labels: Tensor):
         """model.py:81-99 -> (u [B], v [B,S]); inference only."""

@@ -129,7 +129,9 @@ class DiffusionTrainer(nn.Module):
         self.gradient_clip_val = gradient_clip_val  # trainer.gradient_clip_val in model.yml:39
         self.diffusion = DiffusionModel(emb_dim, a_dim, style_dim, diffusion_args)
         self.diffusion_ema = _EMA(self.diffusion)
-        self.global_step = 0
+        self.global_step = 0  # optimizer steps taken: drives the LR schedule (Lightning's global_step)
+        self.adam_step = 0    # steps the AdamW moments have seen: drives the bias corrections; differs from global_step after
+        #                       resuming from a checkpoint without optimizer state (cli.load_checkpoint)
         self._opt = None  # lazily built flat optimizer state
         self._ema_updates = None
 
@@ -178,7 +180,7 @@ class DiffusionTrainer(nn.Module):
                 k = p.numel()
                 targets.append(o['g'][off:off + k].view(p.shape))
                 off += _pad64(k)
-            self.diffusion._grad_targets = targets
+            o['targets'] = targets  # handed to the model only for the duration of training_step (direct-gradient mode)
         if not _is_flat(ema_params, o.get('ema')):
             o['ema'] = _flatten(ema_params)
         self._opt = o
@@ -203,23 +205,31 @@ class DiffusionTrainer(nn.Module):
         betas = self.opt_args.get('betas', (0.9, 0.999))
         if self._ema_updates is None:  # one-time host read (e.g. after loading a checkpoint)
             self._ema_updates = int(self.diffusion_ema.n_averaged.item())
-        lib.adamw_ema_step(o['p'], o['g'], o['m'], o['v'], o['ema'], self.global_step + 1, self.current_lr(), betas[0],
+        lib.adamw_ema_step(o['p'], o['g'], o['m'], o['v'], o['ema'], self.adam_step + 1, self.current_lr(), betas[0],
                            betas[1], self.opt_args.get('eps', 1e-8), self.opt_args.get('weight_decay', 1e-2),
                            self.gradient_clip_val or 0.0, 1.0 / world_size, 0.99, self._ema_updates == 0,
                            o['acc'], o['scal'])
         self._ema_updates += 1
         self.diffusion_ema.n_averaged += 1
         self.global_step += 1
+        self.adam_step += 1
         # parameters changed in place through the flat buffer: invalidate the packed operand copies
         self.diffusion._rt.key = None
         self.diffusion_ema.module._rt.key = None
 
     def training_step(self, batch, batch_idx: int = 0, world_size: int = 1):
         """train.py:120-126 + the Lightning loop body around it (model.yml: clip 1.0, accumulate 1)."""
-        self.configure_optimizers()
+        o = self.configure_optimizers()
         self.zero_grad()
-        loss, log = self(self.diffusion, *batch)
-        loss.backward()
+        # direct-gradient mode, scoped to this call: the backward of `diffusion` accumulates straight into the flat buffer and
+        # autograd sees no parameter gradients; any other autograd user of the module (torch.autograd.grad, .grad readers)
+        # gets ordinary gradients
+        self.diffusion._grad_targets = o['targets']
+        try:
+            loss, log = self(self.diffusion, *batch)
+            loss.backward()
+        finally:
+            self.diffusion._grad_targets = None
         self.optimizer_step(world_size)
         return loss.detach(), log
 
