@@ -215,7 +215,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    base = cpu_train_baseline(budget_s=150.0, iters=max(1, args.steps), warmup=max(0, min(args.warmup, 1)))
+    base = cpu_train_baseline(budget_s=100.0, iters=max(1, args.steps), warmup=max(0, min(args.warmup, 1)))
     value = base['value']
     threads = base['cores']
     # extrapolation check: a measured no_grad forward at L = 8192 vs the F_fwd-scaled L = 512 one
@@ -234,7 +234,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'samples/s',
         'n_gpus': args.gpus, 'steps': base['steps_run'], 'warmup': base['warmup_run'],
         'requested': {'steps': args.steps, 'warmup': args.warmup,
-                      'note': 'timed steps stop at a 150 s budget (one CPU step at seq_len 8192 takes tens of seconds); '
+                      'note': 'timed steps stop at a 100 s budget (one CPU step at seq_len 8192 takes tens of seconds); '
                               '`steps` / `warmup` are what actually ran'},
         'ms_per_step': base['seconds_per_step'] * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
