@@ -217,6 +217,22 @@ OSD_API int osd_style_forward(const float* const* params, const float* st, const
 OSD_API int osd_style_sample(const float* const* params, const float* labels, float* s_inout, int num_steps,
                              float* scratch, float* eta_u0_out, int B, void* stream);
 
+/* ---- style model training: `fit-style` (osu_dreamer/models/style/train.py:48-109, scripts/fit_style.py).  Exact fp32 on the
+ * CUDA cores: 18 GFLOP per step at batch 512 is launch latency, not throughput.
+ * osd_style_train_forward = StyleModel.forward (model.py:81-99) keeping its activations in `workspace`
+ * (osd_style_train_workspace_floats(B) floats); osd_style_loss = the distance-marching loss of StyleTrainer.forward
+ * (train.py:70-88): out4 = {loss, osl, del, u_mape} and the gradients du [B], dv [B,32] (acc_scratch: 4 floats);
+ * osd_style_backward = what autograd computes for that forward: given du, dv it ACCUMULATES into grads[60] (HOST array of
+ * DEVICE fp32 pointers, parameter shapes, reference state-dict order; entries 3 and 4 -- the Fourier-feature buffers --
+ * are not touched and may be NULL).  labels < 0 select the null embedding (label dropping is the caller's draw). */
+OSD_API size_t osd_style_train_workspace_floats(int B);
+OSD_API int osd_style_train_forward(const float* const* params, const float* st, const float* labels, float* u, float* v,
+                                    float* workspace, int B, void* stream);
+OSD_API int osd_style_loss(const float* st, const float* s1, const float* u_pred, const float* v_pred, float osl_weight,
+                           float del_weight, float* out4, float* du, float* dv, float* acc_scratch, int B, void* stream);
+OSD_API int osd_style_backward(const float* const* params, const float* st, const float* labels, const float* du,
+                               const float* dv, float* const* grads, float* workspace, int B, void* stream);
+
 /* Gradient of DiffusionModel.forward (what autograd computes for the reference at train.py:84 + Lightning's
  * backward): given du [B] and dv [B,6,L], ACCUMULATES the parameter gradients into grads[164] (HOST array of
  * DEVICE fp32 pointers, parameter shapes).  `workspace` is the save=1 workspace the forward filled;

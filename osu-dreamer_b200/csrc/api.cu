@@ -69,6 +69,21 @@ int osd_style_sample(const float* const* params, const float* labels, float* s_i
   return launch_style_sample(params, labels, s_inout, num_steps, scratch, eta_u0_out, B, static_cast<cudaStream_t>(stream));
 }
 
+size_t osd_style_train_workspace_floats(int B) { return style_train_workspace_floats(B); }
+int osd_style_train_forward(const float* const* params, const float* st, const float* labels, float* u, float* v, float* workspace,
+                            int B, void* stream) {
+  return launch_style_train_forward(params, st, labels, u, v, workspace, B, static_cast<cudaStream_t>(stream));
+}
+int osd_style_loss(const float* st, const float* s1, const float* u_pred, const float* v_pred, float osl_weight, float del_weight,
+                   float* out4, float* du, float* dv, float* acc_scratch, int B, void* stream) {
+  return launch_style_loss(st, s1, u_pred, v_pred, osl_weight, del_weight, out4, du, dv, acc_scratch, B,
+                           static_cast<cudaStream_t>(stream));
+}
+int osd_style_backward(const float* const* params, const float* st, const float* labels, const float* du, const float* dv,
+                       float* const* grads, float* workspace, int B, void* stream) {
+  return launch_style_backward(params, st, labels, du, dv, grads, workspace, B, static_cast<cudaStream_t>(stream));
+}
+
 int osd_rope_table(const float* inv_freq_host, int L, float* rope, void* stream) {
   return launch_rope_table(inv_freq_host, L, rope, static_cast<cudaStream_t>(stream));
 }

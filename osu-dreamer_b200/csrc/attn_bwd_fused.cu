@@ -94,6 +94,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
   uint64_t* kvt_ready = bars + 11;  // K / V copied into TMEM
   uint64_t* acc_done = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* st_empty = bars + 14;  // [2] -w D statistics of the stage read by all softmax warps (generic-proxy reads vs the
+                                   // next bulk copy into the same stage; also implied by ds_full -> dK -> q_empty, but that
+                                   // chain runs through tcgen05.commit, which compute-sanitizer racecheck cannot follow)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_t = (p.L + 127) / 128;  // kv tiles == q tiles
@@ -123,6 +126,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
     mbar_init(dq_empty, 8);
     mbar_init(kvt_ready, 8);
     mbar_init(acc_done, 1);
+    mbar_init(&st_empty[0], 8);
+    mbar_init(&st_empty[1], 8);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -144,6 +149,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       for (int i = 0; i < n_q; ++i) {
         const int st = i & 1;
         mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_wait(&st_empty[st], ((i >> 1) & 1) ^ 1);
         mbar_expect_tx(&q_full[st], 2 * FT + 512);
         tma_load_3d(sQ + st * FT, &p.tma_qkv, &q_full[st], h * 64, qi * 128, b);
         tma_load_3d(sDO + st * FT, &p.tma_dy, &q_full[st], h * 64, qi * 128, b);
@@ -372,7 +378,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0) {
+        mbar_arrive(ds_full);
+        mbar_arrive(&st_empty[i & 1]);
+      }
       if (trw) FB_TRACE(1 + grp, 5, i);
       if (i > 0) drain_issue(qprev);
       qprev = qt;

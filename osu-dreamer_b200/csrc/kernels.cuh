@@ -21,6 +21,14 @@ int launch_style_forward(const float* const* params, const float* st, const floa
                          int B, cudaStream_t s);
 int launch_style_sample(const float* const* params, const float* labels, float* s_io, int num_steps, float* scratch,
                         float* eta_u0_out, int B, cudaStream_t s);
+// style model training (style_train.cu): forward with saved activations, loss, backward (gradients accumulate into G[60])
+size_t style_train_workspace_floats(int B);
+int launch_style_train_forward(const float* const* params, const float* st, const float* labels, float* u, float* v, float* ws,
+                               int B, cudaStream_t s);
+int launch_style_loss(const float* st, const float* s1, const float* u, const float* v, float osl_w, float del_w, float* out4,
+                      float* du, float* dv, float* acc_scratch, int B, cudaStream_t s);
+int launch_style_backward(const float* const* params, const float* st, const float* labels, const float* du, const float* dv,
+                          float* const* grads, float* ws, int B, cudaStream_t s);
 size_t rope_table_floats(int L);  // [L][64] + the 32-row-transposed copy
 int launch_rope_table(const float* inv_freq_host, int L, float* rope, cudaStream_t stream);
 int launch_cf_to_tm(const float* in, void* out, int out_bf16, int B, int C, int L, cudaStream_t stream);

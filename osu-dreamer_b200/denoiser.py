@@ -170,15 +170,16 @@ class DiffusionModel(nn.Module):
         key = (self._mode(), tuple(p.data_ptr() for p in ps), tuple(p._version for p in ps))
         if rt.key != key:
             rt.parr = lib.param_array([p.detach() for p in ps])
-            if rt.packed is None or rt.packed.device != ps[0].device:
-                rt.packed = torch.empty(lib.packed_bytes(self._mode()), dtype=torch.uint8, device=ps[0].device)
+            need = lib.packed_bytes(self._mode())  # depends on the precision (fp32-grade operands are (hi | lo) pairs)
+            if rt.packed is None or rt.packed.device != ps[0].device or rt.packed.numel() != need:
+                rt.packed = torch.empty(need, dtype=torch.uint8, device=ps[0].device)
             lib.pack_weights(rt.parr, rt.packed, self._mode())
             rt.key = key
         return rt
 
     def _workspace(self, B, L, a_batch, save, tag=''):
         rt = self._rt
-        k = (B, L, a_batch, save, tag)
+        k = (B, L, a_batch, save, tag, self._mode())  # sizes depend on the precision mode and the depth
         if k not in rt.ws:
             if len(rt.ws) > 6:
                 rt.ws.clear()
