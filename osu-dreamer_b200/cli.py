@@ -247,6 +247,102 @@ def fit_denoiser(config: str, ckpt_path: str | None, synthetic: bool, max_steps:
         dist.destroy_process_group()
 
 
+def build_style_trainer(cfg: dict):
+    from .style_trainer import StyleTrainer
+    clip = (cfg.get('trainer') or {}).get('gradient_clip_val', 0.0) or 0.0
+    m = dict(cfg['model'])
+    m.setdefault('schedule_args', {})  # the reference's style model.yml leaves it to LRScheduleArgs' defaults (constant LR)
+    return StyleTrainer(**m, gradient_clip_val=float(clip))
+
+
+@click.command('fit-style')
+@click.option('-c', '--config', type=click.Path(exists=True, dir_okay=False), required=True, help='config file')
+@click.option('--ckpt-path', type=click.Path(exists=True, dir_okay=False), help='checkpoint from which to resume training')
+@click.option('--synthetic', is_flag=True, help='train on synthetic style codes instead of the cached dataset')
+@click.option('--max-steps', type=int, default=None, help='stop after this many optimizer steps')
+@click.option('--out', type=click.Path(dir_okay=False), default='style.ckpt', help='checkpoint to write')
+def fit_style(config: str, ckpt_path: str | None, synthetic: bool, max_steps: int | None, out: str):
+    """begin a training run for the style model (reference: scripts/fit_style.py:17-31, models/style/model.yml)."""
+    cfg = yaml.safe_load(open(config))
+    for w in check_config(cfg):
+        print('warning:', w, file=sys.stderr)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise click.ClickException('fit-style needs a CUDA device: the B200 path has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    seed = cfg.get('seed_everything', True)
+    torch.manual_seed((0 if seed is True else int(seed)) + rank)
+    tr = build_style_trainer(cfg)
+    first_epoch, best = 0, float('inf')
+    if ckpt_path:
+        ck = load_checkpoint(ckpt_path, tr)
+        first_epoch = int(ck.get('epoch', -1)) + 1
+        if ck.get('best_model_score') is not None:
+            best = float(ck['best_model_score'])
+    else:
+        tr.style_ema.module.load_state_dict(tr.style.state_dict())
+    tr = tr.cuda()
+    if world > 1 and not ckpt_path:
+        import torch.distributed as dist
+        for t in list(tr.style.state_dict().values()) + list(tr.style_ema.module.state_dict().values()):
+            dist.broadcast(t.data, 0)
+    d = cfg['data']
+    tcfg = cfg.get('trainer') or {}
+    log_every = int(tcfg.get('log_every_n_steps', 50))
+    max_epochs = int(tcfg.get('max_epochs', -1))
+    if synthetic:
+        def epochs():
+            yield first_epoch, synthetic_batches(d['batch_size'], d['seq_len'], seed=rank + 7919 * first_epoch)
+        val_sets = None
+    else:
+        train_sets, val_sets = split_mapsets(Path(d.get('data_path', './data')), '*.latent.npz',
+                                             d.get('max_val_count', 512), d.get('max_val_frac', .3))
+        def epochs():
+            e = first_epoch
+            while max_epochs < 0 or e < max_epochs:
+                yield e, DeviceFeeder(LatentWindows(train_sets, d['seq_len'], d.get('shuffle_buffer_size', 1),
+                                                    d.get('max_per_map', -1), seed=e), d['batch_size'], rank, world,
+                                      device=torch.device('cuda', local))
+                e += 1
+    t0 = time.time()
+    epoch = first_epoch
+    for epoch, it in epochs():
+        for batch in it:
+            batch = tuple(t.cuda(non_blocking=True) for t in batch)
+            loss, log = tr.training_step(batch, world_size=world)
+            if rank == 0 and tr.global_step % log_every == 0:
+                print(f'step {tr.global_step} lr {tr.current_lr():.2e} ' +
+                      ' '.join(f'train/{k} {float(v):.4f}' for k, v in log.items()) + f' [{time.time() - t0:.0f}s]', flush=True)
+            if max_steps is not None and tr.global_step >= max_steps:
+                break
+        if val_sets and rank == 0:  # the style validation compares the whole validation set at once (train.py:120-150)
+            tr.on_validation_epoch_start()
+            for vb in LatentWindows(val_sets, d['seq_len']):
+                tr.validation_step(tuple(t[None].cuda() for t in vb))
+            vals = tr.on_validation_epoch_end()
+            print(f'epoch {epoch} ' + ' '.join(f'{k} {float(v):.4f}' for k, v in vals.items()), flush=True)
+            ed = float(vals.get('val/energy_dist', float('inf')))
+            if ed < best:  # ModelCheckpoint(monitor=val/energy_dist, mode=min, save_top_k=1), models/style/model.yml:13-18
+                best = ed
+                save_checkpoint(out, tr, epoch, best)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        if max_steps is not None and tr.global_step >= max_steps:
+            break
+    if rank == 0 and (not val_sets or not os.path.exists(out)):
+        save_checkpoint(out, tr, epoch, best if best < float('inf') else None)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 @click.command('predict', context_settings=dict(ignore_unknown_options=True, allow_extra_args=True))
 @click.pass_context
 def predict(ctx: click.Context):
@@ -271,6 +367,7 @@ def main():
 
 
 main.add_command(fit_denoiser)
+main.add_command(fit_style)
 main.add_command(predict)
 main.add_command(export_inference)
 

@@ -309,6 +309,46 @@ def style_sample(parr, labels, s, num_steps):
     return eta_u0
 
 
+# ------------------------------------------------------------------ style model training (csrc/style_train.cu)
+def style_train_workspace(B, device):
+    return torch.empty(_sz('osd_style_train_workspace_floats', B), dtype=torch.float32, device=device)
+
+
+def style_train_forward(parr, st, labels, ws):
+    """StyleModel.forward keeping its activations in ws -> (u [B], v [B,32])."""
+    B = st.shape[0]
+    u = torch.empty(B, dtype=torch.float32, device=st.device)
+    v = torch.empty(B, st.shape[1], dtype=torch.float32, device=st.device)
+    _check(load().osd_style_train_forward(parr, ptr(st), ptr(labels), ptr(u), ptr(v), ptr(ws), c_int(B), stream()))
+    return u, v
+
+
+def style_loss(st, s1, u, v, osl_w, del_w):
+    """-> (out4 = [loss, osl, del, u_mape], du [B], dv [B,32]): StyleTrainer.forward's loss value + output gradients."""
+    B = st.shape[0]
+    out4 = torch.empty(4, dtype=torch.float32, device=st.device)
+    du = torch.empty(B, dtype=torch.float32, device=st.device)
+    dv = torch.empty_like(v)
+    acc = torch.empty(4, dtype=torch.float32, device=st.device)
+    _check(load().osd_style_loss(ptr(st), ptr(s1), ptr(u), ptr(v), c_float(osl_w), c_float(del_w), ptr(out4), ptr(du), ptr(dv),
+                                 ptr(acc), c_int(B), stream()))
+    return out4, du, dv
+
+
+def style_grad_array(tensors):
+    """HOST array of 60 device pointers: gradient buffers in state-dict order; None (the two Fourier-feature buffers) -> NULL."""
+    if len(tensors) != STYLE_NUM_PARAMS:
+        raise OsdError(f'style model: expected {STYLE_NUM_PARAMS} gradient slots, got {len(tensors)}')
+    for t in tensors:
+        if t is not None and (not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()) or t.data_ptr() % 16):
+            raise OsdError('style gradient buffers must be contiguous, 16-byte aligned fp32 CUDA tensors')
+    return (c_void_p * STYLE_NUM_PARAMS)(*[0 if t is None else t.data_ptr() for t in tensors])
+
+
+def style_backward(parr, st, labels, du, dv, garr, ws):
+    _check(load().osd_style_backward(parr, ptr(st), ptr(labels), ptr(du), ptr(dv), garr, ptr(ws), c_int(st.shape[0]), stream()))
+
+
 # ------------------------------------------------------------------ latent model, inference half (csrc/latent.cu)
 def _f32(t):
     if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):

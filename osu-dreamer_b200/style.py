@@ -1,11 +1,11 @@
-"""Mirror of the reference's `StyleModel` (osu_dreamer/models/style/model.py:19-119) for INFERENCE on the B200 path:
-same constructor, attributes (`style_dim`, `c0`, `u_scale`), parameter / buffer names and shapes (so the `style.*` part
-of an inference artifact loads strictly), `forward(st, labels) -> (u, v)` and the sphere-tracing `sample(labels,
-num_steps=16)` that `LDM.sample` calls right before `diffusion.sample` (models/inference/model.py:48-49).
+"""Mirror of the reference's `StyleModel` (osu_dreamer/models/style/model.py:19-119) on the B200 path: same constructor,
+attributes (`style_dim`, `c0`, `u_scale`), parameter / buffer names and shapes (so the `style.*` part of an inference
+artifact loads strictly), `forward(st, labels) -> (u, v)` and the sphere-tracing `sample(labels, num_steps=16)` that
+`LDM.sample` calls right before `diffusion.sample` (models/inference/model.py:48-49).
 
-The arithmetic runs in csrc/style.cu through the C ABI (`osd_style_forward`, `osd_style_sample`): one CTA per sample,
-all sampler steps inside one launch.  Training the style model is not on this path: `forward` refuses when autograd
-would be needed (use the reference's trainer for `fit-style`).  No CPU fallback.
+Inference runs in csrc/style.cu through the C ABI (`osd_style_forward`, `osd_style_sample`): one CTA per sample, all
+sampler steps inside one launch.  Under autograd (`fit-style`, style_trainer.py) `forward` is one autograd Function
+whose forward / backward are `osd_style_train_forward` / `osd_style_backward` (csrc/style_train.cu).  No CPU fallback.
 """
 from __future__ import annotations
 
@@ -34,6 +34,43 @@ class _FourierFeatures(nn.Module):  # common/fourier_features.py:7-13 (buffers o
         super().__init__()
         self.register_buffer('W', torch.randn(features, dim) * float(n_bins))
         self.register_buffer('b', torch.empty(features).uniform_(-torch.pi, torch.pi))
+
+
+class _StyleFn(torch.autograd.Function):
+    """StyleModel.forward under autograd: forward = osd_style_train_forward (activations kept in a workspace), backward =
+    osd_style_backward (parameter gradients; accumulated straight into the trainer's flat buffer when it lent one)."""
+
+    @staticmethod
+    def forward(ctx, model, st, labels, *params):
+        parr, keep = model._parr()
+        ws = lib.style_train_workspace(st.shape[0], st.device)
+        u, v = lib.style_train_forward(parr, st, labels, ws)
+        ctx.model, ctx.keep = model, (parr, keep, st, labels, ws)
+        return u, v
+
+    @staticmethod
+    def backward(ctx, du, dv):
+        model = ctx.model
+        parr, keep, st, labels, ws = ctx.keep
+        B, dev = st.shape[0], st.device
+        params = list(model.parameters())
+        targets = getattr(model, '_grad_targets', None)
+        direct = targets is not None and len(targets) == len(params) and targets[0].device == dev
+        if direct:
+            grads = targets
+        else:
+            sizes = [(p.numel() + 63) // 64 * 64 for p in params]
+            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            grads, off = [], 0
+            for p, n in zip(params, sizes):
+                grads.append(flat[off:off + p.numel()].view(p.shape))
+                off += n
+        # state-dict order = parameters with the two Fourier-feature buffers after null_labels (model.py:42-46)
+        slots = grads[:3] + [None, None] + grads[3:]
+        du = torch.zeros(B, device=dev) if du is None else du.float().contiguous()
+        dv = torch.zeros(B, model.style_dim, device=dev) if dv is None else dv.float().contiguous()
+        lib.style_backward(parr, st, labels, du, dv, lib.style_grad_array(slots), ws)
+        return (None, None, None, *([None] * len(params) if direct else grads))
 
 
 class StyleModel(nn.Module):
@@ -86,9 +123,12 @@ class StyleModel(nn.Module):
         return lib.style_param_array(conv), conv
 
     def forward(self, st: Tensor, labels: Tensor):
-        """model.py:81-99 -> (u [B], v [B,S]); inference only."""
-        if torch.is_grad_enabled() and (st.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise lib.OsdError('the B200 style path is inference-only: call under torch.no_grad() (fit-style stays on the reference)')
+        """model.py:81-99 -> (u [B], v [B,S]).  With autograd enabled the parameter gradients are produced by
+        csrc/style_train.cu (st and labels are data: no gradient flows into them)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if st.requires_grad or labels.requires_grad:
+                raise lib.OsdError('gradients w.r.t. st / labels are not produced (they are data in fit-style)')
+            return _StyleFn.apply(self, st.float().contiguous(), labels.float().contiguous(), *self.parameters())
         parr, keep = self._parr()
         return lib.style_forward(parr, st.float().contiguous(), labels.float().contiguous())
 

@@ -122,7 +122,7 @@ def test_trainer_gradients_match_reference_golden(golden_dir, oracle_sd):
     worst.sort(reverse=True)
     print('worst norm errors:', [(round(a, 4), n) for a, _, n in worst[:8]])
     print('worst head errors:', sorted([(round(h, 3), n) for _, h, n in worst], reverse=True)[:8])
-    assert worst[0][0] < 5e-2, worst[:5]
+    assert worst[0][0] < 2e-2, worst[:5]  # north_star bf16 tolerance (measured <= 1.1e-2)
 
 
 def test_trainer_gradients_match_live_oracle(oracle_sd):
@@ -141,4 +141,4 @@ def test_trainer_gradients_match_live_oracle(oracle_sd):
         errs.append((e, name))
     errs.sort(reverse=True)
     print('worst relative L2 gradient errors:', [(round(e, 4), n) for e, n in errs[:10]])
-    assert errs[0][0] < 6e-2, errs[:5]
+    assert errs[0][0] < 2e-2, errs[:5]  # north_star bf16 tolerance (measured <= 1.2e-2)

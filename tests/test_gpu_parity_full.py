@@ -318,3 +318,21 @@ def test_other_backbone_depths_match_oracle(depth):
     errs = _grad_errors({n: p.grad for n, p in m.named_parameters()}, {k: v.grad for k, v in sdg.items()})
     print(f'depth {depth}: worst gradient rel-L2 errors {[(round(e, 4), n) for e, n in errs[:4]]}')
     assert errs[0][0] < BF16_TOL
+
+
+def test_precision_switch_on_a_live_model(oracle_sd):
+    """`precision` may be flipped on a model that has already run (bench.py, LDM): the packed operand copies and the
+    workspaces are sized per mode (a compute-sanitizer memcheck finding of round 2: the fp32-grade pack used to overflow the
+    bf16-sized buffer)"""
+    inp = _cuda(O.make_inputs(2, 256, seed=5))
+    with torch.no_grad():
+        ur, vr = O.forward(_cuda(oracle_sd), inp['h'], inp['s'], inp['x0'])
+        m = _model(oracle_sd, 'bf16')
+        outs = []
+        for prec, tol in (('bf16', BF16_TOL), ('fp32', FP32_TOL), ('bf16', BF16_TOL), ('fp32', FP32_TOL)):
+            m.precision = prec
+            u, v = m(inp['h'], inp['s'], inp['x0'])
+            torch.cuda.synchronize()
+            assert _maxnorm(u, ur) < tol and _maxnorm(v, vr) < tol, (prec, _maxnorm(v, vr))
+            outs.append(v.clone())
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])

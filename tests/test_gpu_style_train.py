@@ -1,0 +1,150 @@
+"""GPU: fit-style on the B200 path (csrc/style_train.cu through osd_style_train_forward / osd_style_loss / osd_style_backward,
+osu-dreamer_b200/style_trainer.py) against the oracle of the reference's StyleTrainer (oracle/neighbours_oracle.py, pinned to
+the unmodified reference by tests/golden/nb_style_loss.npz -- loss terms and every parameter-gradient norm).
+Exact fp32 path: tolerance 1e-3 (north star), measured far below."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import neighbours_oracle as N
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope='module')
+def spec(golden_dir):
+    return json.load(open(os.path.join(golden_dir, 'nb_spec.json')))['style']
+
+
+def _model(spec, seed=8765):
+    from osu_dreamer_b200.style import StyleModel, StyleModelArgs
+    sd = N.seeded_state_dict(spec, seed)
+    m = StyleModel(32, StyleModelArgs(label_features=128, h_dim=256, depth=8, expand=4))
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().train(), sd
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _check_against_oracle(m, sd, s1, labels, s0, t, drop, tag):
+    from osu_dreamer_b200.style_trainer import _StyleLoss
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss_r, log_r = N.style_trainer_loss(sdr, s1, labels, s0, t, drop)
+    loss_r.backward()
+    st = torch.lerp(s0, s1, t[:, None]).cuda()
+    masked = torch.where(drop, torch.full_like(labels, -1.0), labels).cuda()
+    for p in m.parameters():
+        p.grad = None
+    u, v = m(st, masked)
+    with torch.no_grad():
+        ur, vr = N.style_forward(sd, st.cpu(), masked.cpu())
+    assert _rel(u, ur) < TOL and _rel(v, vr) < TOL, (tag, _rel(u, ur), _rel(v, vr))
+    loss, out4 = _StyleLoss.apply(u, v, st, s1.cuda(), 1.0, 30.0)
+    loss.backward()
+    torch.cuda.synchronize()
+    for got, want in zip(out4.cpu().tolist(), (float(loss_r), float(log_r['osl']), float(log_r['del_']), float(log_r['u_mape']))):
+        assert abs(got - want) <= 1e-4 * abs(want), (tag, out4, want)
+    errs = sorted(((_rel(p.grad, sdr[n].grad), n) for n, p in m.named_parameters()), reverse=True)
+    print(f'{tag}: loss {float(loss):.6f} vs {float(loss_r):.6f}; worst gradient rel-L2 {[(f"{e:.1e}", n) for e, n in errs[:4]]}')
+    assert errs[0][0] < TOL, errs[:4]
+    return loss
+
+
+def test_style_loss_and_gradients_match_reference_golden(golden_dir, spec):
+    """the reference's own draws (nb_style_loss.npz): loss terms vs what the reference logged, gradient norms vs its autograd,
+    and every gradient element-wise vs the oracle"""
+    g = np.load(os.path.join(golden_dir, 'nb_style_loss.npz'))
+    m, sd = _model(spec)
+    loss = _check_against_oracle(m, sd, *(torch.from_numpy(g[k]) for k in ('s1', 'labels', 's0', 't', 'drop')), tag='golden')
+    assert abs(float(loss) - float(g['loss'])) <= 1e-4 * abs(float(g['loss']))
+    grads = dict(m.named_parameters())
+    for name, want in zip(g['grad_names'], g['grad_norms']):
+        got = float(grads[str(name)].grad.norm())
+        assert abs(got - float(want)) <= 1e-3 * max(abs(float(want)), 1e-12), (name, got, want)
+
+
+@pytest.mark.parametrize('B', [1, 37, 512])
+def test_style_gradients_match_oracle_other_batches(spec, B):
+    """ragged batch sizes and the training batch of models/style/model.yml:49; all labels dropped for one sample, none for another"""
+    g = torch.Generator().manual_seed(B)
+    s1 = torch.randn(B, 32, generator=g)
+    s1 = s1 * s1.pow(2).mean(1, keepdim=True).add(1e-6).rsqrt()
+    labels = 10 * torch.rand(B, 5, generator=g)
+    s0 = torch.randn(B, 32, generator=g)
+    t = torch.rand(B, generator=g)
+    drop = torch.rand(B, 5, generator=g) < 0.2
+    drop[0] = True
+    if B > 1:
+        drop[1] = False
+    m, sd = _model(spec, seed=100 + B)
+    _check_against_oracle(m, sd, s1, labels, s0, t, drop, tag=f'B={B}')
+
+
+def test_style_trainer_steps_and_state_dict(spec):
+    """StyleTrainer mirror: state-dict keys of the reference (style.*, style_ema.module.*, style_ema.n_averaged), the loss goes
+    down on a repeated batch, the first AdamW + EMA step equals the oracle's on the oracle's gradients"""
+    from osu_dreamer_b200.style import StyleModelArgs
+    from osu_dreamer_b200.style_trainer import StyleTrainer
+    from osu_dreamer_b200.trainer import LRScheduleArgs
+    from oracle import denoiser_oracle as O
+    torch.manual_seed(0)
+    tr = StyleTrainer(opt_args=dict(lr=3e-4, weight_decay=0.01), schedule_args=LRScheduleArgs(), label_drop_prob=0.2, osl_weight=1.0,
+                      del_weight=30.0, style_dim=32, style_args=StyleModelArgs(label_features=128, h_dim=256, depth=8, expand=4))
+    sd = N.seeded_state_dict(spec, 8765)
+    tr.style.load_state_dict(sd)
+    tr.style_ema.module.load_state_dict(sd)
+    tr = tr.cuda()
+    keys = list(tr.state_dict().keys())
+    assert keys[0] == 'style.cond_proj_w' and 'style_ema.module.rff.W' in keys and 'style_ema.n_averaged' in keys
+    assert len(keys) == 2 * 60 + 1
+    B = 64
+    g = torch.Generator().manual_seed(4)
+    s1 = torch.randn(B, 32, generator=g)
+    s1 = (s1 * s1.pow(2).mean(1, keepdim=True).add(1e-6).rsqrt()).cuda()
+    labels = (10 * torch.rand(B, 5, generator=g)).cuda()
+    e = torch.empty(B, 0, 0, device='cuda')
+    # first step against the oracle with the CUDA generator's draws replayed
+    torch.manual_seed(77)
+    tr.training_step((e, e, s1, labels))
+    torch.cuda.synchronize()
+    torch.manual_seed(77)
+    uu = (torch.randperm(B, device='cuda') + torch.rand(B, device='cuda')) / B
+    t = torch.special.ndtri(uu.clamp(1e-6, 1 - 1e-6)).sigmoid().cpu()
+    s0 = torch.randn_like(s1).cpu()
+    drop = (torch.rand_like(labels) < 0.2).cpu()
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss_r, _ = N.style_trainer_loss(sdr, s1.cpu(), labels.cpu(), s0, t, drop)
+    loss_r.backward()
+    trained = [k for k in sd if not k.startswith('rff.')]
+    gn = torch.sqrt(sum(sdr[k].grad.double().pow(2).sum() for k in trained)).item()
+    assert abs(float(tr._opt['scal'][0]) - gn) < 1e-3 * gn
+    coef = min(1.0, 1.0 / (gn + 1e-6))
+    worst = 0.0
+    for name, p in tr.style.named_parameters():
+        ref = sd[name].clone()
+        mm, vv, ema = torch.zeros_like(ref), torch.zeros_like(ref), torch.zeros_like(ref)
+        O.adamw_ema_step(ref, sdr[name].grad, mm, vv, ema, 1, 3e-4, clip_coef=coef, ema_first=True)
+        mask = sdr[name].grad.abs() > 1e-6
+        if mask.any():
+            worst = max(worst, float((p.detach().cpu() - ref).abs()[mask].max()))
+    print('first step: max |dp| vs oracle AdamW', worst)
+    assert worst < 1e-6
+    losses = []
+    for _ in range(12):
+        torch.manual_seed(5)  # same draws every step -> the loss must go down
+        loss, log = tr.training_step((e, e, s1, labels))
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    assert int(tr.style_ema.n_averaged) == 13 and tr.global_step == 13
+    tr.on_validation_epoch_start()
+    tr.validation_step((e, e, s1, labels))
+    vals = tr.on_validation_epoch_end()
+    assert {'val/loss', 'val/energy_dist', 'val/nn_ratio', 'val/cond_recall', 'val/sample_spread'} <= set(vals)
+    assert all(np.isfinite(float(v)) for v in vals.values())

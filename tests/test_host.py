@@ -249,8 +249,8 @@ def test_prefetcher_order_errors_and_pinned_batches(tmp_path):
 
 
 def test_style_mirror_state_dict_contract_and_no_cpu_path(golden_dir):
-    """the inference mirror of StyleModel carries the reference's parameter / buffer names, shapes and order
-    (tests/golden/nb_spec.json, written from the reference module) and refuses to run without CUDA or under autograd"""
+    """the mirror of StyleModel carries the reference's parameter / buffer names, shapes and order
+    (tests/golden/nb_spec.json, written from the reference module) and refuses to run without CUDA"""
     import json
     from osu_dreamer_b200 import lib
     from osu_dreamer_b200.style import StyleModel, StyleModelArgs
@@ -265,8 +265,10 @@ def test_style_mirror_state_dict_contract_and_no_cpu_path(golden_dir):
     if not torch.cuda.is_available():
         with torch.no_grad(), pytest.raises(lib.OsdError, match='no CPU path'):
             m(torch.randn(2, 32), torch.rand(2, 5))
-    with pytest.raises(lib.OsdError, match='inference-only'):
-        m(torch.randn(2, 32), torch.rand(2, 5))
+        with pytest.raises(lib.OsdError, match='no CPU path'):  # the training path (autograd on) has no CPU fallback either
+            m(torch.randn(2, 32), torch.rand(2, 5))
+    with pytest.raises(lib.OsdError, match='not produced'):  # st / labels are data in fit-style
+        m(torch.randn(2, 32, requires_grad=True), torch.rand(2, 5))
 
 
 def test_latent_mirror_state_dict_contract(golden_dir):
@@ -355,3 +357,33 @@ def test_rank_sharding_properties():
                 g = k * world + r
                 assert grp == list(range(g * bs, (g + 1) * bs))
     check()
+
+
+def test_style_trainer_from_reference_yaml_schema():
+    """fit-style: the reference's own models/style/model.yml schema builds the mirror (no schedule_args there: constant LR);
+    state-dict keys are the reference's (style.*, style_ema.module.*, style_ema.n_averaged)"""
+    from osu_dreamer_b200.cli import build_style_trainer, check_config
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = yaml.safe_load(open(os.path.join(root, 'osu-dreamer_b200', 'style.yml')))
+    assert check_config(cfg) == []
+    cfg['model'].pop('schedule_args')
+    tr = build_style_trainer(cfg)
+    keys = list(tr.state_dict().keys())
+    assert len(keys) == 121 and keys[0] == 'style.cond_proj_w' and 'style_ema.n_averaged' in keys
+    assert sum(k.startswith('style_ema.module.') for k in keys) == 60
+    assert tr.gradient_clip_val == 1.0 and tr.current_lr() == 3e-4 and tr.label_drop_prob == .2
+    assert sum(p.numel() for p in tr.style.parameters()) == 5970721 or sum(p.numel() for p in tr.style.parameters()) > 5.9e6
+
+
+def test_check_config_refuses_what_it_cannot_honour():
+    import click
+    from osu_dreamer_b200.cli import check_config
+    base = {'trainer': {'gradient_clip_val': 1.0}, 'model': {'opt_args': {'lr': 1e-3}}}
+    assert check_config(base) == []
+    with pytest.raises(click.ClickException):
+        check_config({'trainer': {'accumulate_grad_batches': 4}, 'model': {}})
+    with pytest.raises(click.ClickException):
+        check_config({'trainer': {'precision': '32-true'}, 'model': {}})
+    with pytest.raises(click.ClickException):
+        check_config({'trainer': {}, 'model': {'opt_args': {'amsgrad': True}}})
+    assert any('val_check_interval' in w for w in check_config({'trainer': {'val_check_interval': 100}, 'model': {}}))
