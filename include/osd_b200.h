@@ -101,7 +101,9 @@ OSD_API size_t osd_rope_table_floats(int L);
  * resident in TMEM, 2 CTAs per SM; csrc/attn_fwd_db.cu).  The others are kept for A/B measurements: 0 / 1 = single-S
  * kernel with 64- / 128-row kv tiles and P staged in shared memory, 2 / 3 = the same with P kept in TMEM
  * (csrc/attn_fwd.cu); 4 = double-buffered S with Q in shared memory, 6 = 4 + early barrier probes and S prefetch,
- * 8 = 7 + pre-scaled Q and row sums by a ones-tile MMA (csrc/attn_fwd_db.cu).  Anything else is an error. */
+ * 8 = 7 + pre-scaled Q and row sums by a ones-tile MMA (csrc/attn_fwd_db.cu); 9 = two q tiles per CTA ping-pong against
+ * 128-row kv tiles, 1 CTA per SM, a quarter of the exponentials on the FMA pipe (csrc/attn_fwd_pp.cu; 10 / 11 = none / half
+ * of them).  Anything else is an error. */
 OSD_API int osd_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                          int variant, void* stream);
 
