@@ -131,11 +131,13 @@ def test_style_trainer_steps_and_state_dict(spec):
         ref = sd[name].clone()
         mm, vv, ema = torch.zeros_like(ref), torch.zeros_like(ref), torch.zeros_like(ref)
         O.adamw_ema_step(ref, sdr[name].grad, mm, vv, ema, 1, 3e-4, clip_coef=coef, ema_first=True)
-        mask = sdr[name].grad.abs() > 1e-6
+        # AdamW's first step is lr * g' / (|g'| + eps) with g' the CLIPPED gradient: compare where |g'| >> eps = 1e-8, elsewhere
+        # the update amplifies fp32 rounding noise of the gradient
+        mask = (sdr[name].grad * coef).abs() > 3e-6
         if mask.any():
             worst = max(worst, float((p.detach().cpu() - ref).abs()[mask].max()))
     print('first step: max |dp| vs oracle AdamW', worst)
-    assert worst < 1e-6
+    assert worst < 2e-6
     losses = []
     for _ in range(12):
         torch.manual_seed(5)  # same draws every step -> the loss must go down
