@@ -121,6 +121,9 @@ int launch_attn_fwd_db_pf(const void* qkv, void* y, float* lse, const float* bou
 // variant 9 (10 / 11: no / half FMA-pipe exponentials): two q tiles per CTA ping-pong, 128-row kv tiles, 1 CTA/SM
 int launch_attn_fwd_pp(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int emu,
                        cudaStream_t stream);
+// variant 12 (13 / 14: no / half FMA-pipe exponentials): "pp" with S and P decoupled in TMEM and an event-driven UMMA issuer
+int launch_attn_fwd_pp2(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int emu,
+                        cudaStream_t stream);
 int launch_attn_fwd_x3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                        cudaStream_t stream);
 int launch_qk_bound(const float* qw, const float* kw, float* out, cudaStream_t stream);
