@@ -395,6 +395,8 @@ int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log
   if (variant == 12) return launch_attn_fwd_pp2(qkv, y, lse, bound_log2, B, L, H, -1, stream);  // pp + decoupled S / P
   if (variant == 13) return launch_attn_fwd_pp2(qkv, y, lse, bound_log2, B, L, H, 0, stream);
   if (variant == 14) return launch_attn_fwd_pp2(qkv, y, lse, bound_log2, B, L, H, 2, stream);
+  if (variant == 15) return launch_attn_fwd_pp3(qkv, y, lse, bound_log2, B, L, H, -1, stream);  // pp2 + 16 softmax warps
+  if (variant == 16) return launch_attn_fwd_pp3(qkv, y, lse, bound_log2, B, L, H, 1, stream);
   if (variant == 4) return launch_attn_fwd_db(qkv, y, lse, bound_log2, B, L, H, stream);  // double-buffered S
   if (variant == 8) return launch_attn_fwd_db_dr(qkv, y, lse, bound_log2, B, L, H, stream);  // direct exponent
   if (variant == 7) return launch_attn_fwd_db_qt(qkv, y, lse, bound_log2, B, L, H, stream);  // Q in TMEM
@@ -402,7 +404,7 @@ int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log
   if (variant == 1) return launch_attn_fwd_t<128, false>(qkv, y, lse, bound_log2, B, L, H, stream);
   if (variant == 2) return launch_attn_fwd_t<64, true>(qkv, y, lse, bound_log2, B, L, H, stream);
   if (variant == 3) return launch_attn_fwd_t<128, true>(qkv, y, lse, bound_log2, B, L, H, stream);
-  OSD_CHECK(variant == 0, "attn_fwd: unknown variant %d (0-4, 6-14)", variant);
+  OSD_CHECK(variant == 0, "attn_fwd: unknown variant %d (0-4, 6-16)", variant);
   return launch_attn_fwd_t<64, false>(qkv, y, lse, bound_log2, B, L, H, stream);
 }
 

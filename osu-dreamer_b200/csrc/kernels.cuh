@@ -124,6 +124,10 @@ int launch_attn_fwd_pp(const void* qkv, void* y, float* lse, const float* bound_
 // variant 12 (13 / 14: no / half FMA-pipe exponentials): "pp" with S and P decoupled in TMEM and an event-driven UMMA issuer
 int launch_attn_fwd_pp2(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int emu,
                         cudaStream_t stream);
+// variant 15 (16: a quarter of the exponentials on the FMA pipe): "pp2" with SIXTEEN softmax warps (each score row split
+// between two threads); fixed-bound softmax only, hands the online case to the "db" kernel on the device
+int launch_attn_fwd_pp3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int emu,
+                        cudaStream_t stream);
 int launch_attn_fwd_x3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                        cudaStream_t stream);
 int launch_qk_bound(const float* qw, const float* kw, float* out, cudaStream_t stream);
