@@ -1,7 +1,12 @@
-// fp32-grade flash attention forward: every bf16 tensor-core product is replaced by the 3-term split
+// fp32-grade flash attention forward: every bf16 tensor-core product is replaced by the split
 //   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo      (a = a_hi + a_lo, both bf16: ~16 mantissa bits)
 // so that S = Q K^T and O = P V carry fp32-like accuracy while still running on tcgen05 (which has no fp32 MMA and
 // whose kind::tf32 truncates its operands).  Used by the precision='fp32' sampling path (BASELINE config 3).
+// Which correction terms run is a launch parameter (qk_mask / pv_mask: bit 1 = lo*hi, bit 2 = hi*lo): the attention
+// kernels are ENERGY bound on the 1 kW part, so every dropped term is time; the error each term buys
+// is measured by tools/x3_terms_sweep.py and the shipped choice is the cheapest one that keeps the 64-step sampler a
+// decade inside the 1e-3 tolerance.  When P_lo is not multiplied, the row sum is taken over the ROUNDED P_hi, so that
+// the normalisation sees the same probabilities as the MMA (a row dominated by one key stays exact).
 // Same structure as attn_fwd_kernel<64, true>: 128 q rows per CTA, 64-row kv tiles, P kept in TMEM.
 //   qkv : bf16 [B*L, 2*3*dh] = (hi block | lo block), each block (q | k | v)
 //   y   : bf16 [B*L, 2*dh]   = (hi | lo)
@@ -9,8 +14,18 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 namespace osd {
 
+// shipped term selection: all three terms for both products until tools/x3_terms_sweep.py says otherwise
+#ifndef X3_DEFAULT_QK
+#define X3_DEFAULT_QK 7
+#endif
+#ifndef X3_DEFAULT_PV
+#define X3_DEFAULT_PV 7
+#endif
 static constexpr int X3_THREADS = 192;
 static constexpr int X3_T128 = 128 * 128;
 static constexpr int X3_T64 = 64 * 128;
@@ -26,6 +41,7 @@ struct AttnX3Params {
   float* lse;
   int B, H, L, dh;
   float scale_log2, scale;
+  int qk_mask, pv_mask;  // bit 1: (Q_lo K_hi | P_lo V_hi), bit 2: (Q_hi K_lo | P_hi V_lo); the hi*hi term always runs
 };
 
 __device__ __forceinline__ float x3_ex2(float x) {
@@ -91,20 +107,21 @@ __global__ void __launch_bounds__(X3_THREADS, 2) attn_fwd_x3_kernel(const __grid
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * X3_T128);
+      mbar_expect_tx(q_full, ((p.qk_mask & 2) ? 2 : 1) * X3_T128);
       tma_load_3d(sQ, &p.tma_q, q_full, h * 64, q0, b);
-      tma_load_3d(sQ + X3_T128, &p.tma_q, q_full, lo_col + h * 64, q0, b);
+      if (p.qk_mask & 2) tma_load_3d(sQ + X3_T128, &p.tma_q, q_full, lo_col + h * 64, q0, b);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], 2 * X3_T64);
+        const bool klo = (p.qk_mask & 4) != 0, vlo = (p.pv_mask & 4) != 0;  // the lo tiles travel only when a term reads them
+        mbar_expect_tx(&k_full[st], (klo ? 2 : 1) * X3_T64);
         tma_load_3d(sK + (2 * st) * X3_T64, &p.tma_kv, &k_full[st], p.dh + h * 64, j * 64, b);
-        tma_load_3d(sK + (2 * st + 1) * X3_T64, &p.tma_kv, &k_full[st], lo_col + p.dh + h * 64, j * 64, b);
+        if (klo) tma_load_3d(sK + (2 * st + 1) * X3_T64, &p.tma_kv, &k_full[st], lo_col + p.dh + h * 64, j * 64, b);
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], 2 * X3_T64);
+        mbar_expect_tx(&v_full[st], (vlo ? 2 : 1) * X3_T64);
         tma_load_3d(sV + (2 * st) * X3_T64, &p.tma_kv, &v_full[st], 2 * p.dh + h * 64, j * 64, b);
-        tma_load_3d(sV + (2 * st + 1) * X3_T64, &p.tma_kv, &v_full[st], lo_col + 2 * p.dh + h * 64, j * 64, b);
+        if (vlo) tma_load_3d(sV + (2 * st + 1) * X3_T64, &p.tma_kv, &v_full[st], lo_col + 2 * p.dh + h * 64, j * 64, b);
       }
     }
   } else if (warp == 1) {
@@ -121,12 +138,16 @@ __global__ void __launch_bounds__(X3_THREADS, 2) attn_fwd_x3_kernel(const __grid
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // Q_hi K_hi^T
           umma_f16_ss(tS, make_smem_desc(aQh + k * 32, 0, 1024), make_smem_desc(aKh + k * 32, 0, 1024), idesc_s, k > 0);
+        if (p.qk_mask & 2) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // Q_lo K_hi^T
-          umma_f16_ss(tS, make_smem_desc(aQl + k * 32, 0, 1024), make_smem_desc(aKh + k * 32, 0, 1024), idesc_s, 1u);
+          for (int k = 0; k < 4; ++k)  // Q_lo K_hi^T
+            umma_f16_ss(tS, make_smem_desc(aQl + k * 32, 0, 1024), make_smem_desc(aKh + k * 32, 0, 1024), idesc_s, 1u);
+        }
+        if (p.qk_mask & 4) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // Q_hi K_lo^T
-          umma_f16_ss(tS, make_smem_desc(aQh + k * 32, 0, 1024), make_smem_desc(aKl + k * 32, 0, 1024), idesc_s, 1u);
+          for (int k = 0; k < 4; ++k)  // Q_hi K_lo^T
+            umma_f16_ss(tS, make_smem_desc(aQh + k * 32, 0, 1024), make_smem_desc(aKl + k * 32, 0, 1024), idesc_s, 1u);
+        }
         umma_commit(&k_empty[st]);
         umma_commit(s_full);
       };
@@ -141,12 +162,16 @@ __global__ void __launch_bounds__(X3_THREADS, 2) attn_fwd_x3_kernel(const __grid
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // P_hi V_hi
           umma_f16_ts(tO, tS + k * 8, make_smem_desc(aVh + k * 16 * 128, 0, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        if (p.pv_mask & 2) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // P_lo V_hi
-          umma_f16_ts(tO, tS + 32 + k * 8, make_smem_desc(aVh + k * 16 * 128, 0, 1024), idesc_o, 1u);
+          for (int k = 0; k < 4; ++k)  // P_lo V_hi
+            umma_f16_ts(tO, tS + 32 + k * 8, make_smem_desc(aVh + k * 16 * 128, 0, 1024), idesc_o, 1u);
+        }
+        if (p.pv_mask & 4) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // P_hi V_lo
-          umma_f16_ts(tO, tS + k * 8, make_smem_desc(aVl + k * 16 * 128, 0, 1024), idesc_o, 1u);
+          for (int k = 0; k < 4; ++k)  // P_hi V_lo
+            umma_f16_ts(tO, tS + k * 8, make_smem_desc(aVl + k * 16 * 128, 0, 1024), idesc_o, 1u);
+        }
         umma_commit(&v_empty[st]);
         umma_commit(o_ready);
         if (j + 1 < n_kv) issue_s(j + 1);  // in-order tensor pipe: overwrites P only after the MMAs above
@@ -201,6 +226,7 @@ __global__ void __launch_bounds__(X3_THREADS, 2) attn_fwd_x3_kernel(const __grid
         }
       }
       float sum = 0.f;
+      const bool plo = (p.pv_mask & 2) != 0;
       uint32_t ph[32], pl[32];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
@@ -208,18 +234,21 @@ __global__ void __launch_bounds__(X3_THREADS, 2) attn_fwd_x3_kernel(const __grid
         float a1 = (i + 1 < valid) ? x3_ex2(fmaf(__uint_as_float(r0[i + 1]), c, neg_mc)) : 0.f;
         float b0 = (32 + i < valid) ? x3_ex2(fmaf(__uint_as_float(r1[i]), c, neg_mc)) : 0.f;
         float b1 = (33 + i < valid) ? x3_ex2(fmaf(__uint_as_float(r1[i + 1]), c, neg_mc)) : 0.f;
-        sum += (a0 + a1) + (b0 + b1);
         const uint32_t ha = pack_bf16(a0, a1), hb = pack_bf16(b0, b1);
         const __nv_bfloat162 fa = *reinterpret_cast<const __nv_bfloat162*>(&ha);
         const __nv_bfloat162 fb = *reinterpret_cast<const __nv_bfloat162*>(&hb);
+        if (plo)
+          sum += (a0 + a1) + (b0 + b1);
+        else  // only P_hi is multiplied: normalise by what the MMA sees
+          sum += (__low2float(fa) + __high2float(fa)) + (__low2float(fb) + __high2float(fb));
         ph[i >> 1] = ha;
         ph[16 + (i >> 1)] = hb;
         pl[i >> 1] = pack_bf16(a0 - __low2float(fa), a1 - __high2float(fa));
         pl[16 + (i >> 1)] = pack_bf16(b0 - __low2float(fb), b1 - __high2float(fb));
       }
       __syncwarp();
-      tmem_st32(tS, ph);       // P_hi: 64 bf16 = 32 columns
-      tmem_st32(tS + 32, pl);  // P_lo
+      tmem_st32(tS, ph);                // P_hi: 64 bf16 = 32 columns
+      if (plo) tmem_st32(tS + 32, pl);  // P_lo
       tmem_wait_st();
       l = l * alpha + sum;
       m = m_new;
@@ -268,6 +297,18 @@ __global__ void __launch_bounds__(X3_THREADS, 2) attn_fwd_x3_kernel(const __grid
   }
 }
 
+// OSD_X3_TERMS="<qk_mask>,<pv_mask>" overrides the shipped term selection (tools/x3_terms_sweep.py)
+static void x3_terms(int* qk, int* pv) {
+  static const int packed = [] {
+    int a = X3_DEFAULT_QK, b = X3_DEFAULT_PV;
+    const char* e = getenv("OSD_X3_TERMS");
+    if (e != nullptr) sscanf(e, "%d,%d", &a, &b);
+    return ((a | 1) & 7) | (((b | 1) & 7) << 8);
+  }();
+  *qk = packed & 7;
+  *pv = (packed >> 8) & 7;
+}
+
 int launch_attn_fwd_x3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                        cudaStream_t stream) {
   OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd_x3: bad arguments");
@@ -284,6 +325,7 @@ int launch_attn_fwd_x3(const void* qkv, void* y, float* lse, const float* bound_
   p.B = B; p.H = H; p.L = L; p.dh = dh;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  x3_terms(&p.qk_mask, &p.pv_mask);
   static DeviceOnce once;
   if (once.first()) {
     OSD_CUDA(cudaFuncSetAttribute(attn_fwd_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X3_SMEM_BYTES));
