@@ -389,13 +389,7 @@ static int launch_attn_fwd_t(const void* qkv, void* y, float* lse, const float* 
 int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int variant,
                     cudaStream_t stream) {
   OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd: bad arguments");
-  if (variant == 9) return launch_attn_fwd_pp(qkv, y, lse, bound_log2, B, L, H, -1, stream);  // ping-pong, 2 q tiles / CTA
-  if (variant == 10) return launch_attn_fwd_pp(qkv, y, lse, bound_log2, B, L, H, 0, stream);
-  if (variant == 11) return launch_attn_fwd_pp(qkv, y, lse, bound_log2, B, L, H, 2, stream);
-  if (variant == 12) return launch_attn_fwd_pp2(qkv, y, lse, bound_log2, B, L, H, -1, stream);  // pp + decoupled S / P
-  if (variant == 13) return launch_attn_fwd_pp2(qkv, y, lse, bound_log2, B, L, H, 0, stream);
-  if (variant == 14) return launch_attn_fwd_pp2(qkv, y, lse, bound_log2, B, L, H, 2, stream);
-  if (variant == 15) return launch_attn_fwd_pp3(qkv, y, lse, bound_log2, B, L, H, -1, stream);  // pp2 + 16 softmax warps
+  if (variant == 15) return launch_attn_fwd_pp3(qkv, y, lse, bound_log2, B, L, H, -1, stream);  // 2 q tiles / CTA, 16 softmax warps
   if (variant == 16) return launch_attn_fwd_pp3(qkv, y, lse, bound_log2, B, L, H, 1, stream);
   if (variant == 4) return launch_attn_fwd_db(qkv, y, lse, bound_log2, B, L, H, stream);  // double-buffered S
   if (variant == 8) return launch_attn_fwd_db_dr(qkv, y, lse, bound_log2, B, L, H, stream);  // direct exponent
@@ -404,7 +398,7 @@ int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log
   if (variant == 1) return launch_attn_fwd_t<128, false>(qkv, y, lse, bound_log2, B, L, H, stream);
   if (variant == 2) return launch_attn_fwd_t<64, true>(qkv, y, lse, bound_log2, B, L, H, stream);
   if (variant == 3) return launch_attn_fwd_t<128, true>(qkv, y, lse, bound_log2, B, L, H, stream);
-  OSD_CHECK(variant == 0, "attn_fwd: unknown variant %d (0-4, 6-16)", variant);
+  OSD_CHECK(variant == 0, "attn_fwd: unknown variant %d (0-4, 6-8, 15, 16)", variant);
   return launch_attn_fwd_t<64, false>(qkv, y, lse, bound_log2, B, L, H, stream);
 }
 

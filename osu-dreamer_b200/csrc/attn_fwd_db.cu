@@ -27,16 +27,6 @@ static constexpr int DB_ONES = 2048;  // variant 8: [16 x 64] bf16 tile of ones 
 static constexpr int DB_SMEM_BYTES = DB_SMEM_TILES + DB_ONES + 256;
 static constexpr uint32_t DB_TMEM_COLS = 256;
 
-// Anti-phase start of the two CTAs that share an SM.  Both CTAs run the same loop: per kv step a softmax warp spends ~400 clk
-// off the SFU (TMEM load, sums, pack, TMEM store, fences, barrier) and 64 MUFU.EX2 = 512 clk of its sub-partition's SFU; the
-// sub-partition hosts one softmax warp of each CTA.  CTAs of one launch wave start together and STAY in lockstep (the offset
-// between them is neutrally stable: whoever leads in the exponentials is caught up while it is off the SFU), so both warps
-// leave the SFU idle at the same time: 2 x 512 + 400 = 1424 clk per step pair, exactly what the kernel measured (1421) -- an
-// SFU that is the binding unit but only 76 % busy (ncu).  Delaying the softmax warps of every second CTA of the FIRST wave by
-// about half a period puts the off-SFU part of one CTA under the exponentials of the other; later CTAs inherit the offset
-// because each starts when its predecessor on that SM slot retires.  The slot is the arrival order on the SM.
-__device__ unsigned int g_db_sm_arrivals[1024];
-
 struct AttnDbParams {
   CUtensorMap tma_q;   // dims (3*dh, L, B), box (64, 128, 1)
   CUtensorMap tma_kv;  // box (64, 64, 1)
@@ -46,8 +36,6 @@ struct AttnDbParams {
   int B, H, L, dh;
   float scale_log2, scale;
   int only_if_online;  // 1: return immediately when the bound is finite (the w8 kernel has done the work)
-  int stagger_clk;     // softmax start delay of odd-slot CTAs of the first wave (0 = off)
-  int first_wave;      // CTAs with blockIdx.x below this belong to the first wave (2 per SM)
 };
 
 __device__ __forceinline__ float db_ex2(float x) {
@@ -105,7 +93,6 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
   uint64_t* o_ready = bars + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   uint64_t* qt_ready = bars + 18;  // QT: Q copied into TMEM by the softmax warps
-  uint32_t* slot_smem = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = (p.L + 127) / 128;
@@ -129,13 +116,6 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
     mbar_init(o_ready, 1);
     mbar_init(qt_ready, 4);
     fence_barrier_init();
-    uint32_t odd = 0;
-    if (p.stagger_clk > 0 && (int)blockIdx.x < p.first_wave) {
-      uint32_t smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      odd = atomicAdd(&g_db_sm_arrivals[smid & 1023], 1u) & 1u;
-    }
-    *slot_smem = odd;
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, DB_TMEM_COLS);
@@ -249,11 +229,6 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(qt_ready);
-    }
-    if (*slot_smem != 0) {  // anti-phase start (see g_db_sm_arrivals)
-      const long long t0 = clock64();
-      while (clock64() - t0 < p.stagger_clk) {
-      }
     }
     const float c = (DR && direct) ? 1.0f : p.scale_log2;  // direct mode: Q was pre-scaled, S is already in octaves
     float bound = INFINITY;
@@ -447,12 +422,6 @@ static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const floa
   p.B = B; p.H = H; p.L = L; p.dh = dh;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
-  static const int stagger = [] {  // OSD_FWD_STAGGER=<clk> for A/B runs; default: half of the 1424-clk lockstep period
-    const char* e = getenv("OSD_FWD_STAGGER");
-    return e != nullptr ? atoi(e) : 700;
-  }();
-  p.stagger_clk = stagger;
-  p.first_wave = 2 * num_sms();
   static DeviceOnce once;
   if (once.first()) {
     OSD_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<PF, QT, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES));

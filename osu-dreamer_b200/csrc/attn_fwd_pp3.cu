@@ -1,10 +1,13 @@
-// Flash attention forward, variant "pp3" -- the kernel the model runs.  ONE CTA per SM works on TWO 128-row q tiles of one
-// (b, h) against 128-row kv tiles that both share; S and P are decoupled in TMEM; SIXTEEN softmax warps.
+// Flash attention forward, variant "pp3" (15 / 16): the cuDNN-shaped layout.  ONE CTA per SM works on TWO 128-row q tiles of
+// one (b, h) against 128-row kv tiles that both share; S and P are decoupled in TMEM; SIXTEEN softmax warps.  Kept next to the
+// model's kernel ("db", variant 7) as the measured alternative: 9.2-9.5 M cycles per launch at B = 16, L = 8192 against db's
+// 9.55 M (ncu), and the SAME time in a sustained loop (5.61 vs 5.55 ms) because both draw the board's 1 kW: at the cap the
+// time of these kernels is their energy (profiles/r02i_fwd_power_ab.json).
 //
-// How it got here (profiles/r02*_fwd_*.json): every earlier forward kernel of this repo -- two CTAs per SM with
-// 64-row kv tiles ("db", variant 7), two q tiles per CTA ping-pong ("pp", 9), the same with S / P decoupled ("pp2", 12) --
-// ran at 0.76-0.84 PFLOP/s whatever its control structure, with neither the SFU (56-76 %), the tensor pipe (37 %) nor the
-// issue slots (42-51 %) saturated, while cuDNN's sm100 kernel (128x128x64 tiles, 256 q rows per CTA, 16 warps) does 1.0.
+// How it got here (profiles/r02*_fwd_*.json): every forward kernel of this repo -- two CTAs per SM with 64-row
+// kv tiles ("db"), two q tiles per CTA ping-pong with P over S ("pp", removed), the same with S / P decoupled ("pp2", removed)
+// -- ran at 0.76-0.84 PFLOP/s whatever its control structure, with neither the SFU (56-76 %), the tensor pipe (37 %) nor the
+// issue slots (42-51 %) saturated, while cuDNN's sm100 kernel (128x128x64 tiles, 256 q rows per CTA, 16 warps) does 0.90-1.0.
 // tools/micro/softmax_bench.cu isolates the cause: the per-element routine (scale FFMA2, MUFU.EX2, row-sum FADD2, bf16 pack)
 // is a dependent chain, and with TWO warps per sub-partition -- 8 softmax warps per SM, which all of those kernels have -- an
 // SM sustains only 11.1 elements/clk; with FOUR per sub-partition 14.7 (SFU limit: 16).  11.1 elements/clk is 2960 clk

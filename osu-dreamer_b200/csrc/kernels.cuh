@@ -118,14 +118,9 @@ int launch_attn_fwd_db_dr(const void* qkv, void* y, float* lse, const float* bou
                           cudaStream_t stream);  // variant 8: + pre-scaled Q (P = 2^S) and row sums by a ones-tile MMA
 int launch_attn_fwd_db_pf(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                           cudaStream_t stream);  // variant 6: early barrier probes + S prefetch
-// variant 9 (10 / 11: no / half FMA-pipe exponentials): two q tiles per CTA ping-pong, 128-row kv tiles, 1 CTA/SM
-int launch_attn_fwd_pp(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int emu,
-                       cudaStream_t stream);
-// variant 12 (13 / 14: no / half FMA-pipe exponentials): "pp" with S and P decoupled in TMEM and an event-driven UMMA issuer
-int launch_attn_fwd_pp2(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int emu,
-                        cudaStream_t stream);
-// variant 15 (16: a quarter of the exponentials on the FMA pipe): "pp2" with SIXTEEN softmax warps (each score row split
-// between two threads); fixed-bound softmax only, hands the online case to the "db" kernel on the device
+// variant 15 (16: a quarter of the exponentials on the FMA pipe): ONE CTA per SM, two q tiles ping-pong against shared
+// 128-row kv tiles, S / P decoupled in TMEM, SIXTEEN softmax warps (each score row split between two threads); fixed-bound
+// softmax only, hands the online case to the "db" kernel on the device
 int launch_attn_fwd_pp3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int emu,
                         cudaStream_t stream);
 int launch_attn_fwd_x3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,

@@ -29,8 +29,6 @@ def _maxnorm(a, b):
 
 
 @pytest.mark.parametrize('variant,fixed', [(0, False), (0, True), (1, False), (1, True), (2, False), (2, True), (3, False), (3, True), (4, False), (4, True), (6, False), (6, True), (7, False), (7, True), (8, False), (8, True),
-                                           (9, False), (9, True), (10, True), (11, False), (11, True),
-                                           (12, False), (12, True), (13, True), (14, False), (14, True),
                                            (15, False), (15, True), (16, True)])
 @pytest.mark.parametrize('B,L', [(1, 128), (2, 256), (1, 200), (2, 1000), (1, 2048), (1, 300), (2, 129)])
 def test_attention_matches_sdpa(B, L, variant, fixed):
