@@ -25,6 +25,9 @@ static constexpr int DB_STAGES = 3;
 static constexpr int DB_SMEM_TILES = DB_T128 + 2 * DB_STAGES * DB_T64;
 static constexpr int DB_ONES = 2048;  // variant 8: [16 x 64] bf16 tile of ones (B operand of the row-sum MMA)
 static constexpr int DB_SMEM_BYTES = DB_SMEM_TILES + DB_ONES + 256;
+// X3 (fp32-grade) layout: Q_hi | Q_lo staging, K x3, (V_hi | V_lo) x3
+static constexpr int DB_SMEM_TILES_X3 = 2 * DB_T128 + DB_STAGES * DB_T64 + 2 * DB_STAGES * DB_T64;
+static constexpr int DB_SMEM_BYTES_X3 = DB_SMEM_TILES_X3 + DB_ONES + 256;
 static constexpr uint32_t DB_TMEM_COLS = 256;
 
 struct AttnDbParams {
@@ -35,7 +38,8 @@ struct AttnDbParams {
   float* lse;
   int B, H, L, dh;
   float scale_log2, scale;
-  int only_if_online;  // 1: return immediately when the bound is finite (the w8 kernel has done the work)
+  int only_if_online;  // 1: return immediately when the bound is finite (another kernel has done the work)
+  int lo_col;          // X3: first column of the lo block of qkv (= 3 * dh)
 };
 
 __device__ __forceinline__ float db_ex2(float x) {
@@ -60,8 +64,19 @@ __device__ __forceinline__ float db_ex2(float x) {
 // QT (variant 7): the Q tile is copied into TMEM once (columns [192, 224)) and is the A operand of S = Q K^T from
 // there (tcgen05.mma .ts), which halves the shared-memory operand reads of the kernel (Q 16 KB + K 8 KB + V 8 KB per
 // kv step -> 16 KB).
-template <bool PF, bool QT, bool DR = false>
+// X3 (needs QT, excludes PF / DR): the fp32-grade attention of precision='fp32' (BASELINE configs[2]) on this kernel's
+// pipeline.  qkv arrives as bf16 (hi | lo) pairs -- [T, 2*3*dh] = hi block | lo block, each (q | k | v) -- and the two
+// products run as  S = Q_hi K_hi^T + Q_lo K_hi^T  and  O += P_hi V_hi + P_hi V_lo : the correction terms that carry the
+// rounding of the operand that is NOT averaged over (q for a score row, v for an output row), four MMA units instead of the
+// six of the full three-term split.  tools/x3_terms_sweep.py (profiles/r02j_x3_terms_sweep.json) measured every subset on
+// the single-buffered kernel this replaces (attn_fwd_x3.cu): this one keeps one forward at 8.7e-5 and the 64-step sampler at
+// 4.0e-5 of the fp32 oracle (tolerance 1e-3; all six units: 1.7e-5 / 2.7e-5; plain bf16 attention: 3.3e-4 / 1.4e-4).  No
+// P_lo and no K_lo exist, so the softmax is the bf16 kernel's except that the row sum is taken over the ROUNDED P (what
+// the MMA multiplies: a row dominated by one key stays exact).  TMEM: ... | Q_hi [192,224) | Q_lo [224,256).  y leaves
+// as (hi | lo) pairs [T, 2*dh].
+template <bool PF, bool QT, bool DR = false, bool X3 = false>
 __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid_constant__ AttnDbParams p) {
+  static_assert(!X3 || (QT && !PF && !DR), "X3 runs on the QT pipeline only");
   extern __shared__ uint8_t smem_raw[];
   if (p.only_if_online && p.bound_log2 != nullptr && *p.bound_log2 < 3.0e38f) return;
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -70,12 +85,13 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
   {
     uint32_t dyn;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    if (pad + DB_SMEM_TILES + DB_ONES + 160 > dyn) __trap();
+    if (pad + (X3 ? DB_SMEM_TILES_X3 : DB_SMEM_TILES) + DB_ONES + 160 > dyn) __trap();
   }
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + DB_T128;
+  constexpr int VT = X3 ? 2 * DB_T64 : DB_T64;  // bytes of one V stage (X3: V_hi | V_lo)
+  uint8_t* sQ = smem;                                // X3: Q_hi | Q_lo
+  uint8_t* sK = sQ + (X3 ? 2 : 1) * DB_T128;
   uint8_t* sV = sK + DB_STAGES * DB_T64;
-  uint8_t* sOnes = sV + DB_STAGES * DB_T64;  // 1024-byte aligned
+  uint8_t* sOnes = sV + DB_STAGES * VT;  // 1024-byte aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + DB_ONES);
   // direct mode (DR): decided once per CTA from the bound
   bool direct = false;
@@ -128,8 +144,9 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(q_full, DB_T128);
+      mbar_expect_tx(q_full, (X3 ? 2 : 1) * DB_T128);
       tma_load_3d(sQ, &p.tma_q, q_full, h * 64, q0, b);
+      if (X3) tma_load_3d(sQ + DB_T128, &p.tma_q, q_full, p.lo_col + h * 64, q0, b);
       int st = 0;
       uint32_t ph = 0;
       for (int j = 0; j < n_kv; ++j) {
@@ -137,8 +154,9 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
         mbar_expect_tx(&k_full[st], DB_T64);
         tma_load_3d(sK + st * DB_T64, &p.tma_kv, &k_full[st], p.dh + h * 64, j * 64, b);
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], DB_T64);
-        tma_load_3d(sV + st * DB_T64, &p.tma_kv, &v_full[st], 2 * p.dh + h * 64, j * 64, b);
+        mbar_expect_tx(&v_full[st], VT);
+        tma_load_3d(sV + st * VT, &p.tma_kv, &v_full[st], 2 * p.dh + h * 64, j * 64, b);
+        if (X3) tma_load_3d(sV + st * VT + DB_T64, &p.tma_kv, &v_full[st], p.lo_col + 2 * p.dh + h * 64, j * 64, b);
         if (++st == DB_STAGES) {
           st = 0;
           ph ^= 1;
@@ -165,6 +183,11 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
           else
             umma_f16_ss(tS, make_smem_desc(aQ + k * 32, 0, 1024), make_smem_desc(aK + k * 32, 0, 1024), idesc_s, k > 0);
         }
+        if (X3) {  // + Q_lo K_hi^T
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ts(tS, tmem_base + 224 + k * 8, make_smem_desc(aK + k * 32, 0, 1024), idesc_s, 1u);
+        }
         umma_commit(&k_empty[st]);
         umma_commit(&s_full[j & 1]);
       };
@@ -181,11 +204,16 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
         mbar_wait(p_full, j & 1);
         mbar_wait(&v_full[st], (j / DB_STAGES) & 1);
         tc_fence_after();
-        const uint32_t aV = smem_u32(sV + st * DB_T64);
+        const uint32_t aV = smem_u32(sV + st * VT);
         const uint32_t tP = tmem_base + (j & 1) * 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ts(tO, tP + k * 8, make_smem_desc(aV + k * 16 * 128, 0, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        if (X3) {  // + P_hi V_lo
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ts(tO, tP + k * 8, make_smem_desc(aV + DB_T64 + k * 16 * 128, 0, 1024), idesc_o, 1u);
+        }
         if (DR && direct) {  // l += P_j x ones  (columns [224, 240))
           const uint32_t aOnes = smem_u32(sOnes);
 #pragma unroll
@@ -225,6 +253,16 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
       }
       __syncwarp();
       tmem_st32(tmem_base + 192 + lane_off, rq);
+      if (X3) {  // the same for this thread's Q_lo row
+        const uint32_t base_lo = base + DB_T128;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(rq[4 * u]), "=r"(rq[4 * u + 1]), "=r"(rq[4 * u + 2]), "=r"(rq[4 * u + 3])
+                       : "r"(base_lo + ((u ^ (row & 7)) << 4)));
+        __syncwarp();
+        tmem_st32(tmem_base + 224 + lane_off, rq);
+      }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -283,10 +321,15 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
           const float2 ea = make_float2(db_ex2(a.x), db_ex2(a.y));
           // half of the exponentials on the FMA pipe (ex2_poly2): the SFU (16 ex2 / clk / SM) is the binding unit at d = 64
           const float2 eb = DB_EMU ? ex2_poly2(bb) : make_float2(db_ex2(bb.x), db_ex2(bb.y));
-          s01 = fadd2(s01, ea);
-          s23 = fadd2(s23, eb);
           pk[i >> 1] = pack_bf16(ea.x, ea.y);
           pk[16 + (i >> 1)] = pack_bf16(eb.x, eb.y);
+          if (X3) {  // normalise by what the MMA multiplies: the bf16-rounded probabilities
+            s01 = fadd2(s01, make_float2(__uint_as_float(pk[i >> 1] << 16), __uint_as_float(pk[i >> 1] & 0xffff0000u)));
+            s23 = fadd2(s23, make_float2(__uint_as_float(pk[16 + (i >> 1)] << 16), __uint_as_float(pk[16 + (i >> 1)] & 0xffff0000u)));
+          } else {
+            s01 = fadd2(s01, ea);
+            s23 = fadd2(s23, eb);
+          }
         }
       } else {
 #pragma unroll
@@ -295,10 +338,15 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
           const float a1 = (i + 1 < valid) ? db_ex2(fmaf(__uint_as_float(r0[i + 1]), c, neg_mc)) : 0.f;
           const float b0 = (32 + i < valid) ? db_ex2(fmaf(__uint_as_float(r1[i]), c, neg_mc)) : 0.f;
           const float b1 = (33 + i < valid) ? db_ex2(fmaf(__uint_as_float(r1[i + 1]), c, neg_mc)) : 0.f;
-          s01 = fadd2(s01, make_float2(a0, a1));
-          s23 = fadd2(s23, make_float2(b0, b1));
           pk[i >> 1] = pack_bf16(a0, a1);
           pk[16 + (i >> 1)] = pack_bf16(b0, b1);
+          if (X3) {
+            s01 = fadd2(s01, make_float2(__uint_as_float(pk[i >> 1] << 16), __uint_as_float(pk[i >> 1] & 0xffff0000u)));
+            s23 = fadd2(s23, make_float2(__uint_as_float(pk[16 + (i >> 1)] << 16), __uint_as_float(pk[16 + (i >> 1)] & 0xffff0000u)));
+          } else {
+            s01 = fadd2(s01, make_float2(a0, a1));
+            s23 = fadd2(s23, make_float2(b0, b1));
+          }
         }
       }
       const float sum = (s01.x + s01.y) + (s23.x + s23.y);
@@ -358,7 +406,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
       __syncwarp();
       tmem_ld32(tO + cch * 32, r);
       tmem_wait_ld();
-      if (ok) {
+      if (ok && !X3) {
         uint4* dst = reinterpret_cast<uint4*>(p.y + ((size_t)b * p.L + q) * p.dh + h * 64 + cch * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -366,6 +414,23 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
                               pack_bf16(__uint_as_float(r[8 * i + 2]) * inv_l, __uint_as_float(r[8 * i + 3]) * inv_l),
                               pack_bf16(__uint_as_float(r[8 * i + 4]) * inv_l, __uint_as_float(r[8 * i + 5]) * inv_l),
                               pack_bf16(__uint_as_float(r[8 * i + 6]) * inv_l, __uint_as_float(r[8 * i + 7]) * inv_l));
+      }
+      if (ok && X3) {  // y as (hi | lo) pairs: [T, 2 * dh]
+        __nv_bfloat16* yrow = p.y + ((size_t)b * p.L + q) * (2 * p.dh) + h * 64 + cch * 32;
+        uint4* dh4 = reinterpret_cast<uint4*>(yrow);
+        uint4* dl4 = reinterpret_cast<uint4*>(yrow + p.dh);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = __uint_as_float(r[8 * i + 2 * e]) * inv_l, v1 = __uint_as_float(r[8 * i + 2 * e + 1]) * inv_l;
+            hw[e] = pack_bf16(v0, v1);
+            lw[e] = pack_bf16(v0 - __uint_as_float(hw[e] << 16), v1 - __uint_as_float(hw[e] & 0xffff0000u));
+          }
+          dh4[i] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          dl4[i] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
       }
     }
     if (ok && p.lse != nullptr) p.lse[((size_t)b * p.H + h) * p.L + q] = m * p.scale + __logf(l);
@@ -381,9 +446,14 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
 
 int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                              int only_if_online, cudaStream_t stream);
-template <bool PF, bool QT, bool DR = false>
+template <bool PF, bool QT, bool DR = false, bool X3 = false>
 static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                                 int only_if_online, cudaStream_t stream);
+// fp32-grade attention (precision='fp32'): qkv bf16 [T, 2*3*dh] (hi block | lo block), y bf16 [T, 2*dh] (hi | lo)
+int launch_attn_fwd_db_x3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                          cudaStream_t stream) {
+  return launch_attn_fwd_db_t<false, true, false, true>(qkv, y, lse, bound_log2, B, L, H, 0, stream);
+}
 int launch_attn_fwd_db(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                        cudaStream_t stream) {
   return launch_attn_fwd_db_t<false, false>(qkv, y, lse, bound_log2, B, L, H, 0, stream);
@@ -404,18 +474,20 @@ int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* 
                              int only_if_online, cudaStream_t stream) {
   return launch_attn_fwd_db_t<false, false>(qkv, y, lse, bound_log2, B, L, H, only_if_online, stream);
 }
-template <bool PF, bool QT, bool DR>
+template <bool PF, bool QT, bool DR, bool X3>
 static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                                 int only_if_online, cudaStream_t stream) {
   OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd_db: bad arguments");
   AttnDbParams p;
   const int dh = H * 64;
-  uint64_t dims[3] = {(uint64_t)3 * dh, (uint64_t)L, (uint64_t)B};
-  uint64_t strides[2] = {(uint64_t)3 * dh * 2, (uint64_t)L * 3 * dh * 2};
+  const uint64_t width = (uint64_t)(X3 ? 6 : 3) * dh;  // X3: (hi block | lo block)
+  uint64_t dims[3] = {width, (uint64_t)L, (uint64_t)B};
+  uint64_t strides[2] = {width * 2, (uint64_t)L * width * 2};
   uint32_t box_q[3] = {64, 128, 1}, box_kv[3] = {64, 64, 1};
   OSD_TRY(make_tmap(&p.tma_q, qkv, 2, 3, dims, strides, box_q));
   OSD_TRY(make_tmap(&p.tma_kv, qkv, 2, 3, dims, strides, box_kv));
   p.bound_log2 = bound_log2;
+  p.lo_col = 3 * dh;
   p.only_if_online = only_if_online;
   p.y = static_cast<__nv_bfloat16*>(y);
   p.lse = lse;
@@ -424,11 +496,12 @@ static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const floa
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   static DeviceOnce once;
   if (once.first()) {
-    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<PF, QT, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES));
+    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<PF, QT, DR, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  X3 ? DB_SMEM_BYTES_X3 : DB_SMEM_BYTES));
   }
   const long long grid = (long long)ceil_div(L, 128) * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_fwd_db: grid too large");
-  attn_fwd_db_kernel<PF, QT, DR><<<(unsigned)grid, DB_THREADS, DB_SMEM_BYTES, stream>>>(p);
+  attn_fwd_db_kernel<PF, QT, DR, X3><<<(unsigned)grid, DB_THREADS, X3 ? DB_SMEM_BYTES_X3 : DB_SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
   return 0;
 }

@@ -123,6 +123,9 @@ int launch_attn_fwd_db_pf(const void* qkv, void* y, float* lse, const float* bou
 // softmax only, hands the online case to the "db" kernel on the device
 int launch_attn_fwd_pp3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int emu,
                         cudaStream_t stream);
+// fp32-grade attention on the db pipeline: S = Q_hi K_hi^T + Q_lo K_hi^T, O += P_hi V_hi + P_hi V_lo (attn_fwd_db.cu, X3)
+int launch_attn_fwd_db_x3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                          cudaStream_t stream);
 int launch_attn_fwd_x3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                        cudaStream_t stream);
 int launch_qk_bound(const float* qw, const float* kw, float* out, cudaStream_t stream);

@@ -168,6 +168,15 @@ static int attn_fwd_variant() {
   return v;
 }
 
+// OSD_X3_KERNEL=old selects the single-buffered fp32-grade attention kernel (attn_fwd_x3.cu, selectable terms) for A/B
+static bool x3_old_kernel() {
+  static const bool v = [] {
+    const char* e = getenv("OSD_X3_KERNEL");
+    return e != nullptr && strcmp(e, "old") == 0;
+  }();
+  return v;
+}
+
 struct FwdCtx {
   const float* const* P;
   PackedW W;
@@ -217,7 +226,8 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
     q.raw_out = c.save ? lb + pl.qkv_raw : nullptr;
     OSD_TRY(launch_gemm(q, s));
     if (X)
-      OSD_TRY(launch_attn_fwd_x3(lb + pl.qkv, lb + pl.y, nullptr, c.W.bound(l), B, L, 16, s));
+      OSD_TRY((x3_old_kernel() ? launch_attn_fwd_x3 : launch_attn_fwd_db_x3)(lb + pl.qkv, lb + pl.y, nullptr, c.W.bound(l), B, L,
+                                                                             16, s));
     else
       OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), c.W.bound(l), B, L, 16,
                               attn_fwd_variant(),

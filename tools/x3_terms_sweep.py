@@ -52,12 +52,18 @@ print('RESULT ' + json.dumps(out))
 ''' % ROOT
 
 res = []
-for qk, pv in ((7, 7), (3, 7), (5, 7), (7, 3), (7, 5), (3, 3), (3, 5), (3, 1), (1, 1)):
-    env = dict(os.environ, OSD_X3_TERMS=f'{qk},{pv}')
+combos = ((7, 7), (3, 7), (5, 7), (7, 3), (7, 5), (3, 3), (3, 5), (3, 1), (1, 1))
+if len(sys.argv) > 1 and sys.argv[1] == 'short':
+    combos = ((7, 7), (3, 5))
+for qk, pv in combos + ((0, 0),):  # (0, 0) = the shipped kernel: the db pipeline with the (3, 5) terms (attn_fwd_db.cu, X3)
+    env = dict(os.environ, OSD_X3_TERMS=f'{qk},{pv}', OSD_X3_KERNEL='old')
+    if (qk, pv) == (0, 0):
+        env.pop('OSD_X3_KERNEL')
     r = subprocess.run([sys.executable, '-c', CHILD], env=env, capture_output=True, text=True, timeout=900)
     line = [ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')]
     d = json.loads(line[0][7:]) if line else {'error': (r.stderr or r.stdout)[-500:]}
-    d.update(qk_mask=qk, pv_mask=pv, mma_units=bin(qk).count('1') + bin(pv).count('1'))
+    d.update(qk_mask=qk or 3, pv_mask=pv or 5, mma_units=bin(qk or 3).count('1') + bin(pv or 5).count('1'),
+             kernel='attn_fwd_db_kernel<X3>' if (qk, pv) == (0, 0) else 'attn_fwd_x3_kernel')
     res.append(d)
     print(json.dumps(d), flush=True)
 json.dump(res, open(os.path.join(ROOT, 'gpurun_out', 'x3_terms_sweep.json'), 'w'), indent=1)
