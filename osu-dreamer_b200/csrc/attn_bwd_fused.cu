@@ -21,6 +21,8 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace osd {
 
 static constexpr int FB_THREADS = 320;
@@ -51,6 +53,7 @@ struct AttnBwdFusedParams {
   __nv_bfloat16* dqkv;  // [B*L, 3*dh]: this kernel writes the dk and dv column blocks
   int B, H, L, Lp, dh;
   float scale, scale_log2;
+  int debug_skip;  // timing experiments only (OSD_FB_SKIP): 1 = no dQ reduce-add (results wrong)
   unsigned long long* trace;  // nullable (tools/trace_attn_bwd.py): event timeline of one CTA, 3 writers x 1024 records
   int trace_cta;
 };
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
                      : "memory");
     };
     auto drain_issue = [&](int qj) {
-      if (lane == 0) {
+      if (lane == 0 && !(p.debug_skip & 1)) {
         tma_reduce_add_3d(&p.tma_dq, stg, h * 64 + grp * 32, qj * 128 + quad * 32, b);
         tma_store_commit();
       }
@@ -583,6 +586,11 @@ int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const 
   p.B = B; p.H = H; p.L = L; p.Lp = Lp; p.dh = dh;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  static const int dbg_skip = [] {
+    const char* e = getenv("OSD_FB_SKIP");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  p.debug_skip = dbg_skip;
   p.trace = g_fb_trace;
   p.trace_cta = g_fb_trace_cta;
   static DeviceOnce once;
