@@ -1,4 +1,4 @@
-"""BASELINE config 5: seq_len sweep {2048, 4096, 8192, 16384}, batch 8, one GPU: train-step (fwd+bwd+optimizer)
+"""BASELINE config 5: seq_len sweep {2048, 4096, 8192, 16384}, batch 8, one GPU (+ the reference's own shapes): train-step (fwd+bwd+optimizer)
 and forward-only time, algorithmic TFLOP/s and algorithmic HBM GB/s against the measured peaks."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,8 +18,9 @@ sd = O.make_state_dict(1234)
 tr.diffusion.load_state_dict(sd)
 tr.diffusion_ema.module.load_state_dict(sd)
 tr = tr.cuda()
-B = 8
-for L in (2048, 4096, 8192, 16384):
+# BASELINE configs[4] (B = 8) plus the shapes the reference itself runs: fit-denoiser at batch 128 x 152 frames
+# (models/diffusion/model.yml:44,47) and predict on a ~4-minute song (l ~ 1500 latent frames, a few difficulties)
+for B, L in ((8, 2048), (8, 4096), (8, 8192), (8, 16384), (128, 152), (4, 1482)):
     g = torch.Generator().manual_seed(L)
     h = torch.randn(B, 128, L, generator=g).cuda()
     x1 = torch.randn(B, 6, L, generator=g)
