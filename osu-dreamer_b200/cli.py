@@ -323,7 +323,7 @@ def fit_style(config: str, ckpt_path: str | None, synthetic: bool, max_steps: in
                 break
         if val_sets and rank == 0:  # the style validation compares the whole validation set at once (train.py:120-150)
             tr.on_validation_epoch_start()
-            for vb in LatentWindows(val_sets, d['seq_len']):
+            for vb in LatentWindows(val_sets, None):  # full maps, one per item (data/modules/latent.py:52, seq_len=None)
                 tr.validation_step(tuple(t[None].cuda() for t in vb))
             vals = tr.on_validation_epoch_end()
             print(f'epoch {epoch} ' + ' '.join(f'{k} {float(v):.4f}' for k, v in vals.items()), flush=True)

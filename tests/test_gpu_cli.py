@@ -72,3 +72,40 @@ def test_fit_resume_export_sample(tmp_path):
     m = m.cuda().eval()
     x = m.sample(torch.randn(1, 128, 200, device='cuda'), torch.randn(3, 32, device='cuda'), 4)
     assert x.shape == (3, 6, 200) and torch.isfinite(x).all()
+
+
+def test_fit_style_resume_export(tmp_path):
+    """fit-style through the CLI on a cached dataset (reference flow: scripts/fit_style.py:17-31, models/style/train.py):
+    training steps, the whole-set validation (val/energy_dist selects the kept checkpoint), resume, and the exported
+    artifact's style.* weights loading strictly into the style mirror and sampling"""
+    import os
+    from click.testing import CliRunner
+    from osu_dreamer_b200.cli import main
+    from osu_dreamer_b200.style import StyleModel, StyleModelArgs
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = yaml.safe_load(open(os.path.join(root, 'osu-dreamer_b200', 'style.yml')))
+    _make_cache(tmp_path / 'data', n_sets=12, maps_per_set=4)
+    cfg['data'].update(batch_size=8, max_val_count=6, shuffle_buffer_size=8, data_path=str(tmp_path / 'data'))
+    cfg['trainer'].update(log_every_n_steps=1, max_epochs=2)
+    cfg_path = tmp_path / 'style_cfg.yml'
+    yaml.safe_dump(cfg, open(cfg_path, 'w'))
+    ck1, ck2 = str(tmp_path / 's1.ckpt'), str(tmp_path / 's2.ckpt')
+    r = CliRunner().invoke(main, ['fit-style', '-c', str(cfg_path), '--max-steps', '5', '--out', ck1], catch_exceptions=False)
+    assert r.exit_code == 0, r.output
+    assert 'step 5 ' in r.output and 'val/energy_dist' in r.output and 'train/u_mape' in r.output
+    a = torch.load(ck1, weights_only=True)
+    assert len(a['state_dict']) == 121 and a['optimizer_state']['step'] == a['global_step']
+    assert all(torch.isfinite(v).all() for v in a['state_dict'].values())
+    assert a['hyper_parameters']['style_args']['h_dim'] == 256
+    r = CliRunner().invoke(main, ['fit-style', '-c', str(cfg_path), '--ckpt-path', ck1, '--max-steps', str(a['global_step'] + 3),
+                                  '--out', ck2], catch_exceptions=False)
+    assert r.exit_code == 0, r.output
+    b = torch.load(ck2, weights_only=True) if os.path.exists(ck2) else None
+    assert b is not None and b['global_step'] == a['global_step'] + 3 and b['epoch'] > a['epoch']
+    assert not torch.equal(a['state_dict']['style.blocks.3.0.weight'], b['state_dict']['style.blocks.3.0.weight'])
+    # the EMA weights are what export-inference ships as style.* (models/inference/artifact.py:31-35)
+    sd = {k[len('style_ema.module.'):]: v for k, v in b['state_dict'].items() if k.startswith('style_ema.module.')}
+    m = StyleModel(32, StyleModelArgs(**b['hyper_parameters']['style_args']))
+    m.load_state_dict(sd, strict=True)
+    s = m.cuda().eval().sample(10 * torch.rand(5, 5, device='cuda'), 16)
+    assert s.shape == (5, 32) and torch.isfinite(s).all()
