@@ -170,34 +170,56 @@ int launch_linear_small(const float* in, const float* W, const float* bias, floa
 
 // ------------------------------------------------------------------------------------------------
 // proj_in (model.py:48,95): x[t][c] = b[c] + sum_e W[c][e] * xt[b][e][l];  xt channels-first fp32.
-__global__ void proj_in_kernel(const float* __restrict__ xt, const float* __restrict__ W,
-                               const float* __restrict__ bias, float* __restrict__ x, int L, int T) {
-  // block: 256 threads = 8 tokens x 32 lanes; each lane produces 16 channels (4 float4)
-  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+// A warp keeps the weights of its lanes' 16 channels in registers (16 x 6 + 16 bias) and walks 32 consecutive tokens: the six
+// inputs of those tokens are six coalesced loads (lane j = token j) handed round by shuffles, so per token the warp issues
+// 6 SHFL + 96 FMA + 4 16-byte stores -- the kernel is bound by its 2 KB/token of output (it was bound by 112 weight loads
+// per token: 0.46 ms at B = 16, L = 8192 against 0.04 ms of HBM time).
+static constexpr int PIN_TOK = 32;
+__global__ void __launch_bounds__(256) proj_in_kernel(const float* __restrict__ xt, const float* __restrict__ W,
+                                                      const float* __restrict__ bias, float* __restrict__ x, int L, int T) {
   const int lane = threadIdx.x & 31;
-  if (t >= T) return;
-  const int b = t / L, l = t % L;
-  float in[6];
+  const int t0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * PIN_TOK;
+  if (t0 >= T) return;
+  float w[16][6], bb[16];
 #pragma unroll
-  for (int e = 0; e < 6; ++e) in[e] = __ldg(xt + ((size_t)b * 6 + e) * L + l);
-#pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const int c0 = v * 128 + lane * 4;
-    float o[4];
+  for (int v = 0; v < 4; ++v)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int c = c0 + i;
-      float acc = __ldg(bias + c);
+      const int c = v * 128 + lane * 4 + i;
+      bb[4 * v + i] = __ldg(bias + c);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) acc = fmaf(__ldg(W + c * 6 + e), in[e], acc);
-      o[i] = acc;
+      for (int e = 0; e < 6; ++e) w[4 * v + i][e] = __ldg(W + c * 6 + e);
     }
-    *reinterpret_cast<float4*>(x + (size_t)t * D + c0) = make_float4(o[0], o[1], o[2], o[3]);
+  float in[6];
+  {
+    const int t = t0 + lane;
+    const int b = t / L, l = t - b * L;  // a warp's 32 tokens may straddle two samples: per-lane addressing
+#pragma unroll
+    for (int e = 0; e < 6; ++e) in[e] = t < T ? __ldg(xt + ((size_t)b * 6 + e) * L + l) : 0.f;
+  }
+  const int n = min(PIN_TOK, T - t0);
+  for (int k = 0; k < n; ++k) {
+    float xin[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) xin[e] = __shfl_sync(0xffffffffu, in[e], k);
+    float* row = x + (size_t)(t0 + k) * D;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float acc = bb[4 * v + i];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) acc = fmaf(w[4 * v + i][e], xin[e], acc);
+        o[i] = acc;
+      }
+      *reinterpret_cast<float4*>(row + v * 128 + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 int launch_proj_in(const float* xt, const float* W, const float* bias, float* x, int B, int L, cudaStream_t stream) {
   const int T = B * L;
-  proj_in_kernel<<<ceil_div(T, 8), 256, 0, stream>>>(xt, W, bias, x, L, T);
+  proj_in_kernel<<<ceil_div(T, 8 * PIN_TOK), 256, 0, stream>>>(xt, W, bias, x, L, T);
   OSD_LAUNCHED();
   return 0;
 }
