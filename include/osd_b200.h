@@ -98,13 +98,12 @@ OSD_API size_t osd_rope_table_floats(int L);
  * bound_log2: optional DEVICE scalar, an upper bound of the scaled scores in log2 units (q,k are RMS-normalised
  * in this model, so such a bound exists per layer): selects the fixed-max softmax; NULL -> online softmax.
  * variant: 7 is the kernel the model runs (128 q rows per CTA, 64-row kv tiles, two S accumulators ping-pong, Q tile
- * resident in TMEM, 2 CTAs per SM; csrc/attn_fwd_db.cu).  The others are kept for A/B measurements: 0 / 1 = single-S
- * kernel with 64- / 128-row kv tiles and P staged in shared memory, 2 / 3 = the same with P kept in TMEM
- * (csrc/attn_fwd.cu); 4 = double-buffered S with Q in shared memory, 6 = 4 + early barrier probes and S prefetch,
- * 8 = 7 + pre-scaled Q and row sums by a ones-tile MMA (csrc/attn_fwd_db.cu); 15 = the cuDNN-shaped layout: one CTA per SM,
- * two q tiles ping-pong against shared 128-row kv tiles, S / P decoupled in TMEM, sixteen softmax warps (16 = the same with a
- * quarter of the exponentials on the FMA pipe; csrc/attn_fwd_pp3.cu) -- within 1 % of variant 7 in time because both sit
- * at the board's power cap.  Anything else is an error. */
+ * resident in TMEM, 2 CTAs per SM; csrc/attn_fwd_db.cu).  Kept for A/B measurements: 4 = the same with Q in shared memory,
+ * 6 = 4 + early barrier probes and S prefetch, 8 = 7 + pre-scaled Q and row sums by a ones-tile MMA (template siblings in the
+ * same file); 15 = the cuDNN-shaped layout: one CTA per SM, two q tiles ping-pong against shared 128-row kv tiles, S / P
+ * decoupled in TMEM, sixteen softmax warps (16 = the same with a quarter of the exponentials on the FMA pipe;
+ * csrc/attn_fwd_pp3.cu) -- within 1 % of variant 7 in time because both sit at the board's power cap.
+ * Anything else is an error. */
 OSD_API int osd_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                          int variant, void* stream);
 

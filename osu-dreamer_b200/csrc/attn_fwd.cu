@@ -1,405 +1,22 @@
-// Bidirectional (non-causal) flash attention forward on tcgen05 for head_dim 64, bf16 operands.
-// Replaces F.scaled_dot_product_attention(q, k, v) at osu_dreamer/common/attn.py:82 of the reference.
-//
-// One CTA = one 128-row query tile of one (batch, head); two CTAs are resident per SM so the softmax of
-// one overlaps the MMAs of the other.
-//   warp 0     : TMA producer  (Q once; K_j, V_j double-buffered, straight out of the token-major
-//                qkv buffer [B*L, 3072] through a 3-D tensor map -> rows past L are zero-filled)
-//   warp 1     : UMMA issuer   S = Q K_j^T  (128x128x64, both operands K-major)
-//                              O += P V_j   (128x64x128, P K-major from smem, V MN-major)
-//   warps 2..5 : online softmax, one thread per query row: TMEM S -> exp2 -> bf16 P in smem (SW128),
-//                O rescale in TMEM when the running max moves, final O / l -> y, log-sum-exp -> lse.
-// TMEM: S fp32 [128 lanes x 128 cols] at column 0, O fp32 [128 x 64] at column 128 (256 allocated).
+// Forward attention dispatch.  The kernels live in attn_fwd_db.cu (the model's: variant 7, and its A/B template siblings 4 / 6 /
+// 8) and attn_fwd_pp3.cu (the cuDNN-shaped layout: 15 / 16).  The first-generation single-accumulator kernels (variants 0-3:
+// 64- / 128-row kv tiles, P staged in shared memory or kept in TMEM) were removed in round 2 once the design had settled;
+// their measurements are in DESIGN.md 5.
 #include "kernels.cuh"
-#include "ptx.cuh"
 
 namespace osd {
 
-static constexpr int AT_BQ = 128;
-static constexpr int AT_D = 64;
-static constexpr int AT_THREADS = 192;
-static constexpr int AT_TILE = 128 * 128;  // bytes of a [128 x 64] bf16 tile
-// BKV = kv rows per tile: 128 -> 2 CTAs/SM (112 KB smem, 256 TMEM columns), 64 -> 3 CTAs/SM (64 KB, 128 columns)
-// PT = keep P in tensor memory (bf16, two per 32-bit column, row = lane) and feed it to the P*V MMA as the
-// A operand straight from TMEM: no P staging in shared memory (which otherwise costs a 32 KB store + 32 KB
-// operand read per 128x128 tile against a 128 B/clk shared-memory port).
-//   BKV=128, PT: S cols [0,128) | P [128,192) | O [192,256)      (S_{j+1} may be issued before P_j V_j)
-//   BKV=64,  PT: S cols [0,64), P aliases S cols [0,32) | O [64,128)   (P_j V_j is issued before S_{j+1})
-template <int BKV, bool PT>
-struct AtCfg {
-  static constexpr int KV_TILE = BKV * 128;               // bytes of a [BKV x 64] bf16 tile
-  static constexpr int P_BYTES = PT ? 0 : (BKV / 64) * AT_TILE;  // [128 q x BKV] bf16 as 64-column sub-tiles
-  static constexpr int SMEM_TILES = AT_TILE + 4 * KV_TILE + P_BYTES;
-  static constexpr int SMEM_BYTES = SMEM_TILES + 256;     // + barriers; base must be 1024-aligned (checked)
-  static constexpr uint32_t TMEM_COLS = (BKV == 128) ? 256 : 128;
-  static constexpr uint32_t S_COL = 0;
-  static constexpr uint32_t P_COL = (BKV == 128) ? 128 : 0;
-  static constexpr uint32_t O_COL = (BKV == 128 && PT) ? 192 : BKV;
-  static constexpr bool P_ALIASES_S = PT && BKV == 64;
-  static constexpr int CTAS = (BKV == 128) ? 2 : (PT ? 4 : 3);
-};
-
-struct AttnFwdParams {
-  CUtensorMap tma_qkv;  // dims (3*dh, L, B), box (64, 128, 1), bf16, SW128  (Q tiles)
-  CUtensorMap tma_kv;   // same tensor, box (64, BKV, 1)                       (K / V tiles)
-  const float* bound_log2;  // optional device scalar: upper bound of the scaled scores in log2 units (fixed-max
-                            // softmax, no running max / O rescale); NULL or a non-finite value -> online softmax
-  __nv_bfloat16* y;     // [B*L, dh]
-  float* lse;           // [B, H, L]
-  int B, H, L;
-  int dh;               // H * 64
-  float scale_log2;     // (1/sqrt(64)) * log2(e)
-  float scale;          // 1/sqrt(64)
-};
-
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-template <int BKV, bool PT>
-__global__ void __launch_bounds__(AT_THREADS, AtCfg<BKV, PT>::CTAS) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
-  using C = AtCfg<BKV, PT>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
-  uint8_t* smem = smem_raw + pad;
-  {
-    uint32_t dyn;
-    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    if (pad + C::SMEM_TILES + 128 > dyn) {
-      if (threadIdx.x == 0) printf("osd attn_fwd: dynamic smem base misaligned (pad %u)\n", pad);
-      __trap();
-    }
-  }
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + AT_TILE;
-  uint8_t* sV = sK + 2 * C::KV_TILE;
-  uint8_t* sP = sV + 2 * C::KV_TILE;  // [BKV/64 sub-tiles of 128 rows x 64 kv] bf16, K-major SW128
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + C::P_BYTES);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* k_empty = bars + 3;  // [2]
-  uint64_t* v_full = bars + 5;   // [2]
-  uint64_t* v_empty = bars + 7;  // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* s_empty = bars + 10;
-  uint64_t* p_full = bars + 11;
-  uint64_t* o_ready = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  const int n_qt = (p.L + AT_BQ - 1) / AT_BQ;
-  const int qt = blockIdx.x % n_qt;
-  const int bh = blockIdx.x / n_qt;
-  const int h = bh % p.H;
-  const int b = bh / p.H;
-  const int q0 = qt * AT_BQ;
-  const int n_kv = (p.L + BKV - 1) / BKV;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tma_qkv);
-    tma_prefetch_desc(&p.tma_kv);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);
-    mbar_init(p_full, 4);
-    mbar_init(o_ready, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ============================================================ TMA producer
-    if (elect_one()) {
-      mbar_expect_tx(q_full, AT_TILE);
-      tma_load_3d(sQ, &p.tma_qkv, q_full, h * AT_D, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], C::KV_TILE);
-        tma_load_3d(sK + st * C::KV_TILE, &p.tma_kv, &k_full[st], p.dh + h * AT_D, j * BKV, b);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], C::KV_TILE);
-        tma_load_3d(sV + st * C::KV_TILE, &p.tma_kv, &v_full[st], 2 * p.dh + h * AT_D, j * BKV, b);
-      }
-    }
-  } else if (warp == 1) {
-    // ============================================================ UMMA issuer
-    if (elect_one()) {
-      const uint32_t idesc_s = make_idesc(FMT_BF16, 0, 0, 128, BKV);
-      const uint32_t idesc_o = make_idesc(FMT_BF16, 0, 1, 128, 64);
-      const uint32_t aQ = smem_u32(sQ);
-      const uint32_t aP = smem_u32(sP);
-      const uint32_t tS = tmem_base + C::S_COL;
-      const uint32_t tO = tmem_base + C::O_COL;
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&k_full[st], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t aK = smem_u32(sK + st * C::KV_TILE);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tS, make_smem_desc(aQ + k * 32, 0, 1024), make_smem_desc(aK + k * 32, 0, 1024), idesc_s,
-                      k > 0 ? 1u : 0u);
-        umma_commit(&k_empty[st]);
-        umma_commit(s_full);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      const uint32_t tP = tmem_base + C::P_COL;
-      for (int j = 0; j < n_kv; ++j) {
-        if (!C::P_ALIASES_S && j + 1 < n_kv) {
-          mbar_wait(s_empty, j & 1);  // softmax has consumed S_j
-          tc_fence_after();
-          issue_s(j + 1);
-        }
-        const int st = j & 1;
-        mbar_wait(p_full, j & 1);
-        mbar_wait(&v_full[st], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t aV = smem_u32(sV + st * C::KV_TILE);
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          // V: MN-major B operand, 16 kv rows (2 KB) per K step
-          const uint64_t vd = make_smem_desc(aV + k * 16 * 128, 0, 1024);
-          if (PT) {
-            umma_f16_ts(tO, tP + k * 8, vd, idesc_o, (j > 0 || k > 0) ? 1u : 0u);  // 16 bf16 = 8 columns per step
-          } else {
-            // P: K-major smem, 64-column sub-tiles of 16 KB
-            const uint64_t pd = make_smem_desc(aP + (k >> 2) * AT_TILE + (k & 3) * 32, 0, 1024);
-            umma_f16_ss(tO, pd, vd, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(&v_empty[st]);
-        umma_commit(o_ready);
-        if (C::P_ALIASES_S && j + 1 < n_kv) issue_s(j + 1);  // tensor pipe is in order: S_{j+1} overwrites P_j after use
-      }
-    }
-  } else {
-    // ============================================================ softmax / correction / epilogue
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tS = tmem_base + C::S_COL + lane_off;
-    const uint32_t tO = tmem_base + C::O_COL + lane_off;
-    const uint32_t tP = tmem_base + C::P_COL + lane_off;
-    const float c = p.scale_log2;
-    // fixed-max mode: q and k are RMS-normalised (attn.py:77-78), so the scaled scores are bounded by a
-    // per-layer constant; softmax is shift-invariant, so exp2(s*c - bound) needs no running max and O is
-    // never rescaled.  Falls back to the online softmax when no finite bound is supplied.
-    float bound = INFINITY;
-    if (p.bound_log2 != nullptr) bound = __ldg(p.bound_log2);
-    const bool fixed = bound < 3.0e38f;
-    float m = fixed ? bound / c : -INFINITY, l = 0.f;
-    const uint32_t sP_row = smem_u32(sP) + row * 128;
-    const int sw = row & 7;
-
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      const int valid = p.L - j * BKV;  // kv columns >= valid are padding (only the last tile)
-      float m_new = m, alpha = 1.0f;
-      if (!fixed) {
-        // ---- pass 1: row max
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int cch = 0; cch < BKV / 32; ++cch) {
-          uint32_t r[32];
-          __syncwarp();
-          tmem_ld32(tS + cch * 32, r);
-          tmem_wait_ld();
-          if (valid >= BKV) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (cch * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-          }
-        }
-        m_new = fmaxf(m, mx);
-        alpha = ex2((m - m_new) * c);
-      }
-      const float neg_mc = -m_new * c;
-      // ---- O correction (needs P V_{j-1} complete; also guarantees the P buffer is free)
-      if (j > 0) {
-        mbar_wait(o_ready, (j - 1) & 1);
-        tc_fence_after();
-        if (!fixed && __any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-          for (int cch = 0; cch < 2; ++cch) {
-            uint32_t r[32];
-            __syncwarp();
-            tmem_ld32(tO + cch * 32, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st32(tO + cch * 32, r);
-          }
-          tmem_wait_st();
-        }
-      }
-      // ---- pass 2: P = exp2(S*c - m*c) -> bf16 smem (SW128 K-major), row sum
-      float sum = 0.f;
-#pragma unroll 1
-      for (int cch = 0; cch < BKV / 32; ++cch) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld32(tS + cch * 32, r);
-        tmem_wait_ld();
-        float pv[32];
-        if (valid >= BKV) {
-          const float2 c2 = make_float2(c, c), n2 = make_float2(neg_mc, neg_mc);
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float2 a = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, n2);
-            pv[i] = ex2(a.x);
-            pv[i + 1] = ex2(a.y);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            pv[i] = (cch * 32 + i < valid) ? ex2(fmaf(__uint_as_float(r[i]), c, neg_mc)) : 0.f;
-        }
-        {  // four independent partial sums: the serial FADD chain was a visible stall
-          float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            s01 = fadd2(s01, make_float2(pv[i], pv[i + 1]));
-            s23 = fadd2(s23, make_float2(pv[i + 2], pv[i + 3]));
-          }
-          sum += (s01.x + s01.y) + (s23.x + s23.y);
-        }
-        if (PT) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
-          tmem_st16(tP + cch * 16, pk);
-        } else {
-          const uint32_t sub = sP_row + (cch >> 1) * AT_TILE;
-#pragma unroll
-          for (int u4 = 0; u4 < 4; ++u4) {
-            const int u = (cch & 1) * 4 + u4;  // 16-byte unit inside the 128-byte row
-            const uint32_t addr = sub + ((u ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                         "r"(pack_bf16(pv[u4 * 8 + 0], pv[u4 * 8 + 1])), "r"(pack_bf16(pv[u4 * 8 + 2], pv[u4 * 8 + 3])),
-                         "r"(pack_bf16(pv[u4 * 8 + 4], pv[u4 * 8 + 5])), "r"(pack_bf16(pv[u4 * 8 + 6], pv[u4 * 8 + 7]))
-                         : "memory");
-          }
-        }
-      }
-      if (PT) tmem_wait_st();
-      l = l * alpha + sum;
-      m = m_new;
-      tc_fence_before();
-      if (!PT) fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (!C::P_ALIASES_S) mbar_arrive(s_empty);
-        mbar_arrive(p_full);
-      }
-    }
-    // ---- epilogue: y = O / l, lse = m*scale + ln(l)
-    mbar_wait(o_ready, (n_kv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l;
-    const int q = q0 + row;
-    const bool ok = q < p.L;
-#pragma unroll 1
-    for (int cch = 0; cch < 2; ++cch) {
-      uint32_t r[32];
-      __syncwarp();
-      tmem_ld32(tO + cch * 32, r);
-      tmem_wait_ld();
-      if (ok) {
-        uint4* dst = reinterpret_cast<uint4*>(p.y + ((size_t)b * p.L + q) * p.dh + h * AT_D + cch * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          dst[i] = make_uint4(pack_bf16(__uint_as_float(r[8 * i]) * inv_l, __uint_as_float(r[8 * i + 1]) * inv_l),
-                              pack_bf16(__uint_as_float(r[8 * i + 2]) * inv_l, __uint_as_float(r[8 * i + 3]) * inv_l),
-                              pack_bf16(__uint_as_float(r[8 * i + 4]) * inv_l, __uint_as_float(r[8 * i + 5]) * inv_l),
-                              pack_bf16(__uint_as_float(r[8 * i + 6]) * inv_l, __uint_as_float(r[8 * i + 7]) * inv_l));
-      }
-    }
-    if (ok && p.lse != nullptr) p.lse[((size_t)b * p.H + h) * p.L + q] = m * p.scale + __logf(l);
-    tc_fence_before();
-  }
-
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 1) {
-    __syncwarp();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
-  }
-}
-
-template <int BKV, bool PT>
-static int launch_attn_fwd_t(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
-                             cudaStream_t stream) {
-  using C = AtCfg<BKV, PT>;
-  AttnFwdParams p;
-  const int dh = H * AT_D;
-  uint64_t dims[3] = {(uint64_t)3 * dh, (uint64_t)L, (uint64_t)B};
-  uint64_t strides[2] = {(uint64_t)3 * dh * 2, (uint64_t)L * 3 * dh * 2};
-  uint32_t box[3] = {64, 128, 1};
-  uint32_t box_kv[3] = {64, (uint32_t)BKV, 1};
-  OSD_TRY(make_tmap(&p.tma_qkv, qkv, 2, 3, dims, strides, box));
-  OSD_TRY(make_tmap(&p.tma_kv, qkv, 2, 3, dims, strides, box_kv));
-  p.bound_log2 = bound_log2;
-  p.y = static_cast<__nv_bfloat16*>(y);
-  p.lse = lse;
-  p.B = B;
-  p.H = H;
-  p.L = L;
-  p.dh = dh;
-  p.scale = 0.125f;
-  p.scale_log2 = 0.125f * 1.4426950408889634f;
-  static DeviceOnce once;
-  if (once.first()) {
-    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<BKV, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  }
-  const int n_qt = ceil_div(L, AT_BQ);
-  const long long grid = (long long)n_qt * H * B;
-  OSD_CHECK(grid < (1ll << 31), "attn_fwd: grid too large");
-  attn_fwd_kernel<BKV, PT><<<(unsigned)grid, AT_THREADS, C::SMEM_BYTES, stream>>>(p);
-  OSD_LAUNCHED();
-  return 0;
-}
-
-// variant: 0 = BKV 64 / P in smem (3 CTAs/SM), 1 = BKV 128 / P in smem (2 CTAs/SM),
-//          2 = BKV 64 / P in TMEM aliasing S, 3 = BKV 128 / P in TMEM
 int launch_attn_fwd(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int variant,
                     cudaStream_t stream) {
   OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd: bad arguments");
-  if (variant == 15) return launch_attn_fwd_pp3(qkv, y, lse, bound_log2, B, L, H, -1, stream);  // 2 q tiles / CTA, 16 softmax warps
+  if (variant == 7) return launch_attn_fwd_db_qt(qkv, y, lse, bound_log2, B, L, H, stream);        // Q in TMEM: the model's kernel
+  if (variant == 15) return launch_attn_fwd_pp3(qkv, y, lse, bound_log2, B, L, H, -1, stream);     // 2 q tiles / CTA, 16 softmax warps
   if (variant == 16) return launch_attn_fwd_pp3(qkv, y, lse, bound_log2, B, L, H, 1, stream);
-  if (variant == 4) return launch_attn_fwd_db(qkv, y, lse, bound_log2, B, L, H, stream);  // double-buffered S
-  if (variant == 8) return launch_attn_fwd_db_dr(qkv, y, lse, bound_log2, B, L, H, stream);  // direct exponent
-  if (variant == 7) return launch_attn_fwd_db_qt(qkv, y, lse, bound_log2, B, L, H, stream);  // Q in TMEM
-  if (variant == 6) return launch_attn_fwd_db_pf(qkv, y, lse, bound_log2, B, L, H, stream);  // + probes / S prefetch
-  if (variant == 1) return launch_attn_fwd_t<128, false>(qkv, y, lse, bound_log2, B, L, H, stream);
-  if (variant == 2) return launch_attn_fwd_t<64, true>(qkv, y, lse, bound_log2, B, L, H, stream);
-  if (variant == 3) return launch_attn_fwd_t<128, true>(qkv, y, lse, bound_log2, B, L, H, stream);
-  OSD_CHECK(variant == 0, "attn_fwd: unknown variant %d (0-4, 6-8, 15, 16)", variant);
-  return launch_attn_fwd_t<64, false>(qkv, y, lse, bound_log2, B, L, H, stream);
+  if (variant == 4) return launch_attn_fwd_db(qkv, y, lse, bound_log2, B, L, H, stream);           // double-buffered S, Q in smem
+  if (variant == 6) return launch_attn_fwd_db_pf(qkv, y, lse, bound_log2, B, L, H, stream);        // + probes / S prefetch
+  if (variant == 8) return launch_attn_fwd_db_dr(qkv, y, lse, bound_log2, B, L, H, stream);        // + direct exponent
+  OSD_CHECK(false, "attn_fwd: unknown variant %d (4, 6, 7, 8, 15, 16)", variant);
+  return 1;
 }
 
 }  // namespace osd

@@ -28,11 +28,11 @@ def _maxnorm(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
 
 
-@pytest.mark.parametrize('variant,fixed', [(0, False), (0, True), (1, False), (1, True), (2, False), (2, True), (3, False), (3, True), (4, False), (4, True), (6, False), (6, True), (7, False), (7, True), (8, False), (8, True),
+@pytest.mark.parametrize('variant,fixed', [(4, False), (4, True), (6, False), (6, True), (7, False), (7, True), (8, False), (8, True),
                                            (15, False), (15, True), (16, True)])
 @pytest.mark.parametrize('B,L', [(1, 128), (2, 256), (1, 200), (2, 1000), (1, 2048), (1, 300), (2, 129)])
 def test_attention_matches_sdpa(B, L, variant, fixed):
-    """both tile shapes, online softmax and the fixed-bound softmax (randn scores/8 stay far below 2^14)"""
+    """every dispatchable forward kernel, online softmax and the fixed-bound softmax (randn scores/8 stay far below 2^14)"""
     from osu_dreamer_b200 import lib
     g = torch.Generator().manual_seed(L)
     qkv = torch.randn(B * L, 3072, generator=g).cuda().to(torch.bfloat16)
