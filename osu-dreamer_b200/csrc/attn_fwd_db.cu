@@ -70,7 +70,7 @@ __device__ __forceinline__ float db_ex2(float x) {
 // rounding of the operand that is NOT averaged over (q for a score row, v for an output row), four MMA units instead of the
 // six of the full three-term split.  tools/x3_terms_sweep.py (profiles/r02j_x3_terms_sweep.json) measured every subset on
 // the single-buffered kernel this replaces (attn_fwd_x3.cu): this one keeps one forward at 8.7e-5 and the 64-step sampler at
-// 4.0e-5 of the fp32 oracle (tolerance 1e-3; all six units: 1.7e-5 / 2.7e-5; plain bf16 attention: 3.3e-4 / 1.4e-4).  No
+// 4.0e-5 of the fp32 reference (tolerance 1e-3; all six units: 1.7e-5 / 2.7e-5; plain bf16 attention: 3.3e-4 / 1.4e-4).  No
 // P_lo and no K_lo exist, so the softmax is the bf16 kernel's except that the row sum is taken over the ROUNDED P (what
 // the MMA multiplies: a row dominated by one key stays exact).  TMEM: ... | Q_hi [192,224) | Q_lo [224,256).  y leaves
 // as (hi | lo) pairs [T, 2*dh].
