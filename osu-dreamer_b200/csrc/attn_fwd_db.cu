@@ -74,9 +74,15 @@ __device__ __forceinline__ float db_ex2(float x) {
 // P_lo and no K_lo exist, so the softmax is the bf16 kernel's except that the row sum is taken over the ROUNDED P (what
 // the MMA multiplies: a row dominated by one key stays exact).  TMEM: ... | Q_hi [192,224) | Q_lo [224,256).  y leaves
 // as (hi | lo) pairs [T, 2*dh].
-template <bool PF, bool QT, bool DR = false, bool X3 = false>
+// MC (variant 17, needs QT): the CTAs of two adjacent q tiles of one (b, h) form a thread-block cluster and share every K / V
+// tile: each loads HALF of it (32 of the 64 kv rows) and TMA-multicasts that half into both CTAs' shared memory, so the
+// L2 -> SM traffic of the kernel halves (34.6 -> 17.3 GB per launch at B = 16, L = 8192) -- the kernel is energy bound
+// (DESIGN.md 5b), bytes are time.  A stage is refilled only when BOTH CTAs' MMAs have read it: the empty barriers count two
+// arrivals and the tcgen05.commit that releases a stage is multicast to the pair.
+template <bool PF, bool QT, bool DR = false, bool X3 = false, bool MC = false>
 __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid_constant__ AttnDbParams p) {
   static_assert(!X3 || (QT && !PF && !DR), "X3 runs on the QT pipeline only");
+  static_assert(!MC || (QT && !PF && !DR && !X3), "MC runs on the plain QT pipeline only");
   extern __shared__ uint8_t smem_raw[];
   if (p.only_if_online && p.bound_log2 != nullptr && *p.bound_log2 < 3.0e38f) return;
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -111,20 +117,21 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
   uint64_t* qt_ready = bars + 18;  // QT: Q copied into TMEM by the softmax warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_qt = (p.L + 127) / 128;
+  const int n_qt = MC ? ((p.L + 255) / 256) * 2 : (p.L + 127) / 128;  // MC: padded to whole pairs (a pad CTA computes, writes nothing)
   const int qt = blockIdx.x % n_qt;
   const int bh = blockIdx.x / n_qt;
   const int h = bh % p.H, b = bh / p.H;
   const int q0 = qt * 128;
   const int n_kv = (p.L + 63) / 64;
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < DB_STAGES; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], MC ? 2 : 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], MC ? 2 : 1);
     }
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
@@ -139,6 +146,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's barriers are initialised before anything of ours can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -152,10 +160,18 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], DB_T64);
-        tma_load_3d(sK + st * DB_T64, &p.tma_kv, &k_full[st], p.dh + h * 64, j * 64, b);
+        if (MC)  // my half of the tile (rows 32 crank .. +32) into both CTAs; the peer sends the other half
+          tma_load_3d_multicast(sK + st * DB_T64 + crank * (DB_T64 / 2), &p.tma_kv, &k_full[st], p.dh + h * 64,
+                                j * 64 + (int)crank * 32, b, 0x3);
+        else
+          tma_load_3d(sK + st * DB_T64, &p.tma_kv, &k_full[st], p.dh + h * 64, j * 64, b);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_expect_tx(&v_full[st], VT);
-        tma_load_3d(sV + st * VT, &p.tma_kv, &v_full[st], 2 * p.dh + h * 64, j * 64, b);
+        if (MC)
+          tma_load_3d_multicast(sV + st * VT + crank * (DB_T64 / 2), &p.tma_kv, &v_full[st], 2 * p.dh + h * 64,
+                                j * 64 + (int)crank * 32, b, 0x3);
+        else
+          tma_load_3d(sV + st * VT, &p.tma_kv, &v_full[st], 2 * p.dh + h * 64, j * 64, b);
         if (X3) tma_load_3d(sV + st * VT + DB_T64, &p.tma_kv, &v_full[st], p.lo_col + 2 * p.dh + h * 64, j * 64, b);
         if (++st == DB_STAGES) {
           st = 0;
@@ -188,7 +204,10 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
           for (int k = 0; k < 4; ++k)
             umma_f16_ts(tS, tmem_base + 224 + k * 8, make_smem_desc(aK + k * 32, 0, 1024), idesc_s, 1u);
         }
-        umma_commit(&k_empty[st]);
+        if (MC)
+          umma_commit_multicast(&k_empty[st], 0x3);
+        else
+          umma_commit(&k_empty[st]);
         umma_commit(&s_full[j & 1]);
       };
       if (QT) {
@@ -221,7 +240,10 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
             umma_f16_ts(tmem_base + 224, tP + k * 8, make_smem_desc(aOnes + k * 32, 0, 1024), idesc_l,
                         (j > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&v_empty[st]);
+        if (MC)
+          umma_commit_multicast(&v_empty[st], 0x3);
+        else
+          umma_commit(&v_empty[st]);
         umma_commit(o_ready);
         if (j + 2 < n_kv) issue_s(j + 2);  // reuses S_{j&1}: issued after the MMA that read P_j from it
       }
@@ -442,11 +464,12 @@ __global__ void __launch_bounds__(DB_THREADS, 2) attn_fwd_db_kernel(const __grid
     __syncwarp();
     tmem_dealloc(tmem_base, DB_TMEM_COLS);
   }
+  if (MC) cluster_sync_all();  // neither CTA leaves while the other may still multicast into it or arrive on its barriers
 }
 
 int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                              int only_if_online, cudaStream_t stream);
-template <bool PF, bool QT, bool DR = false, bool X3 = false>
+template <bool PF, bool QT, bool DR = false, bool X3 = false, bool MC = false>
 static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                                 int only_if_online, cudaStream_t stream);
 // fp32-grade attention (precision='fp32'): qkv bf16 [T, 2*3*dh] (hi block | lo block), y bf16 [T, 2*dh] (hi | lo)
@@ -474,7 +497,12 @@ int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* 
                              int only_if_online, cudaStream_t stream) {
   return launch_attn_fwd_db_t<false, false>(qkv, y, lse, bound_log2, B, L, H, only_if_online, stream);
 }
-template <bool PF, bool QT, bool DR, bool X3>
+// variant 17: K / V tiles shared by a 2-CTA cluster through TMA multicast
+int launch_attn_fwd_db_mc(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                          cudaStream_t stream) {
+  return launch_attn_fwd_db_t<false, true, false, false, true>(qkv, y, lse, bound_log2, B, L, H, 0, stream);
+}
+template <bool PF, bool QT, bool DR, bool X3, bool MC>
 static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                                 int only_if_online, cudaStream_t stream) {
   OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd_db: bad arguments");
@@ -483,7 +511,7 @@ static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const floa
   const uint64_t width = (uint64_t)(X3 ? 6 : 3) * dh;  // X3: (hi block | lo block)
   uint64_t dims[3] = {width, (uint64_t)L, (uint64_t)B};
   uint64_t strides[2] = {width * 2, (uint64_t)L * width * 2};
-  uint32_t box_q[3] = {64, 128, 1}, box_kv[3] = {64, 64, 1};
+  uint32_t box_q[3] = {64, 128, 1}, box_kv[3] = {64, MC ? 32u : 64u, 1};  // MC: each CTA of the pair loads half a kv tile
   OSD_TRY(make_tmap(&p.tma_q, qkv, 2, 3, dims, strides, box_q));
   OSD_TRY(make_tmap(&p.tma_kv, qkv, 2, 3, dims, strides, box_kv));
   p.bound_log2 = bound_log2;
@@ -496,12 +524,29 @@ static int launch_attn_fwd_db_t(const void* qkv, void* y, float* lse, const floa
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   static DeviceOnce once;
   if (once.first()) {
-    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<PF, QT, DR, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    OSD_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<PF, QT, DR, X3, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   X3 ? DB_SMEM_BYTES_X3 : DB_SMEM_BYTES));
   }
-  const long long grid = (long long)ceil_div(L, 128) * H * B;
+  const long long grid = (long long)(MC ? 2 * ceil_div(L, 256) : ceil_div(L, 128)) * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_fwd_db: grid too large");
-  attn_fwd_db_kernel<PF, QT, DR, X3><<<(unsigned)grid, DB_THREADS, X3 ? DB_SMEM_BYTES_X3 : DB_SMEM_BYTES, stream>>>(p);
+  if (MC) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(DB_THREADS);
+    cfg.dynamicSmemBytes = DB_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OSD_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_db_kernel<PF, QT, DR, X3, MC>, p));
+    OSD_LAUNCHED();
+    return 0;
+  }
+  attn_fwd_db_kernel<PF, QT, DR, X3, MC><<<(unsigned)grid, DB_THREADS, X3 ? DB_SMEM_BYTES_X3 : DB_SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
   return 0;
 }

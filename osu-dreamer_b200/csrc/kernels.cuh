@@ -123,6 +123,9 @@ int launch_attn_fwd_db_pf(const void* qkv, void* y, float* lse, const float* bou
 // softmax only, hands the online case to the "db" kernel on the device
 int launch_attn_fwd_pp3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int emu,
                         cudaStream_t stream);
+// variant 17: variant 7 with the K / V tiles shared by a 2-CTA cluster (each CTA loads half a tile, TMA multicast)
+int launch_attn_fwd_db_mc(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
+                          cudaStream_t stream);
 // fp32-grade attention on the db pipeline: S = Q_hi K_hi^T + Q_lo K_hi^T, O += P_hi V_hi + P_hi V_lo (attn_fwd_db.cu, X3)
 int launch_attn_fwd_db_x3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
                           cudaStream_t stream);
