@@ -19,9 +19,9 @@
 //     runs under the exponentials of step j; P_g(j) goes to its own TMEM columns, so O_g += P_g(j) V_j and S_g(j+1) do not
 //     order each other; the UMMA issuer is event driven (polls s_free / p_full of both groups);
 //   * K / V tiles are loaded once per 256 q rows: L2 -> SM traffic 34.6 -> 17.4 GB per launch at B = 16, L = 8192.
-// This kernel implements the fixed-bound softmax only (q, k leave RMSNorm(64): per-layer score bound, no running max, no O
-// rescale); it returns at once when no finite bound is given, and the launcher then runs the "db" kernel (online softmax),
-// which in turn returns at once when the bound is finite -- both decisions on the device, no host synchronisation.
+// Fixed-bound softmax (q, k leave RMSNorm(64): per-layer score bound, no running max, no O rescale); without a finite bound
+// the same kernel runs the online softmax: the two halves of a row agree on its maximum through shared memory every step
+// (one named barrier per step and q tile) and half 0 rescales the row's O.
 //
 //   warps : 0 TMA producer | 1 TMEM allocator + UMMA issuer | 2-17 softmax: (warp - 2) = 8 h + 4 g + i, quadrant = warp % 4
 //   TMEM  : S_0 [0,128) | S_1 [128,256) | P_0 bf16 [256,320) | P_1 [320,384) | O_0 [384,448) | O_1 [448,512)
@@ -38,7 +38,7 @@ static constexpr int P3_THREADS = 576;  // 18 warps
 static constexpr int P3_TILE = 128 * 128;  // bytes of a [128 x 64] bf16 tile
 static constexpr int P3_STAGES = 3;
 static constexpr int P3_SMEM_TILES = 2 * P3_TILE + 2 * P3_STAGES * P3_TILE;
-static constexpr int P3_LSUM = 2 * 128 * 4;  // partial row sums of column half 1, per q tile
+static constexpr int P3_LSUM = (2 * 128 + 2 * 2 * 2 * 128) * 4;  // partial row sums of column half 1 per q tile | online-softmax row maxima [2 buffers][2 tiles][2 halves][128]
 static constexpr int P3_SMEM_BYTES = P3_SMEM_TILES + P3_LSUM + 256 + 1024;
 static constexpr uint32_t P3_TMEM_COLS = 512;
 
@@ -57,7 +57,7 @@ __device__ __forceinline__ float pp3_ex2(float x) {
   return y;
 }
 
-// one chunk of 32 score columns -> 32 probabilities (bf16 pairs in pk[16]); EMU of every 4 pairs use the FMA-pipe exponential
+// one chunk of 32 score columns -> 32 probabilities (bf16 pairs in pk[16]); EMU of every 8 pairs use the FMA-pipe exponential
 template <int EMU>
 __device__ __forceinline__ void pp3_chunk(const uint32_t (&r)[32], float c, float neg_mc, uint32_t (&pk)[16], float2& s01,
                                          float2& s23) {
@@ -66,7 +66,7 @@ __device__ __forceinline__ void pp3_chunk(const uint32_t (&r)[32], float c, floa
   for (int p = 0; p < 16; ++p) {
     const float2 a = ffma2(make_float2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1])), c2, n2);
     float2 e;
-    if ((p & 3) < EMU)
+    if ((p & 7) < EMU)
       e = ex2_poly2(a);
     else
       e = make_float2(pp3_ex2(a.x), pp3_ex2(a.y));
@@ -92,7 +92,6 @@ __device__ __forceinline__ void pp3_chunk_masked(const uint32_t (&r)[32], float 
 template <int EMU>
 __global__ void __launch_bounds__(P3_THREADS, 1) attn_fwd_pp3_kernel(const __grid_constant__ AttnPp3Params p) {
   extern __shared__ uint8_t smem_raw[];
-  if (p.bound_log2 == nullptr || !(*p.bound_log2 < 3.0e38f)) return;  // online softmax: the "db" kernel does the work
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
@@ -245,10 +244,11 @@ __global__ void __launch_bounds__(P3_THREADS, 1) attn_fwd_pp3_kernel(const __gri
     const uint32_t tP = tmem_base + 256 + g * 64 + hh * 32 + lane_off;
     const uint32_t tO = tmem_base + 384 + g * 64 + lane_off;
     const float c = p.scale_log2;
-    const float bound = __ldg(p.bound_log2);
-    const float m = bound / c;
-    const float neg_mc = -bound;
-    float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+    float bound = INFINITY;
+    if (p.bound_log2 != nullptr) bound = __ldg(p.bound_log2);
+    const bool fixed = bound < 3.0e38f;  // else: online softmax, the two halves of a row agree on its maximum every step
+    float m = fixed ? bound / c : -INFINITY, l = 0.f;
+    float* sMax = sL + 2 * 128;
     for (int j = 0; j < n_kv; ++j) {
       const int valid = p.L - j * 128 - hh * 64;  // valid columns of this thread's half
       mbar_wait(&s_full[g], j & 1);
@@ -261,26 +261,67 @@ __global__ void __launch_bounds__(P3_THREADS, 1) attn_fwd_pp3_kernel(const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[g]);  // S_g(j+1) may overwrite the accumulator from here on
+      float alpha = 1.0f;
+      bool o_waited = false;
+      if (!fixed) {
+        float mx = -INFINITY;
 #pragma unroll
-      for (int cch = 0; cch < 2; ++cch) {
-        uint32_t pk[16];
-        if (valid >= 64)
-          pp3_chunk<EMU>(rs[cch], c, neg_mc, pk, s01, s23);
-        else
-          pp3_chunk_masked(rs[cch], c, neg_mc, valid - cch * 32, pk, s01);
-        if (cch == 0 && j > 0) {  // P_g's columns are free once PV_g(j-1) has read them (a step ago)
+        for (int cch = 0; cch < 2; ++cch)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cch * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(rs[cch][i]));
+        float* buf = sMax + ((j & 1) * 2 + g) * 256;  // double-buffered by step parity: one barrier per step is enough
+        buf[hh * 128 + row] = mx;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+        mx = fmaxf(mx, buf[(hh ^ 1) * 128 + row]);
+        const float m_new = fmaxf(m, mx);
+        alpha = pp3_ex2((m - m_new) * c);
+        m = m_new;
+        if (j > 0) {
           mbar_wait(&o_ready[g], (j - 1) & 1);
           tc_fence_after();
+          o_waited = true;
+          if (hh == 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {  // half 0 rescales the row's O; PV_g(j) waits for its p_full arrive
+#pragma unroll 1
+            for (int cch = 0; cch < 4; ++cch) {  // 16 columns at a time: the 64 scores of this step stay in registers
+              uint32_t ro[16];
+              __syncwarp();
+              tmem_ld16(tO + cch * 16, ro);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+              tmem_st16(tO + cch * 16, ro);
+            }
+            tmem_wait_st();
+          }
         }
-        __syncwarp();
-        tmem_st16(tP + cch * 16, pk);
       }
+      const float neg_mc = -m * c;
+      float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+      // all 64 probabilities first, the P buffer second: by the time they are packed, O_g += P_g(j-1) V has long read the
+      // previous P (waiting before the first store cost 9.8 % of the softmax warps' samples: the fastest warp of a group
+      // reached it while the slowest was still finishing step j-1)
+      uint32_t pk[2][16];
+#pragma unroll
+      for (int cch = 0; cch < 2; ++cch) {
+        if (valid >= 64)
+          pp3_chunk<EMU>(rs[cch], c, neg_mc, pk[cch], s01, s23);
+        else
+          pp3_chunk_masked(rs[cch], c, neg_mc, valid - cch * 32, pk[cch], s01);
+      }
+      if (j > 0 && !o_waited) {  // P_g's columns are free once PV_g(j-1) has read them
+        mbar_wait(&o_ready[g], (j - 1) & 1);
+        tc_fence_after();
+      }
+      __syncwarp();
+      tmem_st16(tP, pk[0]);
+      tmem_st16(tP + 16, pk[1]);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
+      l = l * alpha + ((s01.x + s01.y) + (s23.x + s23.y));
     }
-    float l = (s01.x + s01.y) + (s23.x + s23.y);
     // the two column halves of a row meet here: half 1 publishes its partial sum, half 0 finishes the row
     if (hh == 1) sL[g * 128 + row] = l;
     asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");  // the 8 warps of q tile g
@@ -319,9 +360,6 @@ __global__ void __launch_bounds__(P3_THREADS, 1) attn_fwd_pp3_kernel(const __gri
   }
 }
 
-int launch_attn_fwd_db_gated(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H,
-                             int only_if_online, cudaStream_t stream);
-
 template <int EMU>
 static int launch_pp3_t(const AttnPp3Params& p, long long grid, cudaStream_t stream) {
   static DeviceOnce once;
@@ -333,8 +371,7 @@ static int launch_pp3_t(const AttnPp3Params& p, long long grid, cudaStream_t str
   return 0;
 }
 
-// emu: share of the exponentials on the FMA pipe, in quarters (0, 1, 2); < 0 = the default (OSD_PP_EMU or 0: at four softmax
-// warps per sub-partition the SFU path alone is the fastest, tools/micro/softmax_bench.cu)
+// emu: share of the exponentials on the FMA pipe, in EIGHTHS (0 .. 4); < 0 = the default (OSD_PP_EMU or 2)
 int launch_attn_fwd_pp3(const void* qkv, void* y, float* lse, const float* bound_log2, int B, int L, int H, int emu,
                        cudaStream_t stream) {
   OSD_CHECK(qkv && y && B > 0 && L > 0 && H > 0, "attn_fwd_pp3: bad arguments");
@@ -352,21 +389,24 @@ int launch_attn_fwd_pp3(const void* qkv, void* y, float* lse, const float* bound
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   static const int emu_default = [] {
     const char* e = getenv("OSD_PP_EMU");
-    return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+    return (e != nullptr && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 2;
   }();
   if (emu < 0) emu = emu_default;
   const long long grid = (long long)ceil_div(L, 256) * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_fwd_pp3: grid too large");
-  if (bound_log2 != nullptr) {
+  {
     if (emu == 1)
       OSD_TRY(launch_pp3_t<1>(p, grid, stream));
     else if (emu == 2)
       OSD_TRY(launch_pp3_t<2>(p, grid, stream));
+    else if (emu == 3)
+      OSD_TRY(launch_pp3_t<3>(p, grid, stream));
+    else if (emu == 4)
+      OSD_TRY(launch_pp3_t<4>(p, grid, stream));
     else
       OSD_TRY(launch_pp3_t<0>(p, grid, stream));
   }
-  // online softmax (no finite bound): the "db" kernel; it returns at once when the bound is finite
-  return launch_attn_fwd_db_gated(qkv, y, lse, bound_log2, B, L, H, bound_log2 != nullptr ? 1 : 0, stream);
+  return 0;
 }
 
 }  // namespace osd

@@ -29,7 +29,8 @@ def _maxnorm(a, b):
 
 
 @pytest.mark.parametrize('variant,fixed', [(4, False), (4, True), (6, False), (6, True), (7, False), (7, True), (8, False), (8, True),
-                                           (15, False), (15, True), (16, True), (17, False), (17, True)])
+                                           (15, False), (15, True), (16, False), (16, True), (17, False), (17, True), (18, False), (18, True),
+                                           (19, True), (20, True)])
 @pytest.mark.parametrize('B,L', [(1, 128), (2, 256), (1, 200), (2, 1000), (1, 2048), (1, 300), (2, 129)])
 def test_attention_matches_sdpa(B, L, variant, fixed):
     """every dispatchable forward kernel, online softmax and the fixed-bound softmax (randn scores/8 stay far below 2^14)"""
