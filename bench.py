@@ -489,7 +489,7 @@ def run_cuda(args):
             y, lse = lib.attn_fwd(qkv, Ba, L)
             dy = torch.randn(Ba * L, 1024, device=dev).to(torch.bfloat16)
             bound = torch.tensor([14.0], device=dev)  # randn scores / 8 stay far below 2^14: same kernel path the model runs
-            ms_f = time_kernel(lambda: lib.attn_fwd(qkv, Ba, L, bound_log2=bound, variant=7), iters=3, warm=1)  # the model's variant
+            ms_f = time_kernel(lambda: lib.attn_fwd(qkv, Ba, L, bound_log2=bound, variant=18), iters=3, warm=1)  # the model's variant at L >= 6144
             ms_b = time_kernel(lambda: lib.attn_bwd_fused(qkv, y, dy, lse, Ba, L), iters=3, warm=1)
             fl_f = 4.0 * Ba * 16 * L * L * 64
             kern = {'attn_fwd': {'ms': ms_f, 'tflops': fl_f / ms_f / 1e9},
@@ -506,7 +506,7 @@ def run_cuda(args):
                     tot = gb(kk['dram__bytes_read.sum']) + gb(kk['dram__bytes_write.sum'])
                     if 'attn_bwd_fused_kernel' in kk['Kernel Name']:
                         ncu_traffic['attn_bwd_fused'] = tot
-                    elif 'attn_fwd_db_kernel' in kk['Kernel Name']:
+                    elif 'attn_fwd_pp3_kernel' in kk['Kernel Name'] or 'attn_fwd_db_kernel' in kk['Kernel Name']:
                         ncu_traffic['attn_fwd'] = tot
                 ncu_src = 'profiles/ncu_attention_summary_latest.json'
             except Exception:  # noqa

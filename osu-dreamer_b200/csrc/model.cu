@@ -158,14 +158,17 @@ static int proj_cl(const float* const* P, const PackedW& W, int mode, int l, con
   return launch_gemm(g, s);
 }
 
-// forward attention kernel of the model: variant 7 (double-buffered S, Q tile resident in TMEM); OSD_ATTN_FWD=<n>
-// selects another variant for A/B measurements
-static int attn_fwd_variant() {
-  static const int v = [] {
+// forward attention kernel of the model; OSD_ATTN_FWD=<n> forces one variant for A/B measurements.  Long sequences run the
+// one-CTA-per-SM kernel with two q tiles and sixteen softmax warps (variant 18, attn_fwd_pp3.cu: -4 % kernel time at L = 8192,
+// +3.7 % sampling throughput, profiles/r02x_*); shorter ones the two-CTA-per-SM kernel (variant 7, attn_fwd_db.cu), whose
+// smaller CTAs balance better when there are few of them (L <= 4096: 3-6 % faster there).
+static int attn_fwd_variant(int L) {
+  static const int forced = [] {
     const char* e = getenv("OSD_ATTN_FWD");
-    return (e != nullptr && e[0] >= '0' && e[0] <= '9') ? atoi(e) : 7;
+    return (e != nullptr && e[0] >= '0' && e[0] <= '9') ? atoi(e) : -1;
   }();
-  return v;
+  if (forced >= 0) return forced;
+  return L >= 6144 ? 18 : 7;
 }
 
 // OSD_X3_KERNEL=old selects the single-buffered fp32-grade attention kernel (attn_fwd_x3.cu, selectable terms) for A/B
@@ -230,7 +233,7 @@ static int pred_forward(const FwdCtx& c, const float* xt, float* u, float* v, cu
                                                                              16, s));
     else
       OSD_TRY(launch_attn_fwd(lb + pl.qkv, lb + pl.y, reinterpret_cast<float*>(lb + pl.lse), c.W.bound(l), B, L, 16,
-                              attn_fwd_variant(),
+                              attn_fwd_variant(L),
                               s));
     GemmArgs o;
     o.A = lb + pl.y; o.B = c.W.out(l); o.lda = 1024 * km; o.ldb = 1024 * km; o.M = T; o.N = 512; o.K = 1024;

@@ -90,13 +90,13 @@ def main():
     y, lse = lib.attn_fwd(qkv, B, L)
     dy = torch.randn(B * L, 1024, device=dev).to(torch.bfloat16)
     bound = torch.tensor([14.0], device=dev)
-    alone = {'attn_fwd_ms': bench.time_kernel(lambda: lib.attn_fwd(qkv, B, L, bound_log2=bound, variant=7), iters=5, warm=2),
+    alone = {'attn_fwd_ms': bench.time_kernel(lambda: lib.attn_fwd(qkv, B, L, bound_log2=bound, variant=18), iters=5, warm=2),
              'attn_bwd_fused_ms': bench.time_kernel(lambda: lib.attn_bwd_fused(qkv, y, dy, lse, B, L), iters=5, warm=2)}
     top = sorted(((v[1] / steps / 1e3, v[0] // steps, k) for k, v in agg.items()), reverse=True)
     fl = 4.0 * B * 16 * L * L * 64
     in_step = {}
     for ms, n, k in top:
-        if 'attn_fwd_db_kernel' in k:
+        if 'attn_fwd_db_kernel' in k or 'attn_fwd_pp3_kernel' in k:
             in_step['attn_fwd'] = {'ms_per_launch': ms / n, 'tflops': fl / (ms / n) / 1e9}
         if 'attn_bwd_fused_kernel' in k:
             in_step['attn_bwd_fused'] = {'ms_per_launch': ms / n, 'tflops': 2 * fl / (ms / n) / 1e9}
