@@ -66,7 +66,15 @@ struct AttnBwdFusedParams {
                                    (unsigned long long)(clock64() & 0xffffffffll);                                   \
   } while (0)
 
-__global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __grid_constant__ AttnBwdFusedParams p) {
+// W16 (OSD_FB_W16=1, A/B): SIXTEEN softmax warps -- four q-column groups of 32 instead of two of 64, four warps per
+// sub-partition instead of two.  The forward showed (tools/micro/softmax_bench.cu, attn_fwd_pp3.cu) that the per-element
+// softmax chain is latency bound at two warps per sub-partition; this kernel's softmax warps are its critical path (§5: they
+// never idle, the tensor pipe is 47 % busy).  Differences: a thread owns 32 score columns; P~ is carried from phase 1 to phase 2
+// as the bf16 pairs that were written to TMEM (16 registers instead of 64 fp32: the register budget at 18 warps is 96), i.e.
+// dS uses the same rounded P~ as dV; P~^T / dS^T of group g sit in the first 16 columns of the group's own 32 consumed columns;
+// the dQ drain stays with groups 0 / 1 (8 warps x [32 x 32] fp32 as before).
+template <bool W16>
+__global__ void __launch_bounds__(W16 ? 576 : FB_THREADS, 1) attn_bwd_fused_kernel(const __grid_constant__ AttnBwdFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   if (*p.fallback != 0) return;
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -123,14 +131,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
     }
     mbar_init(s_full, 1);
     mbar_init(dp_full, 1);
-    mbar_init(pt_full, 8);
-    mbar_init(ds_full, 8);
+    mbar_init(pt_full, W16 ? 16 : 8);
+    mbar_init(ds_full, W16 ? 16 : 8);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 8);
     mbar_init(kvt_ready, 8);
     mbar_init(acc_done, 1);
-    mbar_init(&st_empty[0], 8);
-    mbar_init(&st_empty[1], 8);
+    mbar_init(&st_empty[0], W16 ? 16 : 8);
+    mbar_init(&st_empty[1], W16 ? 16 : 8);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -198,16 +206,16 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
         FB_TRACE(0, 10, i);
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dV += P^T_i dO_i : q (K dim) chunk k lives at columns (k/4)*64 + (k%4)*8
-          umma_f16_ts(tDV, tS + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc(aDO + k * 16 * 128, 0, 1024), id_o,
-                      (k > 0) ? 1u : acc);
+          umma_f16_ts(tDV, tS + (W16 ? (k >> 1) * 32 + (k & 1) * 8 : (k >> 2) * 64 + (k & 3) * 8),
+                      make_smem_desc(aDO + k * 16 * 128, 0, 1024), id_o, (k > 0) ? 1u : acc);
         if (i + 1 < n_q) issue_s(i + 1);  // overwrites P^T_i only after dV_i has read it
         mbar_wait(ds_full, i & 1);
         tc_fence_after();
         FB_TRACE(0, 12, i);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_f16_ts(tDK, tDP + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc(aQ + k * 16 * 128, 0, 1024), id_o,
-                      (k > 0) ? 1u : acc);
+          umma_f16_ts(tDK, tDP + (W16 ? (k >> 1) * 32 + (k & 1) * 8 : (k >> 2) * 64 + (k & 3) * 8),
+                      make_smem_desc(aQ + k * 16 * 128, 0, 1024), id_o, (k > 0) ? 1u : acc);
         umma_commit(&q_empty[st]);
         if (i + 1 < n_q) issue_dp(i + 1);  // overwrites dS^T_i (TMEM) only after dK_i has read it
         if (i > 0) {
@@ -222,6 +230,186 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
         FB_TRACE(0, 16, i);
       }
       umma_commit(acc_done);
+    }
+  } else if constexpr (W16) {
+    // ================================================================== softmax, 16 warps (thread = kv row, 32 q columns)
+    const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;   // q-column group: columns [32 grp, 32 grp + 32)
+    const int row = quad * 32 + lane;  // kv row
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const bool drainer = grp < 2;      // groups 0 / 1 also copy K / V into TMEM, drain dQ and write dK / dV
+    if (drainer) {  // one-time copy of this thread's K (grp 0) or V (grp 1) row (128 B, SW128 smem) into TMEM
+      mbar_wait(kv_full, 0);
+      const uint32_t base = smem_u32(grp == 0 ? sK : sV) + row * 128;
+      uint32_t r[32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[4 * u]), "=r"(r[4 * u + 1]), "=r"(r[4 * u + 2]), "=r"(r[4 * u + 3])
+                     : "r"(base + ((u ^ (row & 7)) << 4)));
+      __syncwarp();
+      tmem_st32(tmem_base + 448 + grp * 32 + lane_off, r);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(kvt_ready);
+    }
+    const uint32_t tS = tmem_base + lane_off + grp * 32, tDP = tmem_base + 128 + lane_off + grp * 32;
+    const uint32_t ds_row = smem_u32(sDS) + (grp >> 1) * FT + row * 128;  // [q chunk of 64][kv row][64 q]: this group's 64-byte half
+    const int cb = (grp & 1) * 4;
+    const int sw = row & 7;
+    const float c = p.scale_log2;
+    const uint32_t tDQ = tmem_base + 384 + lane_off + grp * 32;
+    uint8_t* stg = sStg + ((warp - 2) & 7) * 4096;
+    const uint32_t stg_row = smem_u32(stg) + lane * 128;
+    auto drain_load = [&](int j) {
+      mbar_wait(dq_full, j & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(tDQ, r);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(dq_empty);
+        tma_store_wait_read<0>();
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + ((u ^ (lane & 7)) << 4)), "r"(r[4 * u]),
+                     "r"(r[4 * u + 1]), "r"(r[4 * u + 2]), "r"(r[4 * u + 3])
+                     : "memory");
+    };
+    auto drain_issue = [&](int qj) {
+      if (lane == 0 && !(p.debug_skip & 1)) {
+        tma_reduce_add_3d(&p.tma_dq, stg, h * 64 + grp * 32, qj * 128 + quad * 32, b);
+        tma_store_commit();
+      }
+    };
+    int qt = i0, qprev = i0;
+    const float* mrow = p.mtile + (size_t)bh * n_q;
+    float m_cur = __ldg(mrow + qt);
+    for (int i = 0; i < n_q; ++i) {
+      const float* st = sStat + (i & 1) * 256 + grp * 32;
+      int qn = qt + 1;
+      if (qn == n_q) qn = 0;
+      const float m_next = __ldg(mrow + qn);
+      // ---- phase 1: P~^T = exp2(S^T * c - m)
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      uint32_t pk1[16];
+      {
+        uint32_t rs[32];
+        __syncwarp();
+        tmem_ld32(tS, rs);
+        tmem_wait_ld();
+        const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_cur, -m_cur);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float2 a = ffma2(make_float2(__uint_as_float(rs[k4 * 4 + 0]), __uint_as_float(rs[k4 * 4 + 1])), c2, nm2);
+          const float2 bb = ffma2(make_float2(__uint_as_float(rs[k4 * 4 + 2]), __uint_as_float(rs[k4 * 4 + 3])), c2, nm2);
+          const float2 e0 = make_float2(fb_ex2(a.x), fb_ex2(a.y));
+          float2 e1;
+          if (FB_EMU == 2 || (FB_EMU == 1 && (k4 & 1)))
+            e1 = ex2_poly2(bb);
+          else
+            e1 = make_float2(fb_ex2(bb.x), fb_ex2(bb.y));
+          pk1[2 * k4] = pack_bf16(e0.x, e0.y);
+          pk1[2 * k4 + 1] = pack_bf16(e1.x, e1.y);
+        }
+      }
+      __syncwarp();
+      tmem_st16(tS, pk1);  // over the first 16 of this group's own 32 consumed columns
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pt_full);
+      // ---- dQ_{i-1}: drained by groups 0 / 1; for everyone: it has consumed the dS^T smem tile
+      if (i > 0) {
+        if (drainer)
+          drain_load(i - 1);
+        else
+          mbar_wait(dq_full, (i - 1) & 1);
+      }
+      // ---- phase 2: dS^T = P~^T o (dP~^T - D~[q])
+      mbar_wait(dp_full, i & 1);
+      tc_fence_after();
+      uint32_t pk2[16];
+      {
+        uint32_t rp[32];
+        __syncwarp();
+        tmem_ld32(tDP, rp);
+        tmem_wait_ld();
+        const float4* d4 = reinterpret_cast<const float4*>(st + 128);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 dv = d4[k4];  // -D of 4 consecutive q columns
+          const float2 p0 = make_float2(__uint_as_float(pk1[2 * k4] << 16), __uint_as_float(pk1[2 * k4] & 0xffff0000u));
+          const float2 p1 = make_float2(__uint_as_float(pk1[2 * k4 + 1] << 16), __uint_as_float(pk1[2 * k4 + 1] & 0xffff0000u));
+          const float2 e0 = fmul2(p0, fadd2(make_float2(__uint_as_float(rp[k4 * 4 + 0]), __uint_as_float(rp[k4 * 4 + 1])),
+                                            make_float2(dv.x, dv.y)));
+          const float2 e1 = fmul2(p1, fadd2(make_float2(__uint_as_float(rp[k4 * 4 + 2]), __uint_as_float(rp[k4 * 4 + 3])),
+                                            make_float2(dv.z, dv.w)));
+          pk2[2 * k4] = pack_bf16(e0.x, e0.y);
+          pk2[2 * k4 + 1] = pack_bf16(e1.x, e1.y);
+        }
+      }
+      __syncwarp();
+      tmem_st16(tDP, pk2);  // TMEM copy: A operand of dK += dS^T Q_i
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4)  // smem copy: MN-major A operand of dQ_i = dS_i K
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + (((cb + u4) ^ sw) << 4)), "r"(pk2[4 * u4]),
+                     "r"(pk2[4 * u4 + 1]), "r"(pk2[4 * u4 + 2]), "r"(pk2[4 * u4 + 3])
+                     : "memory");
+      tmem_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(ds_full);
+        mbar_arrive(&st_empty[i & 1]);
+      }
+      if (i > 0 && drainer) drain_issue(qprev);
+      qprev = qt;
+      qt = qn;
+      m_cur = m_next;
+    }
+    if (drainer) {
+      drain_load(n_q - 1);
+      fence_proxy_async_smem();
+      __syncwarp();
+      drain_issue(qprev);
+      // ---- epilogue: group 0 writes dK (x scale), group 1 writes dV
+      mbar_wait(acc_done, 0);
+      tc_fence_after();
+      const int kv = kv0 + row;
+      const bool ok = kv < p.L;
+      const uint32_t tACC = tmem_base + (grp == 0 ? 320 : 256) + lane_off;
+      const float mul = grp == 0 ? p.scale : 1.0f;
+#pragma unroll 1
+      for (int cch = 0; cch < 2; ++cch) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tACC + cch * 32, r);
+        tmem_wait_ld();
+        if (ok) {
+          uint4* dst = reinterpret_cast<uint4*>(p.dqkv + ((size_t)b * p.L + kv) * (3 * p.dh) + (grp == 0 ? 1 : 2) * p.dh +
+                                                h * 64 + cch * 32);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            dst[k] = make_uint4(pack_bf16(__uint_as_float(r[8 * k]) * mul, __uint_as_float(r[8 * k + 1]) * mul),
+                                pack_bf16(__uint_as_float(r[8 * k + 2]) * mul, __uint_as_float(r[8 * k + 3]) * mul),
+                                pack_bf16(__uint_as_float(r[8 * k + 4]) * mul, __uint_as_float(r[8 * k + 5]) * mul),
+                                pack_bf16(__uint_as_float(r[8 * k + 6]) * mul, __uint_as_float(r[8 * k + 7]) * mul));
+        }
+      }
+      tc_fence_before();
+      if (lane == 0) tma_store_wait<0>();
+      __syncwarp();
+    } else {
+      tc_fence_before();
     }
   } else {
     // ================================================================== softmax (thread = kv row, 64 q columns)
@@ -593,13 +781,21 @@ int launch_attn_bwd_fused(const void* qkv, const void* y, const void* dy, const 
   p.debug_skip = dbg_skip;
   p.trace = g_fb_trace;
   p.trace_cta = g_fb_trace_cta;
+  static const bool w16 = [] {
+    const char* e = getenv("OSD_FB_W16");
+    return e != nullptr && e[0] == '1';
+  }();
   static DeviceOnce once;
   if (once.first()) {
-    OSD_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BYTES));
+    OSD_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BYTES));
+    OSD_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BYTES));
   }
   const long long grid = (long long)n_t * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_bwd_fused: grid too large");
-  attn_bwd_fused_kernel<<<(unsigned)grid, FB_THREADS, FB_SMEM_BYTES, stream>>>(p);
+  if (w16)
+    attn_bwd_fused_kernel<true><<<(unsigned)grid, 576, FB_SMEM_BYTES, stream>>>(p);
+  else
+    attn_bwd_fused_kernel<false><<<(unsigned)grid, FB_THREADS, FB_SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
   if (convert_dq) {
     const size_t n8 = (size_t)B * L * dh / 8;

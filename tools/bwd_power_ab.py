@@ -50,8 +50,12 @@ print('RESULT ' + json.dumps({'ms': ms, 'tflops_algorithmic': 8.0 * B * 16 * L *
 p.terminate()
 ''' % ROOT
 res = []
-for name, which, env in (('fused', 'fused', {}), ('fused, no dQ reduce-add (timing only)', 'fused', {'OSD_FB_SKIP': '1'}), ('two-pass', '2pass', {}),
-                         ('cudnn sdpa bwd', 'cudnn', {}), ('fused', 'fused', {})):
+SETS = (('fused', 'fused', {}), ('fused, 16 softmax warps', 'fused', {'OSD_FB_W16': '1'}), ('fused', 'fused', {}),
+        ('fused, 16 softmax warps', 'fused', {'OSD_FB_W16': '1'}))
+if len(sys.argv) > 1 and sys.argv[1] == 'all':
+    SETS = (('fused', 'fused', {}), ('fused, no dQ reduce-add (timing only)', 'fused', {'OSD_FB_SKIP': '1'}), ('two-pass', '2pass', {}),
+            ('cudnn sdpa bwd', 'cudnn', {}), ('fused', 'fused', {}))
+for name, which, env in SETS:
     r = subprocess.run([sys.executable, '-c', CHILD, which], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     line = [ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')]
     d = json.loads(line[0][7:]) if line else {'error': (r.stderr or r.stdout)[-400:]}
