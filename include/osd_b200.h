@@ -75,6 +75,10 @@ OSD_API unsigned long long osd_launch_count(void);
 OSD_API int osd_gemm(const void* A, int a_major, int64_t lda, const void* B, int b_major, int64_t ldb, void* C,
              int64_t ldc, int c_fp32, const float* bias, int M, int N, int K, int elem, int epi, int split_k,
              void* stream);
+/* the split_k the library's own weight-gradient GEMMs use for an [M x N] reduce-add product over K: whole waves of the
+ * persistent grid (CTAs, or CTA pairs = cta_group::2 [256 x 256] tiles where osd_gemm runs them: bf16, N % 256 == 0, more than
+ * 8 k-blocks of 64 per work item) */
+OSD_API int osd_gemm_split_k(int M, int N, int K);
 
 /* qkv projection with the fused epilogue: bias + per-head RMSNorm(q), RMSNorm(k) + RoPE
  * (osu_dreamer/common/attn.py:75-81).  x [T,512], w [3072,512], out bf16 [T,3072];

@@ -24,6 +24,8 @@ int osd_gemm(const void* A, int a_major, int64_t lda, const void* B, int b_major
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 
+int osd_gemm_split_k(int M, int N, int K) { return gemm_split_for(M, N, K); }
+
 int osd_qkv_proj(const void* x, const void* w, const float* bias, const float* qnorm_w, const float* knorm_w,
                  const float* rope, void* out, void* raw_out, int T, int L, int elem, void* stream) {
   GemmArgs g;

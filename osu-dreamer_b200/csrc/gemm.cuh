@@ -41,5 +41,8 @@ struct GemmArgs {
 };
 
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+// split-K factor for a reduce-add GEMM (weight gradients: small M x N, K = tokens): the split whose work items fill whole
+// waves of the persistent grid (CTAs, or CTA pairs where launch_gemm will use them) with the fewest k-blocks per wave
+int gemm_split_for(int M, int N, int K);
 
 }  // namespace osd

@@ -320,14 +320,6 @@ static bool attn_bwd_two_pass() {
   return v;
 }
 
-static int split_for(int M, int N, int K, int bn) {
-  const int tiles = ceil_div(M, 128) * ceil_div(N, bn);
-  const int kb = ceil_div(K, 64);
-  int s = ceil_div(4 * num_sms(), tiles);
-  if (s > kb) s = kb;
-  if (s < 1) s = 1;
-  return s;
-}
 // dX[M,N] = dY[M,K] * W[K,N]   (W stored [K rows][N] row-major = MN-major B operand)
 static int gemm_dgrad(const void* dY, int64_t ldy, const void* W, int64_t ldw, void* dX, int64_t ldx, int x_fp32,
                       int atomic, int M, int N, int K, cudaStream_t s) {
@@ -343,7 +335,7 @@ static int gemm_wgrad(const void* dY, int64_t ldy, const void* X, int64_t ldx, f
   GemmArgs g;
   g.A = dY; g.a_major = MAJOR_MN; g.lda = ldy; g.B = X; g.b_major = MAJOR_MN; g.ldb = ldx;
   g.M = M; g.N = N; g.K = T; g.elem = ELEM_BF16; g.epi = EPI_ATOMIC; g.C = dW; g.ldc = ldw; g.c_fp32 = 1;
-  g.split_k = split_for(M, N, T, (N % 256 == 0) ? 256 : 128);
+  g.split_k = gemm_split_for(M, N, T);
   return launch_gemm(g, s);
 }
 

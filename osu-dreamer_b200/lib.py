@@ -96,6 +96,11 @@ def gemm(A, B, C, bias=None, a_major=MAJOR_K, b_major=MAJOR_K, epi=EPI_STORE, sp
     return C
 
 
+def gemm_split_k(M: int, N: int, K: int) -> int:
+    """the split-K factor the library's weight-gradient GEMMs use for this shape (whole waves of the persistent grid)"""
+    return int(load().osd_gemm_split_k(c_int(M), c_int(N), c_int(K)))
+
+
 def rope_table(L: int, device) -> torch.Tensor:
     """fp32 cos|sin table [L, 2, 32] followed by its 32-row-transposed copy (flat, osd_rope_table_floats(L) floats);
     inv_freq formed exactly as osu_dreamer/common/attn.py:16-18."""

@@ -1,5 +1,6 @@
 """GEMM shapes of one denoiser layer at the bench size (T = 16 x 8192 tokens): time per launch and TFLOP/s.
-Run twice (OSD_GEMM_EW=4 forces the 4-epilogue-warp layout) for an A/B."""
+Run twice for an A/B: OSD_GEMM_EW=4 forces the 4-epilogue-warp layout, OSD_GEMM_PAIR=0 / 1 switches the CTA-pair kernel off /
+on for every eligible shape (default: K >= 1024)."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -46,6 +47,12 @@ for name, N, K in (('dgrad proj_o (dhn)', 1408, 512), ('dgrad proj_vg (dz2)', 51
     A, Bm, C = rnd(T, K), rnd(K, N), torch.empty(T, N, dtype=bf, device=dev)
     ms = timeit(lambda: lib.gemm(A, Bm, C, b_major=lib.MAJOR_MN))
     rows.append((name, N, K, ms))
+# wgrad: dW[M,N] += dY[T,M]^T X[T,N] (both MN-major, split-K reduce-add into fp32)
+for name, M, N in (('wgrad qkv', 3072, 512), ('wgrad out_proj', 512, 1024), ('wgrad proj_vg', 2816, 512), ('wgrad proj_o', 512, 1408)):
+    A, Bm, C = rnd(T, M), rnd(T, N), torch.zeros(M, N, dtype=f32, device=dev)
+    sk = lib.gemm_split_k(M, N, T)
+    ms = timeit(lambda: lib.gemm(A, Bm, C, a_major=lib.MAJOR_MN, b_major=lib.MAJOR_MN, epi=lib.EPI_ATOMIC, split_k=sk))
+    rows.append((f'{name} [{M}x{N}] split {sk}', N, M, ms))  # the TF/s line below uses 2 T N K with K := M
 for name, N, K, ms in rows:
     print(f'{name:40s} N={N:5d} K={K:5d}  {ms * 1e3:8.1f} us  {2 * T * N * K / ms / 1e9:7.0f} TF/s', flush=True)
 print('sum', sum(r[3] for r in rows))
