@@ -27,7 +27,7 @@ def check(name, got, ref, tol):
 
 
 for M in (32768, 20000 + 77 * 8, 512 * 37):
-    for N, K in ((512, 1024), (2816, 512), (1024, 512), (512, 1408), (768, 64)):
+    for N, K in ((512, 1024), (2816, 512), (1024, 512), (512, 1408), (1408, 512), (768, 64), (96, 512)):
         A, B = rnd(M, K), rnd(N, K)
         ref = A.float() @ B.float().T
         bias = rnd(N, dtype=f32)
@@ -37,12 +37,14 @@ for M in (32768, 20000 + 77 * 8, 512 * 37):
         check(f'B MN-major bf16 out M={M} N={N} K={K}', lib.gemm(A, Bt, torch.empty(M, N, dtype=bf, device=dev), b_major=lib.MAJOR_MN), ref, 6e-3)
 # wgrad shape: A [K=T, M] MN-major, B [K=T, N] MN-major, split-K reduce-add into fp32
 T = 16384
-for M, N in ((3072, 512), (512, 1024), (2816, 512)):
+for M, N in ((3072, 512), (512, 1024), (2816, 512), (512, 1408)):
     A, B = rnd(T, M), rnd(T, N)
     ref = A.float().T @ B.float()
     C = torch.zeros(M, N, dtype=f32, device=dev)
-    lib.gemm(A, B, C, a_major=lib.MAJOR_MN, b_major=lib.MAJOR_MN, epi=lib.EPI_ATOMIC, split_k=16)
-    check(f'wgrad MN/MN split-K 16 M={M} N={N} K={T}', C, ref, 2e-5)
+    for sk in (16, lib.gemm_split_k(M, N, T)):
+        C.zero_()
+        lib.gemm(A, B, C, a_major=lib.MAJOR_MN, b_major=lib.MAJOR_MN, epi=lib.EPI_ATOMIC, split_k=sk)
+        check(f'wgrad MN/MN split-K {sk} M={M} N={N} K={T}', C, ref, 2e-5)
 # fused QKV epilogue: bitwise against the single-CTA kernel (subprocess-free: the pair switch is per process, so compare
 # against a torch restatement at bf16 tolerance instead)
 L, Bn = 4096, 6
