@@ -277,6 +277,19 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_cons
       const int r0 = tm * C::TM + (int)rank * BM + quad * 32;
       const int m = r0 + lane;
       const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+      // The accumulator is handed back as soon as this warp's LAST chunk is in registers, not after it is processed and
+      // stored: at K <= 512 the issuer waits for a free accumulator on nearly every item (ncu), and the epilogue warps in turn
+      // wait for the next one -- the earlier release takes the last chunk's work out of that hand-off.
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR)
+            mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+          else
+            mbar_arrive(&tempty_bar[acc]);
+        }
+      };
 
       if constexpr (QKV) {
         // 64-column chunks = one attention head of q, k or v.  Packed fp32x2 math throughout: with K = 512 this epilogue, not
@@ -298,6 +311,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_cons
           tmem_ld32(trow + c * 64 + 32, r1v);
           if (n0 >= p.N) {  // warp-uniform
             tmem_wait_ld();
+            if (c + NSUB >= BN / 64) release_acc();
             continue;
           }
           float2 xa[16], xb[16];  // columns [0, 32) and [32, 64) of the head, two per element
@@ -309,6 +323,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_cons
               b1[j4] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32) + j4);
             }
             tmem_wait_ld();
+            if (c + NSUB >= BN / 64) release_acc();
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               xa[2 * j4] = fadd2(make_float2(__uint_as_float(r0v[4 * j4]), __uint_as_float(r0v[4 * j4 + 1])), make_float2(b0[j4].x, b0[j4].y));
@@ -372,6 +387,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_cons
           __syncwarp();
           tmem_ld32(trow + c * 32, r);
           tmem_wait_ld();
+          if (c + NSUB >= BN / 32) release_acc();
           if (n0 >= p.N) continue;  // warp-uniform
           if (p.bias != nullptr && p.epi != EPI_ATOMIC) {
 #pragma unroll
@@ -403,6 +419,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_cons
           tmem_ld32(trow + c * 64 + 32, rb);
           if (n0 >= p.N) {  // warp-uniform
             tmem_wait_ld();
+            if (c + NSUB >= BN / 64) release_acc();
             continue;
           }
           uint32_t w[32];
@@ -411,6 +428,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 16; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
             tmem_wait_ld();
+            if (c + NSUB >= BN / 64) release_acc();
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float2 a0 = fadd2(make_float2(__uint_as_float(ra[4 * j4]), __uint_as_float(ra[4 * j4 + 1])), make_float2(bv[j4].x, bv[j4].y));
@@ -422,6 +440,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_cons
             }
           } else {
             tmem_wait_ld();
+            if (c + NSUB >= BN / 64) release_acc();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               w[j] = pack_bf16(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1]));
@@ -440,6 +459,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_cons
           tmem_ld32(trow + c * 64, ra);
           tmem_ld32(trow + c * 64 + 32, rb);
           tmem_wait_ld();
+          if (c + NSUB >= BN / 64) release_acc();
           if (n0 >= p.N) continue;  // warp-uniform
           uint32_t w[32];
 #pragma unroll
@@ -473,14 +493,6 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_cons
             stage_out(&p.tma_c, w, p.N + n0, r0, false);
           }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (PAIR)
-          mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
-        else
-          mbar_arrive(&tempty_bar[acc]);
       }
     }
     if (lane == 0) tma_store_wait<0>();  // all bulk stores of this warp complete before the CTA retires its smem
