@@ -92,8 +92,22 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = (p.L + 127) / 128;
-  const int qt = blockIdx.x % n_qt;
-  const int bh = blockIdx.x / n_qt;
+  // Work items = (q tile, head, sample).  Launched directly the grid has one CTA per item and this loop runs once; as the
+  // gated fallback of the single-pass backward the grid is two CTAs per SM (an empty 16 384-CTA launch cost 70 us, twice per
+  // layer), and in the rare case that the gate is open every CTA walks its items, re-initialising barriers and TMEM each time.
+  const unsigned n_work = (unsigned)n_qt * p.H * p.B;
+  if (warp == 1) {  // TMEM: once per CTA (the allocation permit is relinquished, so not per item)
+    tmem_alloc(tmem_slot, BW_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+#pragma unroll 1
+  for (unsigned work = blockIdx.x; work < n_work; work += gridDim.x) {
+  const int qt = work % n_qt;
+  const int bh = work / n_qt;
   const int h = bh % p.H, b = bh / p.H;
   const int q0 = qt * 128;
   const int n_kv = (p.L + 63) / 64;
@@ -112,14 +126,9 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
     mbar_init(p1_done, 4);
     fence_barrier_init();
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, BW_TMEM_COLS);
-    tmem_relinquish();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -283,6 +292,12 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
   }
   __syncthreads();
   tc_fence_after();
+  if (work + gridDim.x < n_work) {  // another item follows: every thread is past its last wait (barrier above)
+    if (warp == 0 && lane == 0)
+      for (int i = 0; i < 11; ++i) mbar_inval(&bars[i]);
+    __syncthreads();
+  }
+  }  // work loop
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, BW_TMEM_COLS);
@@ -327,8 +342,19 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kt = (p.L + 127) / 128;
-  const int kt = blockIdx.x % n_kt;
-  const int bh = blockIdx.x / n_kt;
+  const unsigned n_work = (unsigned)n_kt * p.H * p.B;  // see attn_bwd_dq_kernel
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BW_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+#pragma unroll 1
+  for (unsigned work = blockIdx.x; work < n_work; work += gridDim.x) {
+  const int kt = work % n_kt;
+  const int bh = work / n_kt;
   const int h = bh % p.H, b = bh / p.H;
   const int kv0 = kt * 128;
   const int n_q = (p.L + 63) / 64;
@@ -346,14 +372,9 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
     mbar_init(pt_full, 4);
     fence_barrier_init();
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, BW_TMEM_COLS);
-    tmem_relinquish();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -540,6 +561,12 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkdv_kernel(const __gr
   }
   __syncthreads();
   tc_fence_after();
+  if (work + gridDim.x < n_work) {  // another item follows: every thread is past its last wait (barrier above)
+    if (warp == 0 && lane == 0)
+      for (int i = 0; i < 10; ++i) mbar_inval(&bars[i]);
+    __syncthreads();
+  }
+  }  // work loop
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, BW_TMEM_COLS);
@@ -630,8 +657,9 @@ static int launch_attn_bwd_main(const void* qkv, const void* dy, const float* ls
     OSD_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM_BYTES));
     OSD_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM_BYTES));
   }
-  const long long grid = (long long)ceil_div(L, 128) * H * B;
+  long long grid = (long long)ceil_div(L, 128) * H * B;
   OSD_CHECK(grid < (1ll << 31), "attn_bwd: grid too large");
+  if (gate != nullptr && grid > 2 * num_sms()) grid = 2 * num_sms();  // fallback launch: resident CTAs only, each walks its items
   attn_bwd_dkdv_kernel<<<(unsigned)grid, BW_THREADS, DKV_SMEM_BYTES, stream>>>(p);
   OSD_LAUNCHED();
   attn_bwd_dq_kernel<<<(unsigned)grid, BW_THREADS, DQ_SMEM_BYTES, stream>>>(p);

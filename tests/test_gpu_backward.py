@@ -39,11 +39,13 @@ def test_attention_backward_matches_autograd(B, L, fused):
         assert e < 2e-2, (name, e)
 
 
-def test_attention_backward_fused_falls_back_on_spread_statistics():
+@pytest.mark.parametrize('B,L', [(1, 512), (3, 1920)])
+def test_attention_backward_fused_falls_back_on_spread_statistics(B, L):
     """a query row whose lse is > 96 octaves above its tile neighbours: the single-pass call must detect it on the
-    device and produce the two-kernel result (which makes no assumption on the statistics)"""
+    device and produce the two-kernel result (which makes no assumption on the statistics).  The fallback kernels are
+    launched on a compact grid (two CTAs per SM) and walk their work items; at (3, 1920) there are 720 items, so every
+    CTA re-initialises its barriers and runs two or three of them -- bit-identical to the one-CTA-per-item launch."""
     from osu_dreamer_b200 import lib
-    B, L = 1, 512
     g = torch.Generator().manual_seed(5)
     qkv = torch.randn(B * L, 3072, generator=g)
     qkv[3, :1024] *= 40.0
