@@ -9,7 +9,7 @@ import sys
 
 so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'osu-dreamer_b200', 'libosd_b200.so')
 txt = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
-keys = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAREDG', 'UBLKCP', 'UTCATOM', 'SYNCS', 'MUFU.EX2', 'FFMA2', 'HMMA', 'ATOM', 'RED']
+keys = ['UTCHMMA', 'UTCHMMA.2CTA', 'UTMALDG.2D.2CTA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAREDG', 'UBLKCP', 'UTCATOM', 'SYNCS', 'MUFU.EX2', 'FFMA2', 'HMMA', 'ATOM', 'RED']
 cur, counts, total = None, collections.OrderedDict(), collections.Counter()
 for ln in txt.splitlines():
     m = re.search(r'Function : (\S+)', ln)
@@ -22,7 +22,7 @@ for ln in txt.splitlines():
         op = m.group(1)
         counts[cur]['_all'] += 1
         for k in keys:
-            if op.startswith(k):
+            if op.startswith(k) and not (k == 'UTCHMMA' and op.startswith('UTCHMMA.2CTA')):
                 counts[cur][k] += 1
                 total[k] += 1
 print(f'{so}: {len(counts)} kernels; totals: ' + ', '.join(f'{k} {total[k]}' for k in keys))
