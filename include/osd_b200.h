@@ -189,6 +189,17 @@ OSD_API void osd_debug_attn_bwd_trace(unsigned long long* buf, int cta);
  * [682,128,1], .bias, proj_o.weight [128,341,1], .bias, blocks.j.1.gamma}; film = films.j(cond) [B,384] (scale | shift |
  * gate) or NULL for the unconditional layers. */
 OSD_API int osd_lat_block(const float* x, float* y, const float* const* w8, const float* film, int B, int L, void* stream);
+/* The same block with its two 1x1 convolutions (128 -> 682, 341 -> 128: 96 % of its FLOPs) as tcgen05 GEMMs on split-TF32
+ * operands (3xTF32: x = hi + lo with hi = tf32(x), hi*hi + lo*hi + hi*lo accumulated in fp32, ~1e-6 of the fp32 result) and the norms /
+ * FiLM / depthwise conv / SwiGLU as three streaming kernels; what LatentModel.audio_encoder / decode run by default
+ * (osd_lat_block stays as the exact-fp32 CUDA-core version).  `packed` = osd_lat_tc_pack_bytes() bytes written once per
+ * block by osd_lat_tc_pack from proj_vg.1.weight, proj_vg.1.bias and proj_o.weight; `ws` = osd_lat_tc_workspace_bytes(B, L)
+ * bytes of scratch.  Arguments otherwise as osd_lat_block. */
+OSD_API size_t osd_lat_tc_pack_bytes(void);
+OSD_API size_t osd_lat_tc_workspace_bytes(int B, int L);
+OSD_API int osd_lat_tc_pack(const float* w1, const float* b1, const float* w2, void* packed, void* stream);
+OSD_API int osd_lat_block_tc(const float* x, float* y, const float* const* w8, const void* packed, const float* film, void* ws,
+                             int B, int L, void* stream);
 /* rms_norm over dim 1 (common/rms_norm.py:7-16) with optional gamma [C] and optional SiLU (act = 1); N = product of the
  * trailing dims */
 OSD_API int osd_lat_rmsnorm(const float* x, const float* gamma, float* y, int B, int C, long long N, int act, void* stream);

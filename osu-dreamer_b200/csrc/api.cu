@@ -40,6 +40,15 @@ size_t osd_rope_table_floats(int L) { return rope_table_floats(L); }
 int osd_lat_block(const float* x, float* y, const float* const* w8, const float* film, int B, int L, void* stream) {
   return launch_lat_block(x, y, w8, film, B, L, static_cast<cudaStream_t>(stream));
 }
+size_t osd_lat_tc_pack_bytes(void) { return lat_tc_pack_bytes(); }
+size_t osd_lat_tc_workspace_bytes(int B, int L) { return lat_tc_workspace_bytes(B, L); }
+int osd_lat_tc_pack(const float* w1, const float* b1, const float* w2, void* packed, void* stream) {
+  return launch_lat_tc_pack(w1, b1, w2, packed, static_cast<cudaStream_t>(stream));
+}
+int osd_lat_block_tc(const float* x, float* y, const float* const* w8, const void* packed, const float* film, void* ws, int B,
+                     int L, void* stream) {
+  return launch_lat_block_tc(x, y, w8, packed, film, ws, B, L, static_cast<cudaStream_t>(stream));
+}
 int osd_lat_rmsnorm(const float* x, const float* gamma, float* y, int B, int C, long long N, int act, void* stream) {
   return launch_lat_rmsnorm(x, gamma, y, B, C, N, act, static_cast<cudaStream_t>(stream));
 }

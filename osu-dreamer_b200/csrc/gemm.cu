@@ -647,9 +647,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   OSD_CHECK(a.N % 32 == 0, "gemm: N=%d must be a multiple of 32", a.N);
   OSD_CHECK(a.epi != EPI_ATOMIC || a.c_fp32, "gemm: EPI_ATOMIC needs an fp32 output");
   OSD_CHECK(a.split_k <= 1 || a.epi == EPI_ATOMIC, "gemm: split-K needs EPI_ATOMIC");
-  OSD_CHECK(!a.split3 || (a.elem == ELEM_BF16 && a.a_major == MAJOR_K && a.b_major == MAJOR_K && a.K % 64 == 0 &&
+  OSD_CHECK(!a.split3 || (a.a_major == MAJOR_K && a.b_major == MAJOR_K && a.K % (a.elem == ELEM_BF16 ? 64 : 32) == 0 &&
                           a.split_k <= 1),
-            "gemm: split3 needs bf16 K-major operands with K %% 64 == 0");
+            "gemm: split3 needs K-major operands with K a multiple of the stage depth (64 bf16 / 32 tf32)");
   OSD_CHECK(!a.c_split || (!a.c_fp32 && a.epi != EPI_ATOMIC && a.N % 64 == 0), "gemm: c_split needs a bf16 store epilogue");
   const int align = a.c_fp32 ? 4 : 8;
   OSD_CHECK(a.ldc % align == 0, "gemm: ldc=%lld must be a multiple of %d", (long long)a.ldc, align);

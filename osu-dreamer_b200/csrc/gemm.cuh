@@ -26,8 +26,10 @@ struct GemmArgs {
   int c_fp32 = 0;
   const float* bias = nullptr;
   int split_k = 1;
-  // 3x-bf16 split precision ("fp32-grade" path): A is [M, 2K] = (hi | lo), B is [N, 2K] = (hi | lo), both K-major;
+  // 3x split precision ("fp32-grade" path): A is [M, 2K] = (hi | lo), B is [N, 2K] = (hi | lo), both K-major;
   // the kernel runs the three partial products A_hi B_hi + A_lo B_hi + A_hi B_lo as one 3K-long reduction.
+  // bf16 elements: hi = bf16(x), lo = bf16(x - hi), ~1e-5 of the fp32 product; tf32 elements (fp32 storage): hi = tf32(x),
+  // lo = x - hi (the tensor core reads its top 19 bits), ~1e-6 -- the latent blocks (latent_tc.cu).
   int split3 = 0;
   // bf16 outputs written as (hi | lo) pairs: C is [M, 2N], hi in columns [0,N), lo = bf16(x - hi) in [N,2N)
   int c_split = 0;

@@ -6,6 +6,12 @@ namespace osd {
 
 // latent model, inference half (latent.cu): fp32 channels-first building blocks
 int launch_lat_block(const float* x, float* y, const float* const* w8, const float* film, int B, int L, cudaStream_t s);
+// the same block with its two 1x1 convolutions on the tensor cores (latent_tc.cu): split-bf16 GEMMs + three streaming kernels
+size_t lat_tc_pack_bytes();
+size_t lat_tc_workspace_bytes(int B, int L);
+int launch_lat_tc_pack(const float* w1, const float* b1, const float* w2, void* packed, cudaStream_t s);
+int launch_lat_block_tc(const float* x, float* y, const float* const* w8, const void* packed, const float* film, void* ws,
+                        int B, int L, cudaStream_t s);
 int launch_lat_rmsnorm(const float* x, const float* gamma, float* y, int B, int C, long long N, int act, cudaStream_t s);
 int launch_lat_conv1x1(const float* x, const float* W, const float* bias, float* y, int B, int Cin, int Cout, long long N,
                        int act, int act_channels, cudaStream_t s);

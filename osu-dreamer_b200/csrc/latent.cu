@@ -254,9 +254,111 @@ __global__ void __launch_bounds__(128) lat_conv1x1_kernel(const float* __restric
     yb[(long long)o * N] = a;
   }
 }
+// The same product when there are only a few positions (N < 32: the Linear layers -- FiLM projections [B,32] -> 384, label
+// predictor): thread = one output (o, n) instead of one position, so a FiLM projection is 384 parallel 32-term sums and not one
+// thread walking all of them (0.45 ms each, 24 of them in `decode`).  Same bias-first ascending fmaf chain per output.
+__global__ void __launch_bounds__(128) lat_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                         const float* __restrict__ bias, float* __restrict__ y, int Cin, int Cout,
+                                                         int N, int act, int act_channels) {
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * 128 + threadIdx.x;
+  if (idx >= Cout * N) return;
+  const int o = idx / N, n = idx % N;
+  const float* xb = x + (long long)b * Cin * N + n;
+  const float* wr = W + (long long)o * Cin;
+  float a = bias ? bias[o] : 0.f;
+  for (int i = 0; i < Cin; ++i) a = fmaf(__ldg(wr + i), xb[(long long)i * N], a);
+  if (act == 1) a = a / (1.0f + expf(-a));
+  else if (act == 2 && o < act_channels) a = 1.0f / (1.0f + expf(-a));
+  y[(long long)b * Cout * N + (long long)o * N + n] = a;
+}
+
+// The same product for the wide cases (Cin a multiple of 4, Cout >= 32: the decoder's mixers and gates at up to 160 k tokens),
+// register-tiled like P4 of lat_block_kernel: block = 32 tokens, thread = 4 tokens x 4 output rows, 8 FMA per memory
+// instruction instead of 0.5.  Every output is still bias + one thread's fmaf chain over i in ascending order, i.e. the result
+// is bit-identical to the kernel above; outputs leave through shared memory so that the stores are 128-byte row segments.
+__global__ void __launch_bounds__(256) lat_conv1x1_tiled_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                                const float* __restrict__ bias, float* __restrict__ y, int Cin,
+                                                                int Cout, long long N, int act, int act_channels) {
+  extern __shared__ __align__(16) float xs[];  // [Cin][32], then reused as the output tile [128][33]
+  const int b = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xb = x + (long long)b * Cin * N;
+  for (int i = warp; i < Cin; i += 8) xs[i * 32 + lane] = (n0 + lane < N) ? xb[(long long)i * N + n0 + lane] : 0.f;
+  __syncthreads();
+  const int tq = threadIdx.x & 7, nr = threadIdx.x >> 3;
+  float* os = xs + Cin * 32;  // [128][33]
+  for (int o0 = 0; o0 < Cout; o0 += 128) {
+    float acc[4][4];
+    const float4* wr[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int o = min(o0 + 4 * nr + r, Cout - 1);  // rows past Cout - 1 are computed on a clamped row and not stored
+      wr[r] = reinterpret_cast<const float4*>(W + (long long)o * Cin);
+      const float bb = bias ? bias[o] : 0.f;
+      acc[r][0] = bb, acc[r][1] = bb, acc[r][2] = bb, acc[r][3] = bb;
+    }
+#pragma unroll 4
+    for (int c4 = 0; c4 < Cin / 4; ++c4) {
+      float4 wv[4], zv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) wv[r] = __ldg(wr[r] + c4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) zv[i] = *reinterpret_cast<const float4*>(xs + (4 * c4 + i) * 32 + 4 * tq);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float ww[4] = {wv[r].x, wv[r].y, wv[r].z, wv[r].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[r][0] = fmaf(ww[i], zv[i].x, acc[r][0]);
+          acc[r][1] = fmaf(ww[i], zv[i].y, acc[r][1]);
+          acc[r][2] = fmaf(ww[i], zv[i].z, acc[r][2]);
+          acc[r][3] = fmaf(ww[i], zv[i].w, acc[r][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int o = o0 + 4 * nr + r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = acc[r][j];
+        if (act == 1) a = a / (1.0f + expf(-a));
+        else if (act == 2 && o < act_channels) a = 1.0f / (1.0f + expf(-a));
+        os[(4 * nr + r) * 33 + 4 * tq + j] = a;
+      }
+    }
+    __syncthreads();
+    if (n0 + lane < N) {
+      float* yb = y + (long long)b * Cout * N + n0 + lane;
+      for (int r = warp; r < 128 && o0 + r < Cout; r += 8) yb[(long long)(o0 + r) * N] = os[r * 33 + lane];
+    }
+    __syncthreads();
+  }
+}
+
 int launch_lat_conv1x1(const float* x, const float* W, const float* bias, float* y, int B, int Cin, int Cout, long long N,
                        int act, int act_channels, cudaStream_t s) {
   OSD_CHECK(x && W && y && B > 0 && Cin > 0 && Cin <= 256 && Cout > 0 && N > 0, "lat_conv1x1: bad arguments");
+  if (N < 32) {
+    dim3 grid_l((unsigned)ceil_div(Cout * (int)N, 128), B);
+    lat_linear_kernel<<<grid_l, 128, 0, s>>>(x, W, bias, y, Cin, Cout, (int)N, act, act_channels);
+    OSD_LAUNCHED();
+    return 0;
+  }
+  if (Cin % 4 == 0 && Cout >= 32 && N >= 32 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+    const int smem_t = (Cin * 32 + 128 * 33) * 4;
+    static int max_set_t = 0;
+    if (smem_t > max_set_t) {
+      OSD_CUDA(cudaFuncSetAttribute(lat_conv1x1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t));
+      max_set_t = smem_t;
+    }
+    dim3 grid_t((unsigned)((N + 31) / 32), B);
+    lat_conv1x1_tiled_kernel<<<grid_t, 256, smem_t, s>>>(x, W, bias, y, Cin, Cout, N, act, act_channels);
+    OSD_LAUNCHED();
+    return 0;
+  }
   const int smem = Cin * 128 * 4;
   static int max_set = 0;
   if (smem > max_set) {

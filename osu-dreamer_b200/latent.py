@@ -147,6 +147,7 @@ class LatentModel(nn.Module):
         self.emb_dim, self.style_dim, self.a_dim = emb_dim, style_dim, args.h_dim
         self.n_downs, self.stride, self.n_layers = n_downs, stride, a.n_layers
         self.chunk_size = stride ** n_downs
+        self.block_impl = 'tc'  # 'fp32': the exact-fp32 CUDA-core block kernel (csrc/latent.cu)
         for name, shape, init in parameter_table(emb_dim, style_dim, n_downs, stride, args):
             _put(self, name, shape, init, {'audio_encoder': _AudioEncoder})
         object.__setattr__(self.audio_encoder, '_owner', (self,))  # not a submodule: no reference cycle in the module tree
@@ -158,14 +159,28 @@ class LatentModel(nn.Module):
             raise lib.OsdError('LatentModel parameters must be on a CUDA device: libosd_b200 has no CPU path')
         return {k: v.detach() for k, v in sd.items()}
 
+    def _packed(self, key: str, w1: Tensor, b1: Tensor, w2: Tensor) -> Tensor:
+        """the block's GEMM weights as (hi | lo) tf32 splits, re-packed when a parameter was replaced or written in place"""
+        cache = self.__dict__.setdefault('_tc_cache', {})
+        tag = tuple((t.data_ptr(), t._version) for t in (w1, b1, w2))
+        hit = cache.get(key)
+        if hit is None or hit[0] != tag:
+            hit = cache[key] = (tag, lib.lat_tc_pack(w1, b1, w2))
+        return hit[1]
+
     def _layer(self, sd, p: str, x: Tensor, cond: Tensor | None) -> Tensor:
-        """unet.py:40-55"""
+        """unet.py:40-55.  `block_impl`: 'tc' (default) = the two 1x1 convolutions as 3xTF32 tcgen05 GEMMs (split operands,
+        ~1e-6 of fp32), 'fp32' = the exact-fp32 CUDA-core kernel."""
+        ws = lib.lat_tc_workspace(x.shape[0], x.shape[2], x.device) if self.block_impl == 'tc' else None
         for j in range(self.n_layers):
             film = lib.lat_conv1x1(cond, sd[f'{p}.films.{j}.weight'], sd[f'{p}.films.{j}.bias']) if cond is not None else None
             b = f'{p}.blocks.{j}.0'
             w8 = [sd[f'{p}.norms.{j}.gamma'], sd[b + '.proj_vg.0.weight'], sd[b + '.proj_vg.0.bias'], sd[b + '.proj_vg.1.weight'],
                   sd[b + '.proj_vg.1.bias'], sd[b + '.proj_o.weight'], sd[b + '.proj_o.bias'], sd[f'{p}.blocks.{j}.1.gamma']]
-            x = lib.lat_block(x, w8, film)
+            if self.block_impl == 'tc':
+                x = lib.lat_block_tc(x, w8, self._packed(f'{p}.{j}', w8[3], w8[4], w8[5]), film, ws)
+            else:
+                x = lib.lat_block(x, w8, film)
         return lib.lat_rmsnorm(x, sd[f'{p}.out_norm.gamma'])
 
     @torch.no_grad()

@@ -370,6 +370,32 @@ def lat_block(x, w8, film=None):
     return y
 
 
+def lat_tc_pack(w1, b1, w2):
+    """(hi | lo) tf32-split copies of a block's two 1x1-conv weights + the padded bias, for lat_block_tc (written once per block)"""
+    lib_ = load()
+    lib_.osd_lat_tc_pack_bytes.restype = c_size_t
+    packed = torch.empty(int(lib_.osd_lat_tc_pack_bytes()), dtype=torch.uint8, device=w1.device)
+    _check(lib_.osd_lat_tc_pack(ptr(_f32(w1)), ptr(_f32(b1)), ptr(_f32(w2)), ptr(packed), stream()))
+    return packed
+
+
+def lat_tc_workspace(B, L, device):
+    return torch.empty(_sz('osd_lat_tc_workspace_bytes', B, L), dtype=torch.uint8, device=device)
+
+
+def lat_block_tc(x, w8, packed, film=None, ws=None):
+    """lat_block with its two 1x1 convolutions as 3xTF32 tcgen05 GEMMs (~1e-6 of fp32); same arguments + the packed weights"""
+    B, C, L = x.shape
+    y = torch.empty_like(x)
+    if ws is None:
+        ws = lat_tc_workspace(B, L, x.device)
+    keep = [_f32(t) for t in w8]
+    arr = (c_void_p * 8)(*[t.data_ptr() for t in keep])
+    _check(load().osd_lat_block_tc(ptr(_f32(x)), ptr(y), arr, ptr(packed), ptr(_f32(film)) if film is not None else c_void_p(0),
+                                   ptr(ws), c_int(B), c_int(L), stream()))
+    return y
+
+
 def lat_rmsnorm(x, gamma=None, silu=False):
     B, C = x.shape[0], x.shape[1]
     N = x.numel() // (B * C)
