@@ -349,10 +349,9 @@ int launch_lat_conv1x1(const float* x, const float* W, const float* bias, float*
   }
   if (Cin % 4 == 0 && Cout >= 32 && N >= 32 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
     const int smem_t = (Cin * 32 + 128 * 33) * 4;
-    static int max_set_t = 0;
-    if (smem_t > max_set_t) {
-      OSD_CUDA(cudaFuncSetAttribute(lat_conv1x1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t));
-      max_set_t = smem_t;
+    static DeviceOnce once_t;  // per device; sized for the largest Cin accepted above
+    if (once_t.first()) {
+      OSD_CUDA(cudaFuncSetAttribute(lat_conv1x1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 32 + 128 * 33) * 4));
     }
     dim3 grid_t((unsigned)((N + 31) / 32), B);
     lat_conv1x1_tiled_kernel<<<grid_t, 256, smem_t, s>>>(x, W, bias, y, Cin, Cout, N, act, act_channels);
@@ -360,10 +359,9 @@ int launch_lat_conv1x1(const float* x, const float* W, const float* bias, float*
     return 0;
   }
   const int smem = Cin * 128 * 4;
-  static int max_set = 0;
-  if (smem > max_set) {
-    OSD_CUDA(cudaFuncSetAttribute(lat_conv1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    max_set = smem;
+  static DeviceOnce once;
+  if (once.first()) {
+    OSD_CUDA(cudaFuncSetAttribute(lat_conv1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 128 * 4));
   }
   dim3 grid((unsigned)((N + 127) / 128), B);
   lat_conv1x1_kernel<<<grid, 128, smem, s>>>(x, W, bias, y, Cin, Cout, N, act, act_channels);
