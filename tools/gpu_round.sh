@@ -20,3 +20,10 @@ tail -4 gpurun_out/${TAG}_seq_sweep.log | cut -c1-300
 python tools/predict_latency.py 4 4 8 2>&1 | tail -1; cp gpurun_out/predict_latency.json gpurun_out/${TAG}_predict_latency_8steps.json
 python tools/predict_latency.py 4 4 64 2>&1 | tail -1; cp gpurun_out/predict_latency.json gpurun_out/${TAG}_predict_latency_64steps.json
 ls -la gpurun_out | tail -14
+# sanitizers over the kernels added late in the round (time-boxed)
+for tool in memcheck racecheck; do
+  log=gpurun_out/${TAG}_sanitizer_${tool}_new.log
+  OSD_GEMM_PAIR=1 timeout 400 compute-sanitizer --tool $tool --print-limit 30 --launch-timeout 120 python tools/sanitize_target.py new > $log 2>&1
+  echo "rc=$?" >> $log
+  echo "== $tool new: $(grep 'ERROR SUMMARY\|RACECHECK SUMMARY' $log | tail -1) $(tail -1 $log)"
+done
