@@ -111,10 +111,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_cons
     }
   }
   tc_fence_before();
-  if constexpr (PAIR)
-    cluster_sync_all();  // the peer's barriers are initialised before anything signals them
-  else
-    __syncthreads();
+  __syncthreads();  // (also in PAIR mode: compute-sanitizer's racecheck does not model barrier.cluster as a CTA barrier and
+                    //  reports the TMEM allocator's shared-memory write against the read below)
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
