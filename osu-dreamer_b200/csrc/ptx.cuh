@@ -196,8 +196,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t cta
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
   return r;
 }
+// Default semantics (release at CTA scope), NOT .release.cluster: the cluster-scope release compiles to MEMBAR.ALL.GPU + ERRBAR
+// in front of the arrive and waits for every outstanding load / bulk store of the thread -- a third of the K = 512 pair GEMM's
+// stall samples sat there (profiles/r02final2_gemm_ncu_summary.json).  What this arrive orders is TMEM traffic (the epilogue's
+// tcgen05.ld before the leader's next MMA), and that is carried by tcgen05.wait::ld + tcgen05.fence::before_thread_sync on
+// this side and tcgen05.fence::after_thread_sync behind the leader's wait.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // bar_cluster_addr: the LEADER's full barrier (mapa_shared(addr, 0)); the destination is this CTA's own shared memory
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
