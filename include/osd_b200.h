@@ -71,6 +71,9 @@ OSD_API unsigned long long osd_launch_count(void);
 /* C[M,N] (+)= A * B^T on tcgen05.  major 0: operand is [rows, K] row-major (K contiguous);
  * major 1: operand is [K, rows] row-major (rows contiguous).  elem: OSD_BF16 / OSD_TF32.
  * epi: 0 store(acc+bias), 1 silu(acc+bias), 2 atomic add into fp32 C (split_k >= 1).
+ * bf16 problems with K >= 512 and enough [256 x 256] tiles run on CTA pairs (tcgen05 ... cta_group::2, M = 256 over a
+ * 2-CTA cluster, half of the B tile staged per CTA); the environment variable OSD_GEMM_PAIR=0 / 1 switches that off / forces it
+ * for every eligible shape (A/B measurements).
  * Replaces the reference's 1x1 Conv1d / Linear call sites. */
 OSD_API int osd_gemm(const void* A, int a_major, int64_t lda, const void* B, int b_major, int64_t ldb, void* C,
              int64_t ldc, int c_fp32, const float* bias, int M, int N, int K, int elem, int epi, int split_k,
