@@ -489,7 +489,7 @@ def run_cuda(args):
             y, lse = lib.attn_fwd(qkv, Ba, L)
             dy = torch.randn(Ba * L, 1024, device=dev).to(torch.bfloat16)
             bound = torch.tensor([14.0], device=dev)  # randn scores / 8 stay far below 2^14: same kernel path the model runs
-            ms_f = time_kernel(lambda: lib.attn_fwd(qkv, Ba, L, bound_log2=bound, variant=18), iters=3, warm=1)  # the model's variant at L >= 6144
+            ms_f = time_kernel(lambda: lib.attn_fwd(qkv, Ba, L, bound_log2=bound, variant=18), iters=3, warm=1)  # the model's variant at L >= 5120
             ms_b = time_kernel(lambda: lib.attn_bwd_fused(qkv, y, dy, lse, Ba, L), iters=3, warm=1)
             fl_f = 4.0 * Ba * 16 * L * L * 64
             kern = {'attn_fwd': {'ms': ms_f, 'tflops': fl_f / ms_f / 1e9},

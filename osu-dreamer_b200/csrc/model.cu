@@ -161,14 +161,15 @@ static int proj_cl(const float* const* P, const PackedW& W, int mode, int l, con
 // forward attention kernel of the model; OSD_ATTN_FWD=<n> forces one variant for A/B measurements.  Long sequences run the
 // one-CTA-per-SM kernel with two q tiles and sixteen softmax warps (variant 18, attn_fwd_pp3.cu: -4 % kernel time at L = 8192,
 // +3.7 % sampling throughput, profiles/r02x_*); shorter ones the two-CTA-per-SM kernel (variant 7, attn_fwd_db.cu), whose
-// smaller CTAs balance better when there are few of them (L <= 4096: 3-6 % faster there).
+// smaller CTAs balance better when there are few of them (tools/attn_fwd_threshold.py at 131 k tokens: variant 18 / 7 = 1.09 at
+// L = 1024, 1.04 at 2048, 0.99 at 3072-4096, 0.97 from 5120 up).
 static int attn_fwd_variant(int L) {
   static const int forced = [] {
     const char* e = getenv("OSD_ATTN_FWD");
     return (e != nullptr && e[0] >= '0' && e[0] <= '9') ? atoi(e) : -1;
   }();
   if (forced >= 0) return forced;
-  return L >= 6144 ? 18 : 7;
+  return L >= 5120 ? 18 : 7;
 }
 
 // OSD_X3_KERNEL=old selects the single-buffered fp32-grade attention kernel (attn_fwd_x3.cu, selectable terms) for A/B
