@@ -2,8 +2,11 @@
 //   warp 0      : TMA producer (one elected lane)
 //   warp 1      : TMEM allocator + UMMA issuer (one elected lane)
 //   warps 2..5  : epilogue (TMEM -> registers -> fused epilogue -> global), lane quadrant = warp % 4
+//                 (warps 2..9 = two per quadrant where the main loop is short, EW = 8)
 // Pipelines: smem full/empty ring (TMA <-> UMMA) and a 2-deep TMEM accumulator ring (UMMA <-> epilogue),
 // so the epilogue of work item i overlaps the main loop of item i+1.
+// PAIR instantiation: the same roles in both CTAs of a 2-CTA cluster, one tcgen05.mma.cta_group::2 (M = 256) issued by the
+// leader over both CTAs' shared memory and TMEM; see Cfg and the helpers under "CTA pairs" in ptx.cuh.
 #include "gemm.cuh"
 #include "ptx.cuh"
 
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_kernel(const __grid_cons
       }
     }
   } else {
-    // ================================================================== epilogue (4 warps)
+    // ================================================================== epilogue (EW warps)
     // Each warp owns 32 accumulator rows.  Output leaves in 128-byte row segments (64 bf16 or 32 fp32 columns):
     // the thread writes its segment into a swizzled [32 x 128 B] staging tile, one lane issues a TMA tensor
     // store (or a TMA reduce-add for split-K / gradient accumulation).  Full-line, coalesced writes; rows past
