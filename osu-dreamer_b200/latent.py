@@ -171,6 +171,8 @@ class LatentModel(nn.Module):
     def _layer(self, sd, p: str, x: Tensor, cond: Tensor | None) -> Tensor:
         """unet.py:40-55.  `block_impl`: 'tc' (default) = the two 1x1 convolutions as 3xTF32 tcgen05 GEMMs (split operands,
         ~1e-6 of fp32), 'fp32' = the exact-fp32 CUDA-core kernel."""
+        if self.block_impl not in ('tc', 'fp32'):
+            raise lib.OsdError(f"LatentModel.block_impl must be 'tc' or 'fp32', not {self.block_impl!r}")
         ws = lib.lat_tc_workspace(x.shape[0], x.shape[2], x.device) if self.block_impl == 'tc' else None
         for j in range(self.n_layers):
             film = lib.lat_conv1x1(cond, sd[f'{p}.films.{j}.weight'], sd[f'{p}.films.{j}.bias']) if cond is not None else None
