@@ -666,9 +666,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     if (a.elem == ELEM_BF16) return launch_cfg<256, ELEM_BF16, true, 8>(a, stream);
     return launch_cfg<256, ELEM_TF32, true, 4>(a, stream);
   }
-  // narrow tiles when the wide ones cannot fill the machine or N is not a multiple of 256
+  // narrow tiles when the wide ones cannot fill the machine or would be more than an eighth padding (wide_n)
   const int wide_items = ceil_div(a.M, BM) * ceil_div(a.N, 256) * (a.split_k < 1 ? 1 : a.split_k);
-  const bool narrow = !(a.elem == ELEM_BF16 ? wide_n(a.N) : a.N % 256 == 0) || wide_items < num_sms();
+  const bool narrow = !wide_n(a.N) || wide_items < num_sms();
   // k-blocks per work item: short main loops cannot hide a 4-warp epilogue (OSD_GEMM_EW=4 forces the old layout)
   static const bool ew4_only = [] {
     const char* e = getenv("OSD_GEMM_EW");
